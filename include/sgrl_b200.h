@@ -1,0 +1,134 @@
+/* sgrl_b200 — C ABI of the B200-native SET (subequivariant transformer) hot path.
+ *
+ * The reference (alpc91/SGRL) has no FFI layer: its hot path sits behind Python nn.Module
+ * objects.  Each entry point below names the reference code it replaces (file:line relative
+ * to the reference's src/).  The Python modules in sgrl_b200/ (same class names, constructor
+ * signatures, state_dict keys as the reference) bind these with ctypes; INTEGRATION.md shows
+ * the stub a reference maintainer would add.
+ *
+ * Conventions: every pointer is a DEVICE pointer to contiguous row-major fp32 (int32 for
+ * indices) owned by the caller; the library allocates nothing, never synchronises and never
+ * throws.  Every call enqueues work on the given cudaStream_t (pass
+ * torch.cuda.current_stream().cuda_stream) and returns 0, or a negative code with a
+ * thread-local message in sgrl_last_error().  Calls are re-entrant per stream.
+ * Tokens are packed limb-major per graph: token t = limb (t - cu_limbs[g]) of graph g.
+ */
+#ifndef SGRL_B200_H
+#define SGRL_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* sgrl_stream_t; /* cudaStream_t */
+
+enum { SGRL_ACTOR = 0, SGRL_CRITIC = 1 };
+
+int sgrl_version(void);
+const char* sgrl_last_error(void);
+
+/* ---- layouts ------------------------------------------------------------------------
+ * One "net" = one reference TransformerModel (SEActor.py:170-287).  A module's arena holds
+ * nb nets: [live net0 | live net1 | .. | dead net0 | ..]; tensor i of net z lives at
+ * z*live_floats + offset (live) or nb*live_floats + z*dead_floats + offset (dead =
+ * nn.MultiheadAttention leftovers kept only for state_dict compatibility, SEActor.py:34-36). */
+int sgrl_param_count(int kind, int n_layers);
+int sgrl_param_info(int kind, int n_layers, int index, char* name, int name_cap,
+                    int* rows, int* cols /*0 => 1-D*/, int64_t* offset, int* live);
+int sgrl_arena_floats(int kind, int n_layers, int64_t* live_floats, int64_t* dead_floats);
+/* floats of forward stash per net instance for T tokens (keep=1: training, every layer kept;
+ * keep=0: rollout, layers alias) and of backward workspace */
+int64_t sgrl_stash_floats(int kind, int n_layers, int64_t T, int keep);
+int64_t sgrl_ws_floats(int64_t T);
+/* offset (floats) and floats-per-token of a named stash buffer (layer<0: global buffer); for tests */
+int sgrl_stash_info(int kind, int n_layers, int64_t T, int keep, const char* name, int layer,
+                    int64_t* offset, int* per_token);
+
+/* ---- whole-network passes -------------------------------------------------------------- */
+typedef struct {
+  int32_t kind;        /* SGRL_ACTOR: TransformerModel(41 -> 3), SGRL_CRITIC: (44 -> 1) */
+  int32_t n_layers;    /* attention_layers (3) */
+  int32_t nb;          /* nets evaluated together on the same input (2 = twin critics) */
+  int32_t T;           /* limb-tokens in the packed batch */
+  int32_t G;           /* graphs (samples) in the batch */
+  int32_t keep;        /* 1: keep every layer's activations for backward */
+  int32_t use_tc;      /* 1: tcgen05 tensor-core projections (3xTF32), 0: fp32 SIMT */
+  int32_t reserved;
+  const float* params; /* live arena of the module (nb * live_floats) */
+  float* grads;        /* gradient arena, same layout; may be NULL for forward / data-only backward */
+  float* stash;        /* nb * stash_stride floats */
+  int64_t stash_stride;
+  float* ws;           /* nb * ws_stride floats (backward only) */
+  int64_t ws_stride;
+  const int32_t* cu_limbs; /* (G+1) token offsets of the graphs */
+  const int32_t* rel_off;  /* (G) float offset of each graph's (n,n,3) relation table, NULL = all 0 */
+  const float* relation;   /* packed relation tables, utils.py:476-481 */
+  const int32_t* rank3;    /* (T,3) traversal ranks of each token's limb, utils.py:368-409 */
+  float max_action;
+  float pad_;
+} SgrlNetCall;
+
+/* SEPolicy.forward (SEActor.py:334-347) / SECritic.forward, Q1 (SECritic.py:66-104), all of
+ * TransformerModel.forward (SEActor.py:237-287), MyTransformerEncoderLayer.forward (:82-125)
+ * and multi_head_attention_forward (subequivariant_attentions.py:82-154).
+ * obs (T,41); act (T,3) for critics (NULL for actors); obs_stride/act_stride = floats between
+ * the inputs of consecutive nets (0: shared).  out: nb x (T x 3) tanh-squashed actions scaled by
+ * max_action, or nb x (T x 1) per-limb Q. */
+int sgrl_set_forward(const SgrlNetCall* call, const float* obs, int64_t obs_stride, const float* act,
+                     int64_t act_stride, float* out, int64_t out_stride, sgrl_stream_t stream);
+
+/* loss.backward() through the same modules (agent.py:151,171).  dout: nb x (T x 3|1) gradient
+ * w.r.t. `out`.  need_wgrad=1 accumulates parameter gradients into call->grads (zero it first);
+ * dact (critics, nullable): nb x (T x 3) gradient w.r.t. the action input (agent.py:167). */
+int sgrl_set_backward(const SgrlNetCall* call, const float* dout, int64_t dout_stride, int need_wgrad,
+                      float* dact, int64_t dact_stride, sgrl_stream_t stream);
+
+/* ---- single kernels (unit tests, profiling) ---------------------------------------------- */
+/* K1: Z=[X P^T | gd], G=Z^T Z, F=||G||+1 (subequivariant_attentions.py:90-96; SEActor.py:93-100,
+ * 256-262).  X (T,3,128); v0 (T,3,8) or NULL (head variant, C=136); P1,P2 (30,C) (P2/Z2 NULL for
+ * one projection); outputs Z,Z2 (T,3,32), G (T,1024), F (T). */
+int sgrl_inv_feature_fwd(const float* X, const float* v0, const float* gd, const float* P1, const float* P2,
+                         float* Z, float* Z2, float* G, float* F, int T, sgrl_stream_t stream);
+int sgrl_inv_feature_bwd(const float* dG, const float* dF, const float* Z, const float* F, float* dZ, int T,
+                         sgrl_stream_t stream);
+/* K2: attention core (subequivariant_attentions.py:109-151) on packed graphs.  qkv (T,768) holds
+ * the already /F-divided and scaled q|k|v; vgp (T,3,252); gd (T,3,2); rel_w (2,3), rel_b (2) or NULL.
+ * Outputs o (T,256), og (T,3,256), p (T,2,16). */
+int sgrl_attention_fwd(const float* qkv, const float* vgp, const float* gd, const float* rel_w, const float* rel_b,
+                       const int32_t* cu_limbs, const int32_t* rel_off, const float* relation, int G,
+                       float* o, float* og, float* p, sgrl_stream_t stream);
+int sgrl_attention_bwd(const float* qkv, const float* vgp, const float* gd, const float* p,
+                       const float* d_o, const float* d_og, const int32_t* cu_limbs, const int32_t* rel_off,
+                       const float* relation, int G, float* dqkv, float* dvgp, float* drel_w /*nullable, accumulates*/,
+                       sgrl_stream_t stream);
+/* K3: C[M,N] = epi(alpha * A B^T): every nn.Linear call site.
+ * trans_a/trans_b as in csrc/gemm_simt.cuh; bias/rowdiv nullable; relu 0/1; use_tc as above. */
+int sgrl_gemm(const float* A, int lda, int trans_a, const float* B, int ldb, int trans_b, float* C, int ldc,
+              int M, int N, int K, float alpha, const float* bias, const float* rowdiv, int relu, int accumulate,
+              int splitk, int use_tc, sgrl_stream_t stream);
+
+/* ---- K5: TD3 glue (agent.py:127-148,167) -------------------------------------------------- */
+int sgrl_td3_smooth_action(const float* pi_target, const float* noise, float* next_action, float noise_clip,
+                           float max_action, int64_t n, sgrl_stream_t stream);
+/* target = r*scale + (1-done)*discount*min(tq1,tq2) broadcast over limbs; loss (1 float, accumulates)
+ * = mse(q1,target)+mse(q2,target); dq1,dq2 = dloss/dq. tok_graph (T) maps token -> sample. */
+int sgrl_td3_critic_loss(const float* q1, const float* q2, const float* tq1, const float* tq2, const float* reward,
+                         const float* done, const int32_t* tok_graph, float* target, float* dq1, float* dq2,
+                         float* loss, float discount, float reward_scale, int T, sgrl_stream_t stream);
+int sgrl_td3_actor_loss(const float* q1, float* dq1, float* loss, int T, sgrl_stream_t stream);
+
+/* ---- K6: optimizer (agent.py:150-156,170-178; common/functional.py:7-10) -------------------- */
+int sgrl_sumsq(const float* g, int64_t n, float* out /*accumulates*/, sgrl_stream_t stream);
+/* clip_grad_norm_(max_norm) + Adam(lr,b1,b2,eps) in one pass over the flat live arena.  sumsq: device
+ * scalar with sum(g^2) (after the all-reduce); step: device int, the 1-based step count to apply;
+ * grad_scale multiplies g first (1/world_size). */
+int sgrl_adam_clip(float* p, const float* g, float* m, float* v, int64_t n, const float* sumsq, const int32_t* step,
+                   float lr, float beta1, float beta2, float eps, float max_norm, float grad_scale, sgrl_stream_t stream);
+int sgrl_bump_step(int32_t* step, sgrl_stream_t stream);
+int sgrl_polyak(float* target, const float* source, int64_t n, float tau, sgrl_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,300 @@
+// K2 — masked multi-head SET attention over packed variable-size limb graphs
+// (subequivariant_attentions.py:109-151).  H=2 heads of width 128, <= 16 limbs per graph.
+//
+// One CTA (a warp-group of 4 warps forward, 8 warps backward) per graph: the graph's
+// q|k|v rows and its vector-stream values [vg_proj(Vg) | gravity | direction] are staged in
+// shared memory once, scores for both heads are formed there, the softmax over the
+// graph's own limbs runs on 16-lane shuffle groups (padding never enters: each graph
+// only ever sees its cu_limbs[g]..cu_limbs[g+1] rows, which is what "masking padded keys
+// with -inf" reduces to for a packed layout), and the same probabilities weight the
+// scalar values (-> o, T x 256) and the three spatial rows of the vector values
+// (-> og, T x 3 x 256).  Layer 0 adds the relational bias W_rel . relation[i][j] + b_rel
+// (SEActor.py:156-158) computed on the fly from the per-morphology relation table.
+#pragma once
+#include "common.cuh"
+#include "layout.h"
+
+namespace sgrl {
+
+constexpr int A_RS = 772;       // padded smem row stride for 768-float rows (bank offset 4/row)
+constexpr int A_DS = 1028;      // padded stride for do|dog rows (256+768)
+constexpr int A_FWD_THREADS = 128;
+constexpr int A_BWD_THREADS = 256;
+
+struct AttnGraphs {
+  const int* cu_limbs;    // (G+1) token offsets
+  const int* rel_off;     // (G) float offset of each graph's (n,n,3) relation table, or nullptr (all 0)
+  const float* relation;  // packed relation tables
+  int G;
+};
+
+__device__ __forceinline__ void attn_stage_common(float* qs, float* vs, const float* __restrict__ QKV,
+                                                  const float* __restrict__ VGP, const float* __restrict__ GD,
+                                                  int t0, int n, int tid, int nthr) {
+  for (int i = tid; i < n * 192; i += nthr) {
+    const int tk = i / 192, c4 = (i % 192) * 4;
+    *reinterpret_cast<float4*>(qs + tk * A_RS + c4) = ldg4(QKV + (long long)(t0 + tk) * 768 + c4);
+  }
+  // vg rows: (t, r, h) -> 126 learned channels, 8-byte aligned
+  for (int i = tid; i < n * 6 * 63; i += nthr) {
+    const int c2 = i % 63, rh = (i / 63) % 6, tk = i / (63 * 6);
+    const int r = rh >> 1, h = rh & 1;
+    const float2 v = __ldg(reinterpret_cast<const float2*>(VGP + (long long)(t0 + tk) * 756 + r * 252 + h * 126) + c2);
+    *reinterpret_cast<float2*>(vs + tk * A_RS + r * 256 + h * 128 + c2 * 2) = v;
+  }
+  for (int i = tid; i < n * 6; i += nthr) {
+    const int tk = i / 6, r = (i % 6) >> 1, k = i & 1;
+    const float v = __ldg(GD + (long long)(t0 + tk) * 6 + (i % 6));
+    vs[tk * A_RS + r * 256 + 126 + k] = v;
+    vs[tk * A_RS + r * 256 + 128 + 126 + k] = v;
+  }
+}
+
+__global__ void __launch_bounds__(A_FWD_THREADS) attention_fwd_kernel(
+    const float* __restrict__ QKV, const float* __restrict__ VGP, const float* __restrict__ GD,
+    float* __restrict__ O, float* __restrict__ OG, float* __restrict__ P, long long zsS,
+    const float* __restrict__ Wrel, const float* __restrict__ brel, long long zsP,   // nullptr unless layer 0
+    AttnGraphs gr) {
+  extern __shared__ __align__(16) float smem[];
+  float* qs = smem;                     // [MAXN][A_RS]   q | k | v
+  float* vs = qs + MAXN * A_RS;         // [MAXN][A_RS]   vgx: [r][h][128]
+  float* S = vs + MAXN * A_RS;          // [2][16][16]
+  const int tid = threadIdx.x, z = blockIdx.y;
+  QKV += z * zsS; VGP += z * zsS; GD += z * zsS; O += z * zsS; OG += z * zsS; P += z * zsS;
+  float wr[HEADS][3] = {{0, 0, 0}, {0, 0, 0}}, br[HEADS] = {0, 0};
+  const bool has_bias = Wrel != nullptr;
+  if (has_bias) {
+    Wrel += z * zsP; brel += z * zsP;
+#pragma unroll
+    for (int h = 0; h < HEADS; ++h) { br[h] = brel[h]; for (int c = 0; c < 3; ++c) wr[h][c] = Wrel[h * 3 + c]; }
+  }
+  for (int g = blockIdx.x; g < gr.G; g += gridDim.x) {
+    const int t0 = gr.cu_limbs[g], n = gr.cu_limbs[g + 1] - t0;
+    const float* rel = has_bias ? gr.relation + (gr.rel_off ? gr.rel_off[g] : 0) : nullptr;
+    __syncthreads();
+    attn_stage_common(qs, vs, QKV, VGP, GD, t0, n, tid, A_FWD_THREADS);
+    __syncthreads();
+    // ---- scores S[h][i][j] = q_i . k_j (+ bias)
+    for (int idx = tid; idx < HEADS * n * n; idx += A_FWD_THREADS) {
+      const int h = idx / (n * n), ij = idx % (n * n), i = ij / n, j = ij % n;
+      const float* q = qs + i * A_RS + h * 128;
+      const float* k = qs + j * A_RS + 256 + h * 128;
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 8
+      for (int c = 0; c < 128; c += 4) {
+        const float4 qv = *reinterpret_cast<const float4*>(q + c), kv = *reinterpret_cast<const float4*>(k + c);
+        a0 = fmaf(qv.x, kv.x, a0); a1 = fmaf(qv.y, kv.y, a1); a2 = fmaf(qv.z, kv.z, a2); a3 = fmaf(qv.w, kv.w, a3);
+      }
+      float s = (a0 + a1) + (a2 + a3);
+      if (has_bias) {
+        const float* rr = rel + (i * n + j) * 3;
+        s += wr[h][0] * rr[0] + wr[h][1] * rr[1] + wr[h][2] * rr[2] + br[h];
+      }
+      S[(h * 16 + i) * 16 + j] = s;
+    }
+    __syncthreads();
+    // ---- softmax over the graph's own limbs: 16-lane shuffle groups, one row each
+    for (int row = tid >> 4; row < HEADS * 16; row += A_FWD_THREADS / 16) {
+      const int h = row >> 4, i = row & 15, j = tid & 15;
+      const bool valid = (i < n) && (j < n);          // uniform per 16-lane group in i
+      float v = valid ? S[row * 16 + j] : -INFINITY;
+      float m = v;
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o, 16));
+      float e = valid ? expf(v - m) : 0.f;
+      float sum = e;
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o, 16);
+      const float p = valid ? e / sum : 0.f;
+      S[row * 16 + j] = p;
+      if (i < n) P[(long long)(t0 + i) * 32 + h * 16 + j] = p;
+    }
+    __syncthreads();
+    // ---- weighted sums: thread = output column; 256 scalar-stream + 768 vector-stream columns
+    for (int col = tid; col < 1024; col += A_FWD_THREADS) {
+      const bool sc = col < 256;
+      const int cc = sc ? col : col - 256;
+      const int h = (cc & 255) >> 7;
+      const float* src = sc ? qs + 512 + cc : vs + cc;
+      const float* Ph = S + h * 256;
+      float acc[MAXN];
+#pragma unroll
+      for (int i = 0; i < MAXN; ++i) acc[i] = 0.f;
+      for (int j = 0; j < n; ++j) {
+        const float vv = src[j * A_RS];
+#pragma unroll
+        for (int i = 0; i < MAXN; ++i) acc[i] = fmaf(Ph[i * 16 + j], vv, acc[i]);   // rows i>=n hold p=0
+      }
+#pragma unroll
+      for (int i = 0; i < MAXN; ++i)
+        if (i < n) {
+          if (sc) O[(long long)(t0 + i) * 256 + cc] = acc[i];
+          else OG[(long long)(t0 + i) * 768 + cc] = acc[i];
+        }
+    }
+  }
+}
+
+constexpr size_t attn_fwd_smem() { return sizeof(float) * (2 * MAXN * A_RS + 512); }
+constexpr size_t attn_bwd_smem() { return sizeof(float) * (2 * MAXN * A_RS + MAXN * A_DS + 1024 + 16); }
+
+// Backward.  Inputs dO (T,256), dOG (T,768) [workspace], saved P, QKV, VGP, GD [stash].
+// Outputs dQKV (T,768) — gradient w.r.t. the *stored* (post /F, post-scale) q|k|v — and
+// dVGP (T,756); layer 0 also accumulates d rel_encoder.weight (bias gradient is exactly 0).
+__global__ void __launch_bounds__(A_BWD_THREADS) attention_bwd_kernel(
+    const float* __restrict__ QKV, const float* __restrict__ VGP, const float* __restrict__ GD, const float* __restrict__ P, long long zsS,
+    const float* __restrict__ dO, const float* __restrict__ dOG, float* __restrict__ dQKV, float* __restrict__ dVGP, long long zsW,
+    float* __restrict__ dWrel, long long zsG, AttnGraphs gr) {
+  extern __shared__ __align__(16) float smem[];
+  float* qs = smem;
+  float* vs = qs + MAXN * A_RS;
+  float* ds = vs + MAXN * A_RS;          // [MAXN][A_DS]  dO | dOG
+  float* Ps = ds + MAXN * A_DS;          // [2][16][16]
+  float* dS = Ps + 512;                  // [2][16][16]
+  float* wacc = dS + 512;                // [6]
+  const int tid = threadIdx.x, z = blockIdx.y;
+  QKV += z * zsS; VGP += z * zsS; GD += z * zsS; P += z * zsS;
+  dO += z * zsW; dOG += z * zsW; dQKV += z * zsW; dVGP += z * zsW;
+  const bool has_bias = dWrel != nullptr;
+  if (has_bias) dWrel += z * zsG;
+  float wloc[6] = {0, 0, 0, 0, 0, 0};
+  for (int g = blockIdx.x; g < gr.G; g += gridDim.x) {
+    const int t0 = gr.cu_limbs[g], n = gr.cu_limbs[g + 1] - t0;
+    const float* rel = has_bias ? gr.relation + (gr.rel_off ? gr.rel_off[g] : 0) : nullptr;
+    __syncthreads();
+    attn_stage_common(qs, vs, QKV, VGP, GD, t0, n, tid, A_BWD_THREADS);
+    for (int i = tid; i < n * 256; i += A_BWD_THREADS) {
+      const int tk = i >> 8, c4 = (i & 255) * 4;
+      const float4 v = c4 < 256 ? ldg4(dO + (long long)(t0 + tk) * 256 + c4) : ldg4(dOG + (long long)(t0 + tk) * 768 + (c4 - 256));
+      *reinterpret_cast<float4*>(ds + tk * A_DS + c4) = v;
+    }
+    for (int i = tid; i < 512; i += A_BWD_THREADS) {
+      const int h = i >> 8, ii = (i >> 4) & 15, j = i & 15;
+      Ps[i] = (ii < n) ? __ldg(P + (long long)(t0 + ii) * 32 + h * 16 + j) : 0.f;
+    }
+    __syncthreads();
+    // ---- dP[h][i][j] = dO_i . v_j + sum_r dOG_i,r . vgx_j,r
+    for (int idx = tid; idx < HEADS * n * n; idx += A_BWD_THREADS) {
+      const int h = idx / (n * n), ij = idx % (n * n), i = ij / n, j = ij % n;
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      const float* d0 = ds + i * A_DS + h * 128;
+      const float* v0 = qs + j * A_RS + 512 + h * 128;
+#pragma unroll 8
+      for (int c = 0; c < 128; c += 4) {
+        const float4 a = *reinterpret_cast<const float4*>(d0 + c), b = *reinterpret_cast<const float4*>(v0 + c);
+        a0 = fmaf(a.x, b.x, a0); a1 = fmaf(a.y, b.y, a1); a2 = fmaf(a.z, b.z, a2); a3 = fmaf(a.w, b.w, a3);
+      }
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        const float* d1 = ds + i * A_DS + 256 + r * 256 + h * 128;
+        const float* v1 = vs + j * A_RS + r * 256 + h * 128;
+#pragma unroll 8
+        for (int c = 0; c < 128; c += 4) {
+          const float4 a = *reinterpret_cast<const float4*>(d1 + c), b = *reinterpret_cast<const float4*>(v1 + c);
+          a0 = fmaf(a.x, b.x, a0); a1 = fmaf(a.y, b.y, a1); a2 = fmaf(a.z, b.z, a2); a3 = fmaf(a.w, b.w, a3);
+        }
+      }
+      dS[(h * 16 + i) * 16 + j] = (a0 + a1) + (a2 + a3);
+    }
+    __syncthreads();
+    // ---- dS = P * (dP - sum_j dP*P), 16-lane groups per row
+    for (int row = tid >> 4; row < HEADS * 16; row += A_BWD_THREADS / 16) {
+      const int i = row & 15, j = tid & 15;
+      const bool valid = (i < n) && (j < n);
+      const float p = valid ? Ps[row * 16 + j] : 0.f;
+      const float dp = valid ? dS[row * 16 + j] : 0.f;
+      float s = p * dp;
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o, 16);
+      const float v = p * (dp - s);
+      dS[row * 16 + j] = v;
+      if (has_bias && valid) {
+        const int h = row >> 4;
+        const float* rr = rel + (i * n + j) * 3;
+        wloc[h * 3 + 0] = fmaf(v, rr[0], wloc[h * 3 + 0]);
+        wloc[h * 3 + 1] = fmaf(v, rr[1], wloc[h * 3 + 1]);
+        wloc[h * 3 + 2] = fmaf(v, rr[2], wloc[h * 3 + 2]);
+      }
+    }
+    __syncthreads();
+    // ---- column sweeps: 256 dq + 256 dk + 256 dv + 768 dvg columns
+    for (int task = tid; task < 1536; task += A_BWD_THREADS) {
+      const int kind = task < 768 ? task >> 8 : 3;
+      const int col = kind < 3 ? (task & 255) : task - 768;
+      const int h = (col & 255) >> 7;
+      float acc[MAXN];
+#pragma unroll
+      for (int i = 0; i < MAXN; ++i) acc[i] = 0.f;
+      if (kind == 0) {            // dq_i = sum_j dS[i][j] k_j
+        for (int j = 0; j < n; ++j) {
+          const float kv = qs[j * A_RS + 256 + col];
+#pragma unroll
+          for (int i = 0; i < MAXN; ++i) acc[i] = fmaf(dS[(h * 16 + i) * 16 + j], kv, acc[i]);
+        }
+      } else {                    // dk_j, dv_j, dvg_j = sum_i W[i][j] x_i   (W = dS for dk, P otherwise)
+        const float* W = (kind == 1 ? dS : Ps) + h * 256;
+        const float* src = kind == 1 ? qs + col : kind == 2 ? ds + col : ds + 256 + col;
+        const int stride = kind == 1 ? A_RS : A_DS;
+        for (int i = 0; i < n; ++i) {
+          const float xv = src[i * stride];
+#pragma unroll
+          for (int j = 0; j < MAXN; ++j) acc[j] = fmaf(W[i * 16 + j], xv, acc[j]);
+        }
+      }
+      if (kind < 3) {
+#pragma unroll
+        for (int i = 0; i < MAXN; ++i)
+          if (i < n) dQKV[(long long)(t0 + i) * 768 + kind * 256 + col] = acc[i];
+      } else {
+        const int c = col & 127, r = col >> 8;
+        if (c < 126) {
+#pragma unroll
+          for (int i = 0; i < MAXN; ++i)
+            if (i < n) dVGP[(long long)(t0 + i) * 756 + r * 252 + h * 126 + c] = acc[i];
+        }
+      }
+    }
+  }
+  if (has_bias) {
+    if (tid < 6) wacc[tid] = 0.f;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      const float s = warp_sum(wloc[k]);
+      if ((tid & 31) == 0) atomicAdd(&wacc[k], s);
+    }
+    __syncthreads();
+    if (tid < 6) atomicAdd(dWrel + tid, wacc[tid]);
+  }
+}
+
+inline int attention_fwd(const float* QKV, const float* VGP, const float* GD, float* O, float* OG, float* P, long long zsS,
+                         const float* Wrel, const float* brel, long long zsP, const AttnGraphs& gr, int nb, cudaStream_t st) {
+  if (gr.G <= 0) return 0;
+  static bool attr_done = false;
+  if (!attr_done) {
+    SGRL_CUDA(cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_fwd_smem()));
+    attr_done = true;
+  }
+  const int gx = gr.G < 4 * NUM_SMS ? gr.G : 4 * NUM_SMS;
+  attention_fwd_kernel<<<dim3(gx, nb), A_FWD_THREADS, attn_fwd_smem(), st>>>(QKV, VGP, GD, O, OG, P, zsS, Wrel, brel, zsP, gr);
+  SGRL_LAUNCH_OK();
+  return 0;
+}
+
+inline int attention_bwd(const float* QKV, const float* VGP, const float* GD, const float* P, long long zsS,
+                         const float* dO, const float* dOG, float* dQKV, float* dVGP, long long zsW,
+                         float* dWrel, long long zsG, const AttnGraphs& gr, int nb, cudaStream_t st) {
+  if (gr.G <= 0) return 0;
+  static bool attr_done = false;
+  if (!attr_done) {
+    SGRL_CUDA(cudaFuncSetAttribute(attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_bwd_smem()));
+    attr_done = true;
+  }
+  const int gx = gr.G < 2 * NUM_SMS ? gr.G : 2 * NUM_SMS;
+  attention_bwd_kernel<<<dim3(gx, nb), A_BWD_THREADS, attn_bwd_smem(), st>>>(QKV, VGP, GD, P, zsS, dO, dOG, dQKV, dVGP, zsW, dWrel, zsG, gr);
+  SGRL_LAUNCH_OK();
+  return 0;
+}
+
+}  // namespace sgrl

@@ -1,0 +1,40 @@
+// Shared device/host helpers for the sgrl_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+
+namespace sgrl {
+
+// ---- error plumbing: C-ABI calls return 0 or a negative code, message kept thread-local
+extern thread_local char g_err[512];
+inline int fail(int code, const char* what, const char* file, int line) {
+  snprintf(g_err, sizeof(g_err), "%s (%s:%d)", what, file, line);
+  return code;
+}
+#define SGRL_CHECK(cond, msg) do { if (!(cond)) return ::sgrl::fail(-2, msg, __FILE__, __LINE__); } while (0)
+#define SGRL_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return ::sgrl::fail(-3, cudaGetErrorString(e__), __FILE__, __LINE__); } while (0)
+#define SGRL_LAUNCH_OK() do { cudaError_t e__ = cudaPeekAtLastError(); if (e__ != cudaSuccess) return ::sgrl::fail(-4, cudaGetErrorString(e__), __FILE__, __LINE__); } while (0)
+#define SGRL_TRY(call) do { int r__ = (call); if (r__ != 0) return r__; } while (0)
+
+constexpr int NUM_SMS = 148;  // B200
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ void stg4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+
+inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+}  // namespace sgrl

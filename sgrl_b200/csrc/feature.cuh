@@ -1,0 +1,236 @@
+// K1 — per-limb invariant feature construction.
+//
+// For every limb-token t with vector-stream features X_t (3 x C):
+//     Z_t = [ X_t P^T | gd_t ]            (3 x 32)   30 learned channels + gravity + target dir
+//     G_t = Z_t^T Z_t                     (32 x 32)  O(3)-invariant Gram; column 30 = projection
+//                                                    of every channel onto the gravity axis
+//     F_t = ||G_t||_F + 1
+// replaces  g_proj -> cat gdir -> bmm(Z^T,Z) -> norm+1  of
+// subequivariant_attentions.py:90-96, SEActor.py:93-100 and SEActor.py:256-262.
+// Optionally a second projection P' gives Z'_t = [X_t P'^T | gd_t] (the operand of the
+// per-token matrix apply, SEActor.py:108-110 / :273-274) from the same staged X tile.
+//
+// HBM-bound: reads 12*C+24 B, writes 4096+4+384 B per token.  One CTA stages P once and
+// walks 32-token tiles: coalesced float4 loads -> padded smem -> 3x4 register micro-tiles
+// for the projection -> per-warp Gram rows written as 512 B coalesced float4 stores.
+#pragma once
+#include "common.cuh"
+
+namespace sgrl {
+
+constexpr int F_TT = 32;        // tokens per tile
+constexpr int F_THREADS = 256;
+
+template <int CE, int NPROJ>
+struct FeatSmem {
+  static constexpr int C = 128 + CE;
+  static constexpr int PJ = 32 * NPROJ;
+  static constexpr int XS = 3 * C + 4;  // padded token stride (floats)
+  static constexpr size_t bytes = sizeof(float) * ((size_t)C * PJ + (size_t)F_TT * XS + (size_t)F_TT * 3 * PJ + F_TT * 8);
+};
+
+// X = [V0 (T,3,8) if CE==8 | Xg (T,3,128)], P1/P2 (30,C) row-major, gd (T,3,2)
+template <int CE, int NPROJ>
+__global__ void __launch_bounds__(F_THREADS) inv_feature_fwd_kernel(
+    const float* __restrict__ Xg, long long zsXg, const float* __restrict__ V0, long long zsV0,
+    const float* __restrict__ gd, long long zsGd,
+    const float* __restrict__ P1, const float* __restrict__ P2, long long zsP,
+    float* __restrict__ Z, float* __restrict__ Z2, float* __restrict__ G, float* __restrict__ Fn, long long zsAct,
+    int T) {
+  using S = FeatSmem<CE, NPROJ>;
+  constexpr int C = S::C, PJ = S::PJ, XS = S::XS, JQ = PJ / 4;
+  extern __shared__ __align__(16) float smem[];
+  float* Ps = smem;                       // [C][PJ]
+  float* Xs = Ps + C * PJ;                // [TT][XS]
+  float* Zs = Xs + F_TT * XS;             // [TT][3][PJ]
+  float* gds = Zs + F_TT * 3 * PJ;        // [TT][8] (6 used)
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, z = blockIdx.y;
+  Xg += z * zsXg; gd += z * zsGd; P1 += z * zsP;
+  if (CE) V0 += z * zsV0;
+  if (NPROJ == 2) P2 += z * zsP;
+  Z += z * zsAct; G += z * zsAct; Fn += z * zsAct;
+  if (NPROJ == 2) Z2 += z * zsAct;
+
+  // stage P transposed: Ps[c][j] = P[j][c]; columns 30,31 (and 62,63) are zero
+  for (int i = tid; i < C * PJ; i += F_THREADS) {
+    const int j = i / C, c = i % C;        // coalesced along c in global
+    const int jj = j & 31;
+    float v = 0.f;
+    if (jj < 30) v = __ldg((j < 32 ? P1 : P2) + jj * C + c);
+    Ps[c * PJ + j] = v;
+  }
+
+  const int ntiles = (T + F_TT - 1) / F_TT;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int t0 = tile * F_TT;
+    __syncthreads();   // previous tile fully consumed (and Ps staged on first pass)
+    // ---- stage X tile (coalesced float4 over the 128-wide part)
+    for (int i = tid; i < F_TT * 3 * 32; i += F_THREADS) {
+      const int tk = i / 96, rem = i % 96, r = rem / 32, c4 = (rem % 32) * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (t0 + tk < T) v = ldg4(Xg + ((long long)(t0 + tk) * 3 + r) * 128 + c4);
+      *reinterpret_cast<float4*>(&Xs[tk * XS + r * C + CE + c4]) = v;
+    }
+    if (CE) {
+      for (int i = tid; i < F_TT * 24; i += F_THREADS) {
+        const int tk = i / 24, rem = i % 24, r = rem / 8, c = rem % 8;
+        Xs[tk * XS + r * C + c] = (t0 + tk < T) ? __ldg(V0 + (long long)(t0 + tk) * 24 + rem) : 0.f;
+      }
+    }
+    for (int i = tid; i < F_TT * 6; i += F_THREADS) {
+      const int tk = i / 6;
+      gds[tk * 8 + i % 6] = (t0 + tk < T) ? __ldg(gd + (long long)(t0 + tk) * 6 + i % 6) : 0.f;
+    }
+    __syncthreads();
+    // ---- projection: each thread owns (token, 4 output channels) x 3 spatial rows
+    for (int w = tid; w < F_TT * JQ; w += F_THREADS) {
+      const int tk = w / JQ, jq = w % JQ;
+      float acc[3][4];
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[r][j] = 0.f;
+      const float* xr = Xs + tk * XS;
+      const float* pj = Ps + jq * 4;
+#pragma unroll 2
+      for (int c = 0; c < C; c += 4) {
+        float4 x[3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) x[r] = *reinterpret_cast<const float4*>(xr + r * C + c);
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+          const float4 pv = *reinterpret_cast<const float4*>(pj + (c + cc) * PJ);
+#pragma unroll
+          for (int r = 0; r < 3; ++r) {
+            const float xv = cc == 0 ? x[r].x : cc == 1 ? x[r].y : cc == 2 ? x[r].z : x[r].w;
+            acc[r][0] = fmaf(xv, pv.x, acc[r][0]);
+            acc[r][1] = fmaf(xv, pv.y, acc[r][1]);
+            acc[r][2] = fmaf(xv, pv.z, acc[r][2]);
+            acc[r][3] = fmaf(xv, pv.w, acc[r][3]);
+          }
+        }
+      }
+      if ((jq & 7) == 7) {   // channels 30,31 of each Z are [gravity, direction]
+#pragma unroll
+        for (int r = 0; r < 3; ++r) { acc[r][2] = gds[tk * 8 + r * 2 + 0]; acc[r][3] = gds[tk * 8 + r * 2 + 1]; }
+      }
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+        *reinterpret_cast<float4*>(&Zs[(tk * 3 + r) * PJ + jq * 4]) = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+    }
+    __syncthreads();
+    // ---- write Z (and Z') coalesced
+    for (int i = tid; i < F_TT * 3 * 8 * NPROJ; i += F_THREADS) {
+      const int which = i / (F_TT * 24), rem = i % (F_TT * 24), row = rem / 8, q = rem % 8;
+      const int tk = row / 3;
+      if (t0 + tk < T) {
+        const float4 v = *reinterpret_cast<const float4*>(&Zs[row * PJ + which * 32 + q * 4]);
+        stg4((which ? Z2 : Z) + ((long long)t0 * 3 + row) * 32 + q * 4, v);
+      }
+    }
+    // ---- Gram + Frobenius norm: one warp per token, 8 x (32 lanes x float4) = 1024 outputs
+    for (int tk = warp; tk < F_TT; tk += F_THREADS / 32) {
+      if (t0 + tk >= T) break;
+      const float* zr = Zs + tk * 3 * PJ;
+      float ss = 0.f;
+      float* g = G + (long long)(t0 + tk) * 1024;
+#pragma unroll
+      for (int n = 0; n < 8; ++n) {
+        const int idx = n * 32 + lane, i = idx >> 3, jq = idx & 7;
+        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+          const float zi = zr[r * PJ + i];
+          const float4 zj = *reinterpret_cast<const float4*>(zr + r * PJ + jq * 4);
+          o.x = fmaf(zi, zj.x, o.x); o.y = fmaf(zi, zj.y, o.y); o.z = fmaf(zi, zj.z, o.z); o.w = fmaf(zi, zj.w, o.w);
+        }
+        stg4(g + idx * 4, o);
+        ss += o.x * o.x + o.y * o.y + o.z * o.z + o.w * o.w;
+      }
+      ss = warp_sum(ss);
+      if (lane == 0) Fn[t0 + tk] = sqrtf(ss) + 1.0f;
+    }
+  }
+}
+
+struct FeatFwdP {
+  const float* Xg; long long zsXg; const float* V0; long long zsV0; const float* gd; long long zsGd;
+  const float* P1; const float* P2; long long zsP;
+  float* Z; float* Z2; float* G; float* Fn; long long zsAct;
+  int T; int nb; int head;   // head=1: X = [V0 | Xg] (C=136)
+};
+
+template <int CE, int NPROJ>
+inline int inv_feature_fwd_launch(const FeatFwdP& p, cudaStream_t st) {
+  using S = FeatSmem<CE, NPROJ>;
+  auto kern = inv_feature_fwd_kernel<CE, NPROJ>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    SGRL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::bytes));
+    attr_done = true;
+  }
+  const int ntiles = ceil_div(p.T, F_TT);
+  const int gx = ntiles < 2 * NUM_SMS ? ntiles : 2 * NUM_SMS;
+  kern<<<dim3(gx, p.nb), F_THREADS, S::bytes, st>>>(p.Xg, p.zsXg, p.V0, p.zsV0, p.gd, p.zsGd, p.P1, p.P2, p.zsP,
+                                                   p.Z, p.Z2, p.G, p.Fn, p.zsAct, p.T);
+  SGRL_LAUNCH_OK();
+  return 0;
+}
+
+inline int inv_feature_fwd(const FeatFwdP& p, cudaStream_t st) {
+  if (p.T <= 0) return 0;
+  const bool two = p.P2 != nullptr;
+  if (p.head) return two ? inv_feature_fwd_launch<8, 2>(p, st) : inv_feature_fwd_launch<8, 1>(p, st);
+  return two ? inv_feature_fwd_launch<0, 2>(p, st) : inv_feature_fwd_launch<0, 1>(p, st);
+}
+
+// ---- backward ------------------------------------------------------------------------
+// Inputs: dG (T,1024) gradient w.r.t. vec(G) from the consumer GEMM, dF (T) accumulated
+// gradient w.r.t. F from every division by F, Z (T,3,32), F (T).
+//   dG_tot = dG + dF * G / (F-1)        (G recomputed from Z; F-1 = ||G||_F, 0 -> subgradient 0)
+//   dZ     = Z (dG_tot + dG_tot^T)      (T,3,32); columns 30,31 (inputs) are ignored downstream
+// If dZ_add != nullptr its contents are added (gradient reaching Z through another path).
+__global__ void __launch_bounds__(256) inv_feature_bwd_kernel(
+    const float* __restrict__ dG, const float* __restrict__ dF, const float* __restrict__ Z,
+    const float* __restrict__ Fn, float* __restrict__ dZ, long long zsAct, long long zsWs, int T) {
+  __shared__ float S[8][32][33];
+  __shared__ float Zw[8][3][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, z = blockIdx.y;
+  dG += z * zsWs; dF += z * zsWs; dZ += z * zsWs; Z += z * zsAct; Fn += z * zsAct;
+  for (int t = blockIdx.x * 8 + warp; t < T; t += gridDim.x * 8) {
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < 3; ++r) Zw[warp][r][lane] = Z[(long long)t * 96 + r * 32 + lane];
+    const float nrm = Fn[t] - 1.0f;
+    const float coef = nrm > 0.f ? dF[t] / nrm : 0.f;
+    __syncwarp();
+    const float zj0 = Zw[warp][0][lane], zj1 = Zw[warp][1][lane], zj2 = Zw[warp][2][lane];
+    const float* dg = dG + (long long)t * 1024;
+#pragma unroll 4
+    for (int i = 0; i < 32; ++i) {
+      const float g = Zw[warp][0][i] * zj0 + Zw[warp][1][i] * zj1 + Zw[warp][2][i] * zj2;
+      S[warp][i][lane] = __ldg(dg + i * 32 + lane) + coef * g;
+    }
+    __syncwarp();
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+#pragma unroll 4
+    for (int i = 0; i < 32; ++i) {
+      const float s = S[warp][i][lane] + S[warp][lane][i];
+      a0 = fmaf(Zw[warp][0][i], s, a0); a1 = fmaf(Zw[warp][1][i], s, a1); a2 = fmaf(Zw[warp][2][i], s, a2);
+    }
+    float* o = dZ + (long long)t * 96;
+    o[lane] = a0; o[32 + lane] = a1; o[64 + lane] = a2;
+  }
+}
+
+inline int inv_feature_bwd(const float* dG, const float* dF, const float* Z, const float* Fn, float* dZ,
+                           long long zsAct, long long zsWs, int T, int nb, cudaStream_t st) {
+  if (T <= 0) return 0;
+  int gx = ceil_div(T, 8);
+  if (gx > 8 * NUM_SMS) gx = 8 * NUM_SMS;
+  inv_feature_bwd_kernel<<<dim3(gx, nb), 256, 0, st>>>(dG, dF, Z, Fn, dZ, zsAct, zsWs, T);
+  SGRL_LAUNCH_OK();
+  return 0;
+}
+
+}  // namespace sgrl

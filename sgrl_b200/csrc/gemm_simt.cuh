@@ -1,0 +1,188 @@
+// Generic fp32 SIMT GEMM with fused epilogue.  Used for every contraction whose shape is
+// too small or too ragged for the tcgen05 path (K = 8/17/20/30/32/145/148, N = 1/3/30)
+// and, in round 1, for the backward contractions (dX = dY W, dW = dY^T X).
+//
+//   C[z][m][n] (op)= epi( alpha * sum_k A(m,k) * B(n,k) )
+//   A(m,k) = transA ? A[k*lda+m] : A[m*lda+k]      B(n,k) = transB ? B[k*ldb+n] : B[n*ldb+k]
+//
+// so  Y = X W^T        -> transA=0, transB=0   (nn.Linear weight is (N,K) row-major)
+//     dX = dY W        -> transA=0, transB=1
+//     dW = dY^T X      -> transA=1, transB=1   (contraction over tokens; split-K + atomics)
+#pragma once
+#include "common.cuh"
+
+namespace sgrl {
+
+struct GemmP {
+  const float* A; long long zsA; int lda; int transA;
+  const float* B; long long zsB; int ldb; int transB;
+  float* C; long long zsC; int ldc;
+  int M, N, K;
+  float alpha;
+  const float* bias; long long zsBias;      // + bias[n]
+  int relu;                                 // max(v,0)
+  const float* rowdiv; long long zsRow;     // v / rowdiv[m]
+  float colscale; int colscale_n;           // v * colscale for n < colscale_n
+  const float* mask; long long zsMask; int ldmask;  // v = mask[m][n] > 0 ? v : 0
+  const float* res1; long long zsR1; int ldr1;      // + res1[m][n]
+  const float* res2; long long zsR2; int ldr2;      // + res2[m][n]
+  int accumulate;                           // C += v instead of C = v
+  int splitk;                               // >1: split K over blockIdx.y, atomicAdd (implies accumulate)
+  int nb;                                   // instances (blockIdx.z)
+};
+
+inline GemmP gemm_defaults() {
+  GemmP p;
+  memset(&p, 0, sizeof(p));
+  p.alpha = 1.f; p.colscale = 1.f; p.splitk = 1; p.nb = 1;
+  return p;
+}
+
+constexpr int GB_M = 64, GB_N = 64, GB_K = 16, G_THREADS = 256, G_PAD = 4;
+
+__device__ __forceinline__ void gemm_fetch(float (&r)[4], const float* __restrict__ src, int ld, int trans,
+                                           int r0, int k0, int rlim, int klim, bool vec, int tid) {
+  if (!trans) {
+    const int row = r0 + (tid >> 2), k = k0 + (tid & 3) * 4;
+    if (row < rlim && vec && k + 3 < klim) {
+      float4 v = ldg4(src + (long long)row * ld + k);
+      r[0] = v.x; r[1] = v.y; r[2] = v.z; r[3] = v.w;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) r[i] = (row < rlim && k + i < klim) ? __ldg(src + (long long)row * ld + k + i) : 0.f;
+    }
+  } else {
+    const int k = k0 + (tid >> 4), row = r0 + (tid & 15) * 4;
+    if (k < klim && vec && row + 3 < rlim) {
+      float4 v = ldg4(src + (long long)k * ld + row);
+      r[0] = v.x; r[1] = v.y; r[2] = v.z; r[3] = v.w;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) r[i] = (k < klim && row + i < rlim) ? __ldg(src + (long long)k * ld + row + i) : 0.f;
+    }
+  }
+}
+
+__device__ __forceinline__ void gemm_stash(float (*s)[GB_M + G_PAD], const float (&r)[4], int trans, int tid) {
+  if (!trans) {
+    const int row = tid >> 2, k = (tid & 3) * 4;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) s[k + i][row] = r[i];
+  } else {
+    const int k = tid >> 4, row = (tid & 15) * 4;
+    *reinterpret_cast<float4*>(&s[k][row]) = make_float4(r[0], r[1], r[2], r[3]);
+  }
+}
+
+__global__ void __launch_bounds__(G_THREADS) gemm_simt_kernel(GemmP p) {
+  __shared__ __align__(16) float As[GB_K][GB_M + G_PAD];
+  __shared__ __align__(16) float Bs[GB_K][GB_N + G_PAD];
+  const int tid = threadIdx.x, z = blockIdx.z;
+  const int tiles_n = (p.N + GB_N - 1) / GB_N;
+  const int m0 = (blockIdx.x / tiles_n) * GB_M, n0 = (blockIdx.x % tiles_n) * GB_N;
+  const float* A = p.A + z * p.zsA;
+  const float* B = p.B + z * p.zsB;
+  // K range of this split
+  const int ktiles = (p.K + GB_K - 1) / GB_K;
+  const int per = (ktiles + p.splitk - 1) / p.splitk;
+  const int kt0 = blockIdx.y * per, kt1 = min(ktiles, kt0 + per);
+  const bool vecA = ((p.lda & 3) == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0);
+  const bool vecB = ((p.ldb & 3) == 0) && ((reinterpret_cast<uintptr_t>(B) & 15) == 0);
+  const int tx = tid & 15, ty = tid >> 4;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  float ra[4], rb[4];
+  if (kt0 < kt1) {
+    gemm_fetch(ra, A, p.lda, p.transA, m0, kt0 * GB_K, p.M, p.K, vecA, tid);
+    gemm_fetch(rb, B, p.ldb, p.transB, n0, kt0 * GB_K, p.N, p.K, vecB, tid);
+    gemm_stash(As, ra, p.transA, tid);
+    gemm_stash(Bs, rb, p.transB, tid);
+  }
+  __syncthreads();
+  for (int kt = kt0; kt < kt1; ++kt) {
+    const bool more = kt + 1 < kt1;
+    if (more) {
+      gemm_fetch(ra, A, p.lda, p.transA, m0, (kt + 1) * GB_K, p.M, p.K, vecA, tid);
+      gemm_fetch(rb, B, p.ldb, p.transB, n0, (kt + 1) * GB_K, p.N, p.K, vecB, tid);
+    }
+#pragma unroll
+    for (int k = 0; k < GB_K; ++k) {
+      const float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+    if (more) {
+      gemm_stash(As, ra, p.transA, tid);
+      gemm_stash(Bs, rb, p.transB, tid);
+    }
+    __syncthreads();
+  }
+  if (kt0 >= kt1 && p.splitk > 1) return;
+
+  // ---- epilogue
+  float* C = p.C + z * p.zsC;
+  const float* bias = p.bias ? p.bias + z * p.zsBias : nullptr;
+  const float* rowdiv = p.rowdiv ? p.rowdiv + z * p.zsRow : nullptr;
+  const float* mask = p.mask ? p.mask + z * p.zsMask : nullptr;
+  const float* res1 = p.res1 ? p.res1 + z * p.zsR1 : nullptr;
+  const float* res2 = p.res2 ? p.res2 + z * p.zsR2 : nullptr;
+  const bool first_split = blockIdx.y == 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= p.M) continue;
+    const float rd = rowdiv ? rowdiv[m] : 1.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= p.N) continue;
+      float v = p.alpha * acc[i][j];
+      if (bias && first_split) v += bias[n];
+      if (p.relu) v = fmaxf(v, 0.f);
+      if (rowdiv) v = v / rd;
+      if (n < p.colscale_n) v *= p.colscale;
+      if (mask) v = mask[(long long)m * p.ldmask + n] > 0.f ? v : 0.f;
+      if (res1) v += res1[(long long)m * p.ldr1 + n];
+      if (res2) v += res2[(long long)m * p.ldr2 + n];
+      float* c = C + (long long)m * p.ldc + n;
+      if (p.splitk > 1) atomicAdd(c, v);
+      else if (p.accumulate) *c += v;
+      else *c = v;
+    }
+  }
+}
+
+inline int gemm_simt(const GemmP& p, cudaStream_t st) {
+  if (p.M <= 0 || p.N <= 0 || p.nb <= 0) return 0;
+  SGRL_CHECK(p.K > 0, "gemm: K must be positive");
+  SGRL_CHECK(p.splitk >= 1, "gemm: splitk");
+  SGRL_CHECK(p.splitk == 1 || (!p.relu && !p.rowdiv && !p.mask && !p.res1 && !p.res2 && p.colscale_n == 0),
+             "gemm: split-K only with a linear epilogue");
+  const int tiles = ceil_div(p.M, GB_M) * ceil_div(p.N, GB_N);
+  dim3 grid(tiles, p.splitk, p.nb);
+  gemm_simt_kernel<<<grid, G_THREADS, 0, st>>>(p);
+  SGRL_LAUNCH_OK();
+  return 0;
+}
+
+// choose a split-K factor for token-contraction GEMMs (dW): fill ~2 waves of the SMs
+inline int pick_splitk(int M, int N, int K, int nb) {
+  const int tiles = ceil_div(M, GB_M) * ceil_div(N, GB_N) * nb;
+  const int ktiles = ceil_div(K, GB_K);
+  int s = (2 * NUM_SMS + tiles - 1) / tiles;
+  if (s > ktiles / 4) s = ktiles / 4;   // at least 4 k-tiles (64 tokens) per split
+  if (s < 1) s = 1;
+  if (s > 64) s = 64;
+  return s;
+}
+
+}  // namespace sgrl

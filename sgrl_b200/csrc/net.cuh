@@ -1,0 +1,470 @@
+// SET network executor: sequences the kernels of one forward / backward pass of nb
+// identical-shape networks (nb=2: twin critics sharing their input, SECritic.py:86-87)
+// over a packed batch of limb graphs.  Host C++ only; every launch goes to ctx.stream.
+//
+// Forward follows TransformerModel.forward (SEActor.py:237-287) / SURVEY.md Appendix A/G;
+// backward follows SURVEY.md Appendix H.  Activations needed by the backward live in the
+// caller-owned stash (layout.h); gradients w.r.t. parameters accumulate into the caller's
+// flat gradient arena, which mirrors the parameter arena.
+#pragma once
+#include "attention.cuh"
+#include "common.cuh"
+#include "feature.cuh"
+#include "gemm_simt.cuh"
+#include "gemm_tc.cuh"
+#include "layout.h"
+#include "misc.cuh"
+
+namespace sgrl {
+
+// ---- backward workspace (floats per token, per net instance) --------------------------
+enum WS {
+  W_DVG, W_DH, W_DUA, W_DUB, W_DQKV, W_DVGP, W_DO, W_DOG, W_DX, W_DDV, W_DZ1, W_DZ2, W_DZ3, W_DG,
+  W_DF1, W_DF2, W_DA, W_DT31, W_DT4, W_DR, W_DFF, W_DUH, W_DSH, W_DQ, WS_COUNT
+};
+inline const int* ws_sizes() {
+  static const int s[WS_COUNT] = {384, 128, 256, 256, 768, 756, 256, 768, 128, 384, 96, 96, 96, 1024,
+                                  1, 1, 256, 512, 1024, 96, 128, 256, 148, 3};
+  return s;
+}
+struct WsLayout { long long o[WS_COUNT]; long long total; };
+inline WsLayout make_ws(long long T) {
+  WsLayout w; long long off = 0;
+  for (int i = 0; i < WS_COUNT; ++i) { w.o[i] = off; off = align_up(off + (long long)ws_sizes()[i] * T, 64); }
+  w.total = off;
+  return w;
+}
+
+struct NetCtx {
+  int kind, L, nb, T;
+  NetLayout lay;
+  const float* params; long long zsP;     // live arena; z-stride = lay.live_floats
+  float* grads; long long zsG;            // gradient arena (same layout) or nullptr
+  StashLayout st; float* stash; long long zsS;
+  WsLayout wl; float* ws; long long zsW;
+  AttnGraphs gr; const int* rank3;
+  float max_action;
+  int use_tc;                             // route eligible GEMMs to the tcgen05 kernel
+  cudaStream_t stream;
+
+  const float* P(long long off) const { return params + off; }
+  float* Gr(long long off) const { return grads + off; }
+  float* S(int id) const { return stash + st.gs[id]; }
+  float* SL(int l, int id) const { return stash + st.ls[l][id]; }
+  float* W(int id) const { return ws + wl.o[id]; }
+  int ng() const { return kind == ACTOR ? 17 : 20; }
+  int ks() const { return D + ng(); }
+};
+
+inline int run_gemm(const NetCtx& c, const GemmP& g) {
+  if (c.use_tc && gemm_tc_eligible(g)) return gemm_tc(g, c.stream);
+  return gemm_simt(g, c.stream);
+}
+
+// Y[M,N] = X[M,K] W^T (+b): X is stash-like, W/b parameters
+inline GemmP lin(const NetCtx& c, const float* X, int ldx, long long zsX, long long w_off, long long b_off,
+                 float* Y, int ldy, long long zsY, int M, int N, int K) {
+  GemmP g = gemm_defaults();
+  g.A = X; g.zsA = zsX; g.lda = ldx; g.transA = 0;
+  g.B = c.P(w_off); g.zsB = c.zsP; g.ldb = K; g.transB = 0;
+  g.C = Y; g.zsC = zsY; g.ldc = ldy;
+  g.M = M; g.N = N; g.K = K; g.nb = c.nb;
+  if (b_off >= 0) { g.bias = c.P(b_off); g.zsBias = c.zsP; }
+  return g;
+}
+// dX[M,Kw] = dY[M,Nw] W[Nw,Kw]  (ldw = row stride of W, w_col0 = first column used)
+inline GemmP dgrad(const NetCtx& c, const float* dY, int lddy, long long w_off, int ldw, float* dX, int lddx, int M, int Nw, int Kw) {
+  GemmP g = gemm_defaults();
+  g.A = dY; g.zsA = c.zsW; g.lda = lddy; g.transA = 0;
+  g.B = c.P(w_off); g.zsB = c.zsP; g.ldb = ldw; g.transB = 1;
+  g.C = dX; g.zsC = c.zsW; g.ldc = lddx;
+  g.M = M; g.N = Kw; g.K = Nw; g.nb = c.nb;
+  return g;
+}
+// dW[Nw,Kw] += dY[M,Nw]^T X[M,Kw]
+inline GemmP wgrad(const NetCtx& c, const float* dY, int lddy, const float* X, int ldx, long long zsX,
+                   long long dw_off, int ldw, int M, int Nw, int Kw) {
+  GemmP g = gemm_defaults();
+  g.A = dY; g.zsA = c.zsW; g.lda = lddy; g.transA = 1;
+  g.B = X; g.zsB = zsX; g.ldb = ldx; g.transB = 1;
+  g.C = c.Gr(dw_off); g.zsC = c.zsG; g.ldc = ldw;
+  g.M = Nw; g.N = Kw; g.K = M; g.nb = c.nb;
+  g.accumulate = 1;
+  g.splitk = pick_splitk(Nw, Kw, M, c.nb);
+  return g;
+}
+inline int colsum(const NetCtx& c, const float* X, int ldx, long long g_off, int M, int N, float alpha = 1.f) {
+  int gy = ceil_div(M, 64); if (gy > 32) gy = 32; if (gy < 1) gy = 1;
+  colsum_kernel<<<dim3(ceil_div(N, 32), gy, c.nb), 256, 0, c.stream>>>(X, ldx, c.zsW, c.Gr(g_off), c.zsG, M, N, alpha);
+  SGRL_LAUNCH_OK();
+  return 0;
+}
+inline int block_copy(const NetCtx& c, float* dst, int ldd, long long zsD, const float* src, int lds, long long zsSrc, int M, int N, int add) {
+  int gx = ceil_div((long long)M * N, 256); if (gx > 4 * NUM_SMS) gx = 4 * NUM_SMS; if (gx < 1) gx = 1;
+  block_copy_kernel<<<dim3(gx, c.nb), 256, 0, c.stream>>>(dst, ldd, zsD, src, lds, zsSrc, M, N, add);
+  SGRL_LAUNCH_OK();
+  return 0;
+}
+inline int layernorm_fwd(const NetCtx& c, const float* a, int lda, const float* b, int ldb, long long g_off, long long b_off,
+                         float* x, float* y, int ldy, float* stats) {
+  layernorm_fwd_kernel<<<dim3(grid_for_warps(c.T), c.nb), 256, 0, c.stream>>>(a, lda, b, ldb, c.P(g_off), c.P(b_off), c.zsP, x, y, ldy,
+                                                                              nullptr, 0, stats, c.zsS, c.T);
+  SGRL_LAUNCH_OK();
+  return 0;
+}
+inline int layernorm_bwd(const NetCtx& c, const float* dy1, int ld1, const float* dy2, int ld2, const float* x, int ldx,
+                         const float* stats, long long g_off, long long b_off, float* dx, int lddx) {
+  int gx = grid_for_warps(c.T); if (gx > 2 * NUM_SMS) gx = 2 * NUM_SMS;
+  layernorm_bwd_kernel<<<dim3(gx, c.nb), 256, 0, c.stream>>>(dy1, ld1, dy2, ld2, x, ldx, stats, c.zsS, c.P(g_off), c.zsP, dx, lddx, c.zsW,
+                                                             c.Gr(g_off), c.Gr(b_off), c.zsG, c.T);
+  SGRL_LAUNCH_OK();
+  return 0;
+}
+inline int rowdiv_bwd(const NetCtx& c, float* dy, int lddy, const float* y, int ldy, const float* Fn, float* dF, int N, float cs, int cs_n) {
+  rowdiv_bwd_kernel<<<dim3(grid_for_warps(c.T), c.nb), 256, 0, c.stream>>>(dy, lddy, c.zsW, y, ldy, Fn, c.zsS, dF, N, cs, cs_n, c.T);
+  SGRL_LAUNCH_OK();
+  return 0;
+}
+inline int zero_ws(const NetCtx& c, int id) {
+  for (int z = 0; z < c.nb; ++z) SGRL_CUDA(cudaMemsetAsync(c.W(id) + z * c.zsW, 0, sizeof(float) * ws_sizes()[id] * (size_t)c.T, c.stream));
+  return 0;
+}
+
+constexpr float QSCALE = 0.08838834764831845f;   // (2*head_dim)^-0.5 = 128^-0.5, subequivariant_attentions.py:88
+constexpr float SQRT_D = 11.313708498984761f;    // sqrt(128), SEActor.py:247,249
+
+// ======================================================================================
+// forward
+// ======================================================================================
+inline int net_forward(const NetCtx& c, const float* obs, long long zsObs, const float* act, long long zsAct,
+                       float* out, long long zsOut) {
+  const int T = c.T, T3 = 3 * c.T, ng = c.ng(), KS = c.ks();
+  const NetLayout& Y = c.lay;
+  cudaStream_t st = c.stream;
+  const long long zS = c.zsS;
+  SGRL_CHECK(c.kind == ACTOR || act != nullptr, "critic forward needs actions");
+  {
+    int gx = ceil_div(T, E_TOK); if (gx > 4 * NUM_SMS) gx = 4 * NUM_SMS;
+    embed_fwd_kernel<<<dim3(gx, c.nb), 128, 0, st>>>(obs, zsObs, c.kind == CRITIC ? act : nullptr, zsAct, c.rank3,
+        c.P(Y.gp[G_GENC_W]), c.P(Y.gp[G_ENC_W]), c.P(Y.gp[G_ENC_B]), c.P(Y.gp[G_POS0]), c.P(Y.gp[G_POS1]), c.P(Y.gp[G_POS2]), c.zsP,
+        c.S(T_V0), c.S(T_GD), c.S(T_SH), KS, c.SL(0, S_VGIN), c.SL(0, S_UA) + 128, 256, zS, T, ng);
+    SGRL_LAUNCH_OK();
+  }
+  for (int l = 0; l < c.L; ++l) {
+    const long long* lp = Y.lp[l];
+    float* Vg = c.SL(l, S_VGIN);
+    float* ua = c.SL(l, S_UA);
+    float* ub = c.SL(l, S_UB);
+    const bool last = l + 1 == c.L;
+    float* Vg_next = last ? c.S(T_VGF) : c.SL(l + 1, S_VGIN);
+    float* h_next = last ? c.S(T_HL) : c.SL(l + 1, S_UA) + 128;
+    const int ld_hn = last ? 128 : 256;
+    // -- attention block: invariant features of Vg -> u = [g-mlp | h]
+    FeatFwdP f{}; f.Xg = Vg; f.zsXg = zS; f.gd = c.S(T_GD); f.zsGd = zS; f.P1 = c.P(lp[L_GPROJ]); f.zsP = c.zsP;
+    f.Z = c.SL(l, S_Z1); f.G = c.SL(l, S_G1); f.Fn = c.SL(l, S_F1); f.zsAct = zS; f.T = T; f.nb = c.nb;
+    SGRL_TRY(inv_feature_fwd(f, st));
+    GemmP g = lin(c, c.SL(l, S_G1), 1024, zS, lp[L_G1_W], lp[L_G1_B], c.SL(l, S_A1), 256, zS, T, 256, 1024); g.relu = 1;
+    SGRL_TRY(run_gemm(c, g));
+    g = lin(c, c.SL(l, S_A1), 256, zS, lp[L_G2_W], lp[L_G2_B], ua, 256, zS, T, 128, 256);
+    SGRL_TRY(run_gemm(c, g));
+    g = lin(c, ua, 256, zS, lp[L_Q_W], lp[L_Q_B], c.SL(l, S_QKV), 768, zS, T, 768, 256);
+    g.rowdiv = c.SL(l, S_F1); g.zsRow = zS; g.colscale = QSCALE; g.colscale_n = 256;
+    SGRL_TRY(run_gemm(c, g));
+    g = lin(c, Vg, 128, zS, lp[L_VG_W], -1, c.SL(l, S_VGP), 252, zS, T3, 252, 128);
+    SGRL_TRY(run_gemm(c, g));
+    SGRL_TRY(attention_fwd(c.SL(l, S_QKV), c.SL(l, S_VGP), c.S(T_GD), c.SL(l, S_O), c.SL(l, S_OG), c.SL(l, S_P), zS,
+                           l == 0 ? c.P(Y.gp[G_REL_W]) : nullptr, l == 0 ? c.P(Y.gp[G_REL_B]) : nullptr, c.zsP, c.gr, c.nb, st));
+    g = lin(c, c.SL(l, S_O), 256, zS, lp[L_NGO_W], lp[L_NGO_B], c.SL(l, S_X1), 128, zS, T, 128, 256);
+    SGRL_TRY(run_gemm(c, g));
+    SGRL_TRY(layernorm_fwd(c, ua + 128, 256, c.SL(l, S_X1), 128, lp[L_N1_W], lp[L_N1_B], c.SL(l, S_X1), ub + 128, 256, c.SL(l, S_ST1)));
+    g = lin(c, c.SL(l, S_OG), 256, zS, lp[L_GO_W], -1, c.SL(l, S_DV), 128, zS, T3, 128, 256);
+    SGRL_TRY(run_gemm(c, g));
+    // -- feed-forward block: invariant features of dV
+    FeatFwdP f2{}; f2.Xg = c.SL(l, S_DV); f2.zsXg = zS; f2.gd = c.S(T_GD); f2.zsGd = zS;
+    f2.P1 = c.P(lp[L_GP2]); f2.P2 = c.P(lp[L_GP3]); f2.zsP = c.zsP;
+    f2.Z = c.SL(l, S_Z2); f2.Z2 = c.SL(l, S_Z3); f2.G = c.SL(l, S_G2); f2.Fn = c.SL(l, S_F2); f2.zsAct = zS; f2.T = T; f2.nb = c.nb;
+    SGRL_TRY(inv_feature_fwd(f2, st));
+    g = lin(c, c.SL(l, S_G2), 1024, zS, lp[L_FG1_W], lp[L_FG1_B], c.SL(l, S_A2), 256, zS, T, 256, 1024); g.relu = 1;
+    SGRL_TRY(run_gemm(c, g));
+    g = lin(c, c.SL(l, S_A2), 256, zS, lp[L_FG2_W], lp[L_FG2_B], ub, 256, zS, T, 128, 256);
+    SGRL_TRY(run_gemm(c, g));
+    g = lin(c, ub, 256, zS, lp[L_L3_W], lp[L_L3_B], c.SL(l, S_T31), 512, zS, T, 512, 256); g.relu = 1;   // [linear3 | linear1]
+    SGRL_TRY(run_gemm(c, g));
+    g = lin(c, c.SL(l, S_T31), 512, zS, lp[L_L4_W], lp[L_L4_B], c.SL(l, S_MM), 1024, zS, T, 1024, 256);
+    g.rowdiv = c.SL(l, S_F2); g.zsRow = zS;
+    SGRL_TRY(run_gemm(c, g));
+    matapply_fwd_kernel<<<dim3(grid_for_warps(T), c.nb), 256, 0, st>>>(c.SL(l, S_Z3), c.SL(l, S_MM), c.SL(l, S_R), zS, T);
+    SGRL_LAUNCH_OK();
+    g = lin(c, c.SL(l, S_R), 32, zS, lp[L_L5_W], -1, Vg_next, 128, zS, T3, 128, 32);
+    g.res1 = Vg; g.zsR1 = zS; g.ldr1 = 128; g.res2 = c.SL(l, S_DV); g.zsR2 = zS; g.ldr2 = 128;
+    SGRL_TRY(run_gemm(c, g));
+    g = lin(c, c.SL(l, S_T31) + 256, 512, zS, lp[L_L2_W], lp[L_L2_B], c.SL(l, S_FF), 128, zS, T, 128, 256);
+    g.rowdiv = c.SL(l, S_F2); g.zsRow = zS;
+    SGRL_TRY(run_gemm(c, g));
+    SGRL_TRY(layernorm_fwd(c, ub + 128, 256, c.SL(l, S_FF), 128, lp[L_N2_W], lp[L_N2_B], c.SL(l, S_X2), h_next, ld_hn, c.SL(l, S_ST2)));
+  }
+  // final LayerNorm -> right part of SH = [s0 | h]
+  SGRL_TRY(layernorm_fwd(c, c.S(T_HL), 128, nullptr, 0, Y.gp[G_NORM_W], Y.gp[G_NORM_B], nullptr, c.S(T_SH) + ng, KS, c.S(T_STF)));
+  // -- heads
+  FeatFwdP fh{}; fh.head = 1; fh.Xg = c.S(T_VGF); fh.zsXg = zS; fh.V0 = c.S(T_V0); fh.zsV0 = zS; fh.gd = c.S(T_GD); fh.zsGd = zS;
+  fh.P1 = c.P(Y.gp[G_GG_W]); fh.P2 = c.kind == ACTOR ? c.P(Y.gp[G_GPH_W]) : nullptr; fh.zsP = c.zsP;
+  fh.Z = c.S(T_ZH); fh.Z2 = c.kind == ACTOR ? c.S(T_ZH2) : nullptr; fh.G = c.S(T_GH); fh.Fn = c.S(T_FH); fh.zsAct = zS; fh.T = T; fh.nb = c.nb;
+  SGRL_TRY(inv_feature_fwd(fh, st));
+  GemmP g = lin(c, c.S(T_GH), 1024, zS, Y.gp[G_H1G_W], Y.gp[G_H1G_B], c.S(T_AH), 128, zS, T, 128, 1024); g.relu = 1;
+  SGRL_TRY(run_gemm(c, g));
+  g = lin(c, c.S(T_AH), 128, zS, Y.gp[G_H2G_W], Y.gp[G_H2G_B], c.S(T_UH), 256, zS, T, 128, 128);
+  SGRL_TRY(run_gemm(c, g));
+  g = lin(c, c.S(T_SH), KS, zS, Y.gp[G_H1NG_W], Y.gp[G_H1NG_B], c.S(T_BH), 128, zS, T, 128, KS); g.relu = 1;
+  SGRL_TRY(run_gemm(c, g));
+  g = lin(c, c.S(T_BH), 128, zS, Y.gp[G_H2NG_W], Y.gp[G_H2NG_B], c.S(T_UH) + 128, 256, zS, T, 128, 128);
+  SGRL_TRY(run_gemm(c, g));
+  if (c.kind == CRITIC) {
+    g = lin(c, c.S(T_UH), 256, zS, Y.gp[G_DNG_W], Y.gp[G_DNG_B], c.S(T_OUT), 1, zS, T, 1, 256);
+    g.rowdiv = c.S(T_FH); g.zsRow = zS;
+    SGRL_TRY(run_gemm(c, g));
+  } else {
+    g = lin(c, c.S(T_UH), 256, zS, Y.gp[G_H1M_W], Y.gp[G_H1M_B], c.S(T_M1), 256, zS, T, 256, 256); g.relu = 1;
+    SGRL_TRY(run_gemm(c, g));
+    g = lin(c, c.S(T_M1), 256, zS, Y.gp[G_H2M_W], Y.gp[G_H2M_B], c.S(T_MH), 1024, zS, T, 1024, 256);
+    g.rowdiv = c.S(T_FH); g.zsRow = zS;
+    SGRL_TRY(run_gemm(c, g));
+    matapply_fwd_kernel<<<dim3(grid_for_warps(T), c.nb), 256, 0, st>>>(c.S(T_ZH2), c.S(T_MH), c.S(T_RH), zS, T);
+    SGRL_LAUNCH_OK();
+    actor_out_fwd_kernel<<<dim3(grid_for_warps(T), c.nb), 256, 0, st>>>(c.S(T_RH), c.S(T_V0), c.P(Y.gp[G_DG_W]), c.zsP, c.S(T_W3), c.S(T_OUT), zS,
+                                                                        c.max_action, T);
+    SGRL_LAUNCH_OK();
+  }
+  const int od = c.kind == ACTOR ? 3 : 1;
+  if (out) SGRL_TRY(block_copy(c, out, od, zsOut, c.S(T_OUT), od, zS, T, od, 0));
+  return 0;
+}
+
+// ======================================================================================
+// backward.  dOut: gradient w.r.t. the forward output (T x 3 actor, T x 1 critic), per
+// instance stride zsDo.  need_wgrad=0 skips parameter gradients (actor step through
+// critic1: only d/d(action) is needed, agent.py:167).  dact (critic only, nullable)
+// receives d/d(action) (T x 3), overwritten.
+// ======================================================================================
+inline int net_backward(const NetCtx& c, const float* dOut, long long zsDo, int need_wgrad, float* dact, long long zsDact) {
+  const int T = c.T, T3 = 3 * c.T, ng = c.ng(), KS = c.ks();
+  const NetLayout& Y = c.lay;
+  cudaStream_t st = c.stream;
+  const long long zS = c.zsS, zW = c.zsW;
+  const bool wg = need_wgrad != 0;
+  SGRL_CHECK(!wg || c.grads != nullptr, "backward with need_wgrad requires a gradient arena");
+  GemmP g;
+  SGRL_TRY(zero_ws(c, W_DF1));   // used as dF of the head block first
+  float* dFh = c.W(W_DF1);
+  if (c.kind == CRITIC) {
+    SGRL_TRY(block_copy(c, c.W(W_DQ), 1, zW, dOut, 1, zsDo, T, 1, 0));
+    SGRL_TRY(rowdiv_bwd(c, c.W(W_DQ), 1, c.S(T_OUT), 1, c.S(T_FH), dFh, 1, 1.f, 0));
+    g = dgrad(c, c.W(W_DQ), 1, Y.gp[G_DNG_W], 256, c.W(W_DUH), 256, T, 1, 256);
+    SGRL_TRY(run_gemm(c, g));
+    if (wg) {
+      SGRL_TRY(run_gemm(c, wgrad(c, c.W(W_DQ), 1, c.S(T_UH), 256, zS, Y.gp[G_DNG_W], 256, T, 1, 256)));
+      SGRL_TRY(colsum(c, c.W(W_DQ), 1, Y.gp[G_DNG_B], T, 1));
+    }
+  } else {
+    actor_out_bwd_kernel<<<dim3(grid_for_warps(T) > 2 * NUM_SMS ? 2 * NUM_SMS : grid_for_warps(T), c.nb), 256, 0, st>>>(
+        dOut, zsDo, c.S(T_OUT), c.S(T_RH), c.S(T_V0), zS, c.P(Y.gp[G_DG_W]), c.zsP, c.W(W_DR), zW,
+        wg ? c.Gr(Y.gp[G_DG_W]) : c.W(W_DQ) /*discarded*/, wg ? c.zsG : zW, c.max_action, T);
+    SGRL_LAUNCH_OK();
+    matapply_bwd_kernel<<<dim3(grid_for_warps(T), c.nb), 256, 0, st>>>(c.W(W_DR), c.S(T_ZH2), c.S(T_MH), c.S(T_FH), zS,
+                                                                       c.W(W_DZ3), c.W(W_DT4), dFh, zW, T);
+    SGRL_LAUNCH_OK();
+    if (wg) {
+      SGRL_TRY(run_gemm(c, wgrad(c, c.W(W_DT4), 1024, c.S(T_M1), 256, zS, Y.gp[G_H2M_W], 256, T, 1024, 256)));
+      SGRL_TRY(colsum(c, c.W(W_DT4), 1024, Y.gp[G_H2M_B], T, 1024));
+    }
+    g = dgrad(c, c.W(W_DT4), 1024, Y.gp[G_H2M_W], 256, c.W(W_DA), 256, T, 1024, 256);
+    g.mask = c.S(T_M1); g.zsMask = zS; g.ldmask = 256;
+    SGRL_TRY(run_gemm(c, g));
+    if (wg) {
+      SGRL_TRY(run_gemm(c, wgrad(c, c.W(W_DA), 256, c.S(T_UH), 256, zS, Y.gp[G_H1M_W], 256, T, 256, 256)));
+      SGRL_TRY(colsum(c, c.W(W_DA), 256, Y.gp[G_H1M_B], T, 256));
+    }
+    g = dgrad(c, c.W(W_DA), 256, Y.gp[G_H1M_W], 256, c.W(W_DUH), 256, T, 256, 256);
+    SGRL_TRY(run_gemm(c, g));
+  }
+  // u[:, :128] = linear2_g(relu(linear1_g(vec G)))
+  if (wg) {
+    SGRL_TRY(run_gemm(c, wgrad(c, c.W(W_DUH), 256, c.S(T_AH), 128, zS, Y.gp[G_H2G_W], 128, T, 128, 128)));
+    SGRL_TRY(colsum(c, c.W(W_DUH), 256, Y.gp[G_H2G_B], T, 128));
+  }
+  g = dgrad(c, c.W(W_DUH), 256, Y.gp[G_H2G_W], 128, c.W(W_DA), 128, T, 128, 128);
+  g.mask = c.S(T_AH); g.zsMask = zS; g.ldmask = 128;
+  SGRL_TRY(run_gemm(c, g));
+  if (wg) {
+    SGRL_TRY(run_gemm(c, wgrad(c, c.W(W_DA), 128, c.S(T_GH), 1024, zS, Y.gp[G_H1G_W], 1024, T, 128, 1024)));
+    SGRL_TRY(colsum(c, c.W(W_DA), 128, Y.gp[G_H1G_B], T, 128));
+  }
+  g = dgrad(c, c.W(W_DA), 128, Y.gp[G_H1G_W], 1024, c.W(W_DG), 1024, T, 128, 1024);
+  SGRL_TRY(run_gemm(c, g));
+  SGRL_TRY(inv_feature_bwd(c.W(W_DG), dFh, c.S(T_ZH), c.S(T_FH), c.W(W_DZ1), zS, zW, T, c.nb, st));
+  // dVgF = dZh[:, :30] gg_proj[:, 8:] (+ dZh2[:, :30] g_proj[:, 8:])
+  g = dgrad(c, c.W(W_DZ1), 32, Y.gp[G_GG_W] + GN, D + GN, c.W(W_DVG), 128, T3, NPJ, 128);
+  SGRL_TRY(run_gemm(c, g));
+  if (c.kind == ACTOR) {
+    g = dgrad(c, c.W(W_DZ3), 32, Y.gp[G_GPH_W] + GN, D + GN, c.W(W_DVG), 128, T3, NPJ, 128); g.accumulate = 1;
+    SGRL_TRY(run_gemm(c, g));
+  }
+  if (wg) {
+    SGRL_TRY(run_gemm(c, wgrad(c, c.W(W_DZ1), 32, c.S(T_V0), 8, zS, Y.gp[G_GG_W], D + GN, T3, NPJ, GN)));
+    SGRL_TRY(run_gemm(c, wgrad(c, c.W(W_DZ1), 32, c.S(T_VGF), 128, zS, Y.gp[G_GG_W] + GN, D + GN, T3, NPJ, 128)));
+    if (c.kind == ACTOR) {
+      SGRL_TRY(run_gemm(c, wgrad(c, c.W(W_DZ3), 32, c.S(T_V0), 8, zS, Y.gp[G_GPH_W], D + GN, T3, NPJ, GN)));
+      SGRL_TRY(run_gemm(c, wgrad(c, c.W(W_DZ3), 32, c.S(T_VGF), 128, zS, Y.gp[G_GPH_W] + GN, D + GN, T3, NPJ, 128)));
+    }
+  }
+  // u[:, 128:] = linear2_ng(relu(linear1_ng([s0 | h])))
+  if (wg) {
+    SGRL_TRY(run_gemm(c, wgrad(c, c.W(W_DUH) + 128, 256, c.S(T_BH), 128, zS, Y.gp[G_H2NG_W], 128, T, 128, 128)));
+    SGRL_TRY(colsum(c, c.W(W_DUH) + 128, 256, Y.gp[G_H2NG_B], T, 128));
+  }
+  g = dgrad(c, c.W(W_DUH) + 128, 256, Y.gp[G_H2NG_W], 128, c.W(W_DA), 128, T, 128, 128);
+  g.mask = c.S(T_BH); g.zsMask = zS; g.ldmask = 128;
+  SGRL_TRY(run_gemm(c, g));
+  if (wg) {
+    SGRL_TRY(run_gemm(c, wgrad(c, c.W(W_DA), 128, c.S(T_SH), KS, zS, Y.gp[G_H1NG_W], KS, T, 128, KS)));
+    SGRL_TRY(colsum(c, c.W(W_DA), 128, Y.gp[G_H1NG_B], T, 128));
+  }
+  g = dgrad(c, c.W(W_DA), 128, Y.gp[G_H1NG_W], KS, c.W(W_DSH), KS, T, 128, KS);
+  SGRL_TRY(run_gemm(c, g));
+  if (dact) SGRL_TRY(block_copy(c, dact, 3, zsDact, c.W(W_DSH) + 17, KS, zW, T, 3, 0));
+  // final LayerNorm
+  SGRL_TRY(layernorm_bwd(c, c.W(W_DSH) + ng, KS, nullptr, 0, c.S(T_HL), 128, c.S(T_STF), Y.gp[G_NORM_W], Y.gp[G_NORM_B], c.W(W_DH), 128));
+
+  for (int l = c.L - 1; l >= 0; --l) {
+    const long long* lp = Y.lp[l];
+    float* Vg = c.SL(l, S_VGIN);
+    float* ua = c.SL(l, S_UA);
+    float* ub = c.SL(l, S_UB);
+    float* T31 = c.SL(l, S_T31);
+    SGRL_TRY(zero_ws(c, W_DF1));
+    SGRL_TRY(zero_ws(c, W_DF2));
+    // LN2 and f = linear2(relu(linear1(u')))/F2
+    SGRL_TRY(layernorm_bwd(c, c.W(W_DH), 128, nullptr, 0, c.SL(l, S_X2), 128, c.SL(l, S_ST2), lp[L_N2_W], lp[L_N2_B], c.W(W_DX), 128));
+    SGRL_TRY(block_copy(c, c.W(W_DFF), 128, zW, c.W(W_DX), 128, zW, T, 128, 0));
+    SGRL_TRY(rowdiv_bwd(c, c.W(W_DFF), 128, c.SL(l, S_FF), 128, c.SL(l, S_F2), c.W(W_DF2), 128, 1.f, 0));
+    if (wg) {
+      SGRL_TRY(run_gemm(c, wgrad(c, c.W(W_DFF), 128, T31 + 256, 512, zS, lp[L_L2_W], 256, T, 128, 256)));
+      SGRL_TRY(colsum(c, c.W(W_DFF), 128, lp[L_L2_B], T, 128));
+    }
+    g = dgrad(c, c.W(W_DFF), 128, lp[L_L2_W], 256, c.W(W_DT31) + 256, 512, T, 128, 256);
+    g.mask = T31 + 256; g.zsMask = zS; g.ldmask = 512;
+    SGRL_TRY(run_gemm(c, g));
+    // Vg' = Vg + dV + linear5([g_proj3(dV)|gd] . M)
+    g = dgrad(c, c.W(W_DVG), 128, lp[L_L5_W], 32, c.W(W_DR), 32, T3, 128, 32);
+    SGRL_TRY(run_gemm(c, g));
+    if (wg) SGRL_TRY(run_gemm(c, wgrad(c, c.W(W_DVG), 128, c.SL(l, S_R), 32, zS, lp[L_L5_W], 32, T3, 128, 32)));
+    matapply_bwd_kernel<<<dim3(grid_for_warps(T), c.nb), 256, 0, st>>>(c.W(W_DR), c.SL(l, S_Z3), c.SL(l, S_MM), c.SL(l, S_F2), zS,
+                                                                       c.W(W_DZ3), c.W(W_DT4), c.W(W_DF2), zW, T);
+    SGRL_LAUNCH_OK();
+    if (wg) {
+      SGRL_TRY(run_gemm(c, wgrad(c, c.W(W_DT4), 1024, T31, 512, zS, lp[L_L4_W], 256, T, 1024, 256)));
+      SGRL_TRY(colsum(c, c.W(W_DT4), 1024, lp[L_L4_B], T, 1024));
+    }
+    g = dgrad(c, c.W(W_DT4), 1024, lp[L_L4_W], 256, c.W(W_DT31), 512, T, 1024, 256);
+    g.mask = T31; g.zsMask = zS; g.ldmask = 512;
+    SGRL_TRY(run_gemm(c, g));
+    // [linear3 | linear1](u')
+    if (wg) {
+      SGRL_TRY(run_gemm(c, wgrad(c, c.W(W_DT31), 512, ub, 256, zS, lp[L_L3_W], 256, T, 512, 256)));
+      SGRL_TRY(colsum(c, c.W(W_DT31), 512, lp[L_L3_B], T, 512));
+    }
+    g = dgrad(c, c.W(W_DT31), 512, lp[L_L3_W], 256, c.W(W_DUB), 256, T, 512, 256);
+    SGRL_TRY(run_gemm(c, g));
+    // u'[:, :128] = linear_g2(relu(linear_g1(vec G2)))
+    if (wg) {
+      SGRL_TRY(run_gemm(c, wgrad(c, c.W(W_DUB), 256, c.SL(l, S_A2), 256, zS, lp[L_FG2_W], 256, T, 128, 256)));
+      SGRL_TRY(colsum(c, c.W(W_DUB), 256, lp[L_FG2_B], T, 128));
+    }
+    g = dgrad(c, c.W(W_DUB), 256, lp[L_FG2_W], 256, c.W(W_DA), 256, T, 128, 256);
+    g.mask = c.SL(l, S_A2); g.zsMask = zS; g.ldmask = 256;
+    SGRL_TRY(run_gemm(c, g));
+    if (wg) {
+      SGRL_TRY(run_gemm(c, wgrad(c, c.W(W_DA), 256, c.SL(l, S_G2), 1024, zS, lp[L_FG1_W], 1024, T, 256, 1024)));
+      SGRL_TRY(colsum(c, c.W(W_DA), 256, lp[L_FG1_B], T, 256));
+    }
+    g = dgrad(c, c.W(W_DA), 256, lp[L_FG1_W], 1024, c.W(W_DG), 1024, T, 256, 1024);
+    SGRL_TRY(run_gemm(c, g));
+    SGRL_TRY(inv_feature_bwd(c.W(W_DG), c.W(W_DF2), c.SL(l, S_Z2), c.SL(l, S_F2), c.W(W_DZ2), zS, zW, T, c.nb, st));
+    // d(dV) = dVg' + dZ2[:, :30] g_proj2 + dZ3[:, :30] g_proj3
+    g = dgrad(c, c.W(W_DZ2), 32, lp[L_GP2], 128, c.W(W_DDV), 128, T3, NPJ, 128);
+    g.res1 = c.W(W_DVG); g.zsR1 = zW; g.ldr1 = 128;
+    SGRL_TRY(run_gemm(c, g));
+    g = dgrad(c, c.W(W_DZ3), 32, lp[L_GP3], 128, c.W(W_DDV), 128, T3, NPJ, 128); g.accumulate = 1;
+    SGRL_TRY(run_gemm(c, g));
+    if (wg) {
+      SGRL_TRY(run_gemm(c, wgrad(c, c.W(W_DZ2), 32, c.SL(l, S_DV), 128, zS, lp[L_GP2], 128, T3, NPJ, 128)));
+      SGRL_TRY(run_gemm(c, wgrad(c, c.W(W_DZ3), 32, c.SL(l, S_DV), 128, zS, lp[L_GP3], 128, T3, NPJ, 128)));
+    }
+    // dV = g_out(og)
+    if (wg) SGRL_TRY(run_gemm(c, wgrad(c, c.W(W_DDV), 128, c.SL(l, S_OG), 256, zS, lp[L_GO_W], 256, T3, 128, 256)));
+    g = dgrad(c, c.W(W_DDV), 128, lp[L_GO_W], 256, c.W(W_DOG), 256, T3, 128, 256);
+    SGRL_TRY(run_gemm(c, g));
+    // LN1: dy = dx2 (residual of LN2) + du'[:, 128:]
+    SGRL_TRY(layernorm_bwd(c, c.W(W_DX), 128, c.W(W_DUB) + 128, 256, c.SL(l, S_X1), 128, c.SL(l, S_ST1), lp[L_N1_W], lp[L_N1_B], c.W(W_DH), 128));
+    // dh = ng_out(o)
+    if (wg) {
+      SGRL_TRY(run_gemm(c, wgrad(c, c.W(W_DH), 128, c.SL(l, S_O), 256, zS, lp[L_NGO_W], 256, T, 128, 256)));
+      SGRL_TRY(colsum(c, c.W(W_DH), 128, lp[L_NGO_B], T, 128));
+    }
+    g = dgrad(c, c.W(W_DH), 128, lp[L_NGO_W], 256, c.W(W_DO), 256, T, 128, 256);
+    SGRL_TRY(run_gemm(c, g));
+    SGRL_TRY(attention_bwd(c.SL(l, S_QKV), c.SL(l, S_VGP), c.S(T_GD), c.SL(l, S_P), zS, c.W(W_DO), c.W(W_DOG), c.W(W_DQKV), c.W(W_DVGP), zW,
+                           (l == 0 && wg) ? c.Gr(Y.gp[G_REL_W]) : nullptr, c.zsG, c.gr, c.nb, st));
+    // vg = vg_proj(Vg): dVg(in) = dVg' + dvg vg_proj
+    if (wg) SGRL_TRY(run_gemm(c, wgrad(c, c.W(W_DVGP), 252, Vg, 128, zS, lp[L_VG_W], 128, T3, 252, 128)));
+    g = dgrad(c, c.W(W_DVGP), 252, lp[L_VG_W], 128, c.W(W_DVG), 128, T3, 252, 128); g.accumulate = 1;
+    SGRL_TRY(run_gemm(c, g));
+    // q|k|v = (W u + b)/F1 (q also * scale)
+    SGRL_TRY(rowdiv_bwd(c, c.W(W_DQKV), 768, c.SL(l, S_QKV), 768, c.SL(l, S_F1), c.W(W_DF1), 768, QSCALE, 256));
+    if (wg) {
+      SGRL_TRY(run_gemm(c, wgrad(c, c.W(W_DQKV), 768, ua, 256, zS, lp[L_Q_W], 256, T, 768, 256)));
+      SGRL_TRY(colsum(c, c.W(W_DQKV), 768, lp[L_Q_B], T, 768));
+    }
+    g = dgrad(c, c.W(W_DQKV), 768, lp[L_Q_W], 256, c.W(W_DUA), 256, T, 768, 256);
+    SGRL_TRY(run_gemm(c, g));
+    // u[:, :128] = linear_g2(relu(linear_g1(vec G1)))
+    if (wg) {
+      SGRL_TRY(run_gemm(c, wgrad(c, c.W(W_DUA), 256, c.SL(l, S_A1), 256, zS, lp[L_G2_W], 256, T, 128, 256)));
+      SGRL_TRY(colsum(c, c.W(W_DUA), 256, lp[L_G2_B], T, 128));
+    }
+    g = dgrad(c, c.W(W_DUA), 256, lp[L_G2_W], 256, c.W(W_DA), 256, T, 128, 256);
+    g.mask = c.SL(l, S_A1); g.zsMask = zS; g.ldmask = 256;
+    SGRL_TRY(run_gemm(c, g));
+    if (wg) {
+      SGRL_TRY(run_gemm(c, wgrad(c, c.W(W_DA), 256, c.SL(l, S_G1), 1024, zS, lp[L_G1_W], 1024, T, 256, 1024)));
+      SGRL_TRY(colsum(c, c.W(W_DA), 256, lp[L_G1_B], T, 256));
+    }
+    g = dgrad(c, c.W(W_DA), 256, lp[L_G1_W], 1024, c.W(W_DG), 1024, T, 256, 1024);
+    SGRL_TRY(run_gemm(c, g));
+    SGRL_TRY(inv_feature_bwd(c.W(W_DG), c.W(W_DF1), c.SL(l, S_Z1), c.SL(l, S_F1), c.W(W_DZ1), zS, zW, T, c.nb, st));
+    if (wg) SGRL_TRY(run_gemm(c, wgrad(c, c.W(W_DZ1), 32, Vg, 128, zS, lp[L_GPROJ], 128, T3, NPJ, 128)));
+    g = dgrad(c, c.W(W_DZ1), 32, lp[L_GPROJ], 128, c.W(W_DVG), 128, T3, NPJ, 128); g.accumulate = 1;
+    SGRL_TRY(run_gemm(c, g));
+    // dh(in) = dx1 + du[:, 128:]
+    SGRL_TRY(block_copy(c, c.W(W_DH), 128, zW, c.W(W_DUA) + 128, 256, zW, T, 128, 1));
+  }
+  // embedding
+  if (wg) {
+    g = wgrad(c, c.W(W_DVG), 128, c.S(T_V0), 8, zS, Y.gp[G_GENC_W], GN, T3, 128, GN); g.alpha = SQRT_D;
+    SGRL_TRY(run_gemm(c, g));
+    g = wgrad(c, c.W(W_DH), 128, c.S(T_SH), KS, zS, Y.gp[G_ENC_W], ng, T, 128, ng); g.alpha = SQRT_D;
+    SGRL_TRY(run_gemm(c, g));
+    SGRL_TRY(colsum(c, c.W(W_DH), 128, Y.gp[G_ENC_B], T, 128, SQRT_D));
+    int gx = ceil_div(T, 64); if (gx > NUM_SMS) gx = NUM_SMS; if (gx < 1) gx = 1;
+    pos_embed_bwd_kernel<<<dim3(gx, c.nb), 128, 0, st>>>(c.W(W_DH), 128, zW, c.rank3, c.Gr(Y.gp[G_POS0]), c.Gr(Y.gp[G_POS1]), c.Gr(Y.gp[G_POS2]), c.zsG, T);
+    SGRL_LAUNCH_OK();
+  }
+  if (dact) {   // + sqrt(128) * dh0 . encoder.weight[:, 17:20]
+    SGRL_CHECK(c.kind == CRITIC, "d/d(action) only exists for critics");
+    g = dgrad(c, c.W(W_DH), 128, Y.gp[G_ENC_W] + 17, ng, dact, 3, T, 128, 3);
+    g.zsC = zsDact; g.alpha = SQRT_D; g.accumulate = 1;
+    SGRL_TRY(run_gemm(c, g));
+  }
+  return 0;
+}
+
+}  // namespace sgrl

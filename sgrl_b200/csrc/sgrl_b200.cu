@@ -1,0 +1,199 @@
+// C-ABI translation unit of libsgrl_b200.so (see include/sgrl_b200.h).
+#include "../../include/sgrl_b200.h"
+
+#include "net.cuh"
+#include "td3.cuh"
+
+namespace sgrl { thread_local char g_err[512] = ""; }
+using namespace sgrl;
+
+#define ST(s) reinterpret_cast<cudaStream_t>(s)
+
+extern "C" {
+
+int sgrl_version(void) { return 1; }
+const char* sgrl_last_error(void) { return g_err; }
+
+int sgrl_param_count(int kind, int n_layers) {
+  if (n_layers < 1 || n_layers > MAX_LAYERS || (kind != ACTOR && kind != CRITIC)) return fail(-2, "bad kind/n_layers", __FILE__, __LINE__);
+  return enumerate_params(kind, n_layers, nullptr, 0);
+}
+
+int sgrl_param_info(int kind, int n_layers, int index, char* name, int name_cap, int* rows, int* cols, int64_t* offset, int* live) {
+  SGRL_CHECK(n_layers >= 1 && n_layers <= MAX_LAYERS && (kind == ACTOR || kind == CRITIC), "bad kind/n_layers");
+  static thread_local ParamInfo buf[512];
+  const int n = enumerate_params(kind, n_layers, buf, 512);
+  SGRL_CHECK(index >= 0 && index < n && n <= 512, "param index out of range");
+  snprintf(name, name_cap, "%s", buf[index].name);
+  *rows = buf[index].rows; *cols = buf[index].cols; *offset = buf[index].offset; *live = buf[index].live;
+  return 0;
+}
+
+int sgrl_arena_floats(int kind, int n_layers, int64_t* live_floats, int64_t* dead_floats) {
+  SGRL_CHECK(n_layers >= 1 && n_layers <= MAX_LAYERS && (kind == ACTOR || kind == CRITIC), "bad kind/n_layers");
+  NetLayout L = make_layout(kind, n_layers);
+  *live_floats = L.live_floats; *dead_floats = L.dead_floats;
+  return 0;
+}
+
+int64_t sgrl_stash_floats(int kind, int n_layers, int64_t T, int keep) { return make_stash(kind, n_layers, T, keep).total; }
+int64_t sgrl_ws_floats(int64_t T) { return make_ws(T).total; }
+
+int sgrl_stash_info(int kind, int n_layers, int64_t T, int keep, const char* name, int layer, int64_t* offset, int* per_token) {
+  StashLayout S = make_stash(kind, n_layers, T, keep);
+  if (layer >= 0) {
+    SGRL_CHECK(layer < n_layers, "layer out of range");
+    for (int i = 0; i < LS_COUNT; ++i)
+      if (!strcmp(name, layer_stash_names()[i])) { *offset = S.ls[layer][i]; *per_token = layer_stash_sizes()[i]; return 0; }
+  } else {
+    for (int i = 0; i < GS_COUNT; ++i)
+      if (!strcmp(name, global_stash_names()[i])) { *offset = S.gs[i]; *per_token = global_stash_size(kind, i); return 0; }
+  }
+  return fail(-2, "unknown stash buffer", __FILE__, __LINE__);
+}
+
+static int make_ctx(const SgrlNetCall* k, cudaStream_t st, NetCtx& c) {
+  SGRL_CHECK(k != nullptr, "null call");
+  SGRL_CHECK(k->kind == ACTOR || k->kind == CRITIC, "kind must be SGRL_ACTOR or SGRL_CRITIC");
+  SGRL_CHECK(k->n_layers >= 1 && k->n_layers <= MAX_LAYERS, "n_layers out of range");
+  SGRL_CHECK(k->nb >= 1 && k->nb <= 4, "nb out of range");
+  SGRL_CHECK(k->T >= 1 && k->G >= 1, "empty batch");
+  SGRL_CHECK(k->params && k->stash && k->cu_limbs && k->relation && k->rank3, "null device pointer");
+  c.kind = k->kind; c.L = k->n_layers; c.nb = k->nb; c.T = k->T;
+  c.lay = make_layout(k->kind, k->n_layers);
+  c.params = k->params; c.zsP = c.lay.live_floats;
+  c.grads = k->grads; c.zsG = c.lay.live_floats;
+  c.st = make_stash(k->kind, k->n_layers, k->T, k->keep);
+  SGRL_CHECK(k->stash_stride >= c.st.total, "stash_stride smaller than sgrl_stash_floats()");
+  c.stash = k->stash; c.zsS = k->stash_stride;
+  c.wl = make_ws(k->T);
+  c.ws = k->ws; c.zsW = k->ws_stride;
+  c.gr.cu_limbs = k->cu_limbs; c.gr.rel_off = k->rel_off; c.gr.relation = k->relation; c.gr.G = k->G;
+  c.rank3 = k->rank3; c.max_action = k->max_action; c.use_tc = k->use_tc; c.stream = st;
+  return 0;
+}
+
+int sgrl_set_forward(const SgrlNetCall* call, const float* obs, int64_t obs_stride, const float* act, int64_t act_stride,
+                     float* out, int64_t out_stride, sgrl_stream_t stream) {
+  NetCtx c;
+  SGRL_TRY(make_ctx(call, ST(stream), c));
+  SGRL_CHECK(obs != nullptr, "null obs");
+  return net_forward(c, obs, obs_stride, act, act_stride, out, out_stride);
+}
+
+int sgrl_set_backward(const SgrlNetCall* call, const float* dout, int64_t dout_stride, int need_wgrad, float* dact,
+                      int64_t dact_stride, sgrl_stream_t stream) {
+  NetCtx c;
+  SGRL_TRY(make_ctx(call, ST(stream), c));
+  SGRL_CHECK(call->keep == 1, "backward needs a forward that ran with keep=1");
+  SGRL_CHECK(call->ws != nullptr && call->ws_stride >= c.wl.total, "workspace missing or smaller than sgrl_ws_floats()");
+  SGRL_CHECK(dout != nullptr, "null dout");
+  return net_backward(c, dout, dout_stride, need_wgrad, dact, dact_stride);
+}
+
+int sgrl_inv_feature_fwd(const float* X, const float* v0, const float* gd, const float* P1, const float* P2, float* Z, float* Z2,
+                         float* G, float* F, int T, sgrl_stream_t stream) {
+  SGRL_CHECK(X && gd && P1 && Z && G && F, "null pointer");
+  SGRL_CHECK((P2 == nullptr) == (Z2 == nullptr), "P2 and Z2 go together");
+  FeatFwdP f{};
+  f.Xg = X; f.V0 = v0; f.gd = gd; f.P1 = P1; f.P2 = P2; f.Z = Z; f.Z2 = Z2; f.G = G; f.Fn = F; f.T = T; f.nb = 1; f.head = v0 != nullptr;
+  return inv_feature_fwd(f, ST(stream));
+}
+
+int sgrl_inv_feature_bwd(const float* dG, const float* dF, const float* Z, const float* F, float* dZ, int T, sgrl_stream_t stream) {
+  SGRL_CHECK(dG && dF && Z && F && dZ, "null pointer");
+  return inv_feature_bwd(dG, dF, Z, F, dZ, 0, 0, T, 1, ST(stream));
+}
+
+int sgrl_attention_fwd(const float* qkv, const float* vgp, const float* gd, const float* rel_w, const float* rel_b,
+                       const int32_t* cu_limbs, const int32_t* rel_off, const float* relation, int G, float* o, float* og, float* p,
+                       sgrl_stream_t stream) {
+  SGRL_CHECK(qkv && vgp && gd && cu_limbs && o && og && p, "null pointer");
+  SGRL_CHECK((rel_w == nullptr) || (rel_b && relation), "bias needs rel_b and relation");
+  AttnGraphs gr{cu_limbs, rel_off, relation, G};
+  return attention_fwd(qkv, vgp, gd, o, og, p, 0, rel_w, rel_b, 0, gr, 1, ST(stream));
+}
+
+int sgrl_attention_bwd(const float* qkv, const float* vgp, const float* gd, const float* p, const float* d_o, const float* d_og,
+                       const int32_t* cu_limbs, const int32_t* rel_off, const float* relation, int G, float* dqkv, float* dvgp,
+                       float* drel_w, sgrl_stream_t stream) {
+  SGRL_CHECK(qkv && vgp && gd && p && d_o && d_og && cu_limbs && dqkv && dvgp, "null pointer");
+  AttnGraphs gr{cu_limbs, rel_off, relation, G};
+  return attention_bwd(qkv, vgp, gd, p, 0, d_o, d_og, dqkv, dvgp, 0, drel_w, 0, gr, 1, ST(stream));
+}
+
+int sgrl_gemm(const float* A, int lda, int trans_a, const float* B, int ldb, int trans_b, float* C, int ldc, int M, int N, int K,
+              float alpha, const float* bias, const float* rowdiv, int relu, int accumulate, int splitk, int use_tc,
+              sgrl_stream_t stream) {
+  SGRL_CHECK(A && B && C, "null pointer");
+  GemmP g = gemm_defaults();
+  g.A = A; g.lda = lda; g.transA = trans_a; g.B = B; g.ldb = ldb; g.transB = trans_b; g.C = C; g.ldc = ldc;
+  g.M = M; g.N = N; g.K = K; g.alpha = alpha; g.bias = bias; g.rowdiv = rowdiv; g.relu = relu; g.accumulate = accumulate;
+  g.splitk = splitk < 1 ? 1 : splitk;
+  if (use_tc) {
+    SGRL_CHECK(gemm_tc_eligible(g), "shape/epilogue not eligible for the tcgen05 path");
+    return gemm_tc(g, ST(stream));
+  }
+  return gemm_simt(g, ST(stream));
+}
+
+int sgrl_td3_smooth_action(const float* pi_target, const float* noise, float* next_action, float noise_clip, float max_action,
+                           int64_t n, sgrl_stream_t stream) {
+  SGRL_CHECK(pi_target && noise && next_action, "null pointer");
+  td3_smooth_action_kernel<<<grid_for_flat(n * 4), 256, 0, ST(stream)>>>(pi_target, noise, next_action, noise_clip, max_action, n);
+  SGRL_LAUNCH_OK();
+  return 0;
+}
+
+int sgrl_td3_critic_loss(const float* q1, const float* q2, const float* tq1, const float* tq2, const float* reward, const float* done,
+                         const int32_t* tok_graph, float* target, float* dq1, float* dq2, float* loss, float discount,
+                         float reward_scale, int T, sgrl_stream_t stream) {
+  SGRL_CHECK(q1 && q2 && tq1 && tq2 && reward && done && tok_graph && target && dq1 && dq2 && loss, "null pointer");
+  int gx = ceil_div(T, 256); if (gx > NUM_SMS) gx = NUM_SMS;
+  td3_critic_loss_kernel<<<gx, 256, 0, ST(stream)>>>(q1, q2, tq1, tq2, reward, done, tok_graph, target, dq1, dq2, loss, discount, reward_scale, T);
+  SGRL_LAUNCH_OK();
+  return 0;
+}
+
+int sgrl_td3_actor_loss(const float* q1, float* dq1, float* loss, int T, sgrl_stream_t stream) {
+  SGRL_CHECK(q1 && dq1 && loss, "null pointer");
+  int gx = ceil_div(T, 256); if (gx > NUM_SMS) gx = NUM_SMS;
+  td3_actor_loss_kernel<<<gx, 256, 0, ST(stream)>>>(q1, dq1, loss, T);
+  SGRL_LAUNCH_OK();
+  return 0;
+}
+
+int sgrl_sumsq(const float* g, int64_t n, float* out, sgrl_stream_t stream) {
+  SGRL_CHECK(g && out, "null pointer");
+  SGRL_CHECK(aligned16(g), "gradient arena must be 16-byte aligned");
+  sumsq_kernel<<<grid_for_flat(n), 256, 0, ST(stream)>>>(g, n, out);
+  SGRL_LAUNCH_OK();
+  return 0;
+}
+
+int sgrl_adam_clip(float* p, const float* g, float* m, float* v, int64_t n, const float* sumsq, const int32_t* step, float lr,
+                   float beta1, float beta2, float eps, float max_norm, float grad_scale, sgrl_stream_t stream) {
+  SGRL_CHECK(p && g && m && v && sumsq && step, "null pointer");
+  SGRL_CHECK((n & 3) == 0 && aligned16(p) && aligned16(g) && aligned16(m) && aligned16(v), "arenas must be 16-byte aligned, n % 4 == 0");
+  AdamCfg c{lr, beta1, beta2, eps, max_norm, grad_scale};
+  adam_clip_kernel<<<grid_for_flat(n), 256, 0, ST(stream)>>>(p, g, m, v, n, sumsq, step, c);
+  SGRL_LAUNCH_OK();
+  return 0;
+}
+
+int sgrl_bump_step(int32_t* step, sgrl_stream_t stream) {
+  SGRL_CHECK(step, "null pointer");
+  bump_step_kernel<<<1, 1, 0, ST(stream)>>>(step);
+  SGRL_LAUNCH_OK();
+  return 0;
+}
+
+int sgrl_polyak(float* target, const float* source, int64_t n, float tau, sgrl_stream_t stream) {
+  SGRL_CHECK(target && source, "null pointer");
+  SGRL_CHECK((n & 3) == 0 && aligned16(target) && aligned16(source), "arenas must be 16-byte aligned, n % 4 == 0");
+  polyak_kernel<<<grid_for_flat(n), 256, 0, ST(stream)>>>(target, source, n, tau);
+  SGRL_LAUNCH_OK();
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,142 @@
+// K5/K6 — TD3 glue and the fused optimizer pass (src/agent.py:127-187, functional.py:7-10).
+#pragma once
+#include "common.cuh"
+
+namespace sgrl {
+
+// next_action = clamp(pi_target(s') + clamp(noise, +-c), +-max_action)        agent.py:128-133
+__global__ void td3_smooth_action_kernel(const float* __restrict__ a, const float* __restrict__ noise, float* __restrict__ out,
+                                         float noise_clip, float max_action, long long n) {
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += gridDim.x * 256LL) {
+    const float nz = fminf(fmaxf(noise[i], -noise_clip), noise_clip);
+    out[i] = fminf(fmaxf(a[i] + nz, -max_action), max_action);
+  }
+}
+
+// target[t] = r[g(t)] * reward_scale + (1 - done[g(t)]) * discount * min(q1t[t], q2t[t])   agent.py:136-139
+// dq1 = 2 (q1 - target)/T, dq2 likewise; loss += sum((q1-y)^2 + (q2-y)^2)/T               agent.py:146-148
+__global__ void __launch_bounds__(256) td3_critic_loss_kernel(
+    const float* __restrict__ q1, const float* __restrict__ q2, const float* __restrict__ tq1, const float* __restrict__ tq2,
+    const float* __restrict__ reward, const float* __restrict__ done, const int* __restrict__ tok_graph,
+    float* __restrict__ target, float* __restrict__ dq1, float* __restrict__ dq2, float* __restrict__ loss,
+    float discount, float reward_scale, int T) {
+  __shared__ float red[8];
+  float acc = 0.f;
+  const float invT = 1.f / (float)T;
+  for (int t = blockIdx.x * 256 + threadIdx.x; t < T; t += gridDim.x * 256) {
+    const int g = tok_graph[t];
+    const float y = reward[g] * reward_scale + (1.f - done[g]) * discount * fminf(tq1[t], tq2[t]);
+    target[t] = y;
+    const float e1 = q1[t] - y, e2 = q2[t] - y;
+    dq1[t] = 2.f * e1 * invT; dq2[t] = 2.f * e2 * invT;
+    acc += e1 * e1 + e2 * e2;
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    float s = red[threadIdx.x];
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) s += __shfl_xor_sync(0xffu, s, o);
+    if (threadIdx.x == 0) atomicAdd(loss, s * invT);
+  }
+}
+
+// actor loss = -mean(Q1):  dq = -1/T, loss += -sum(q)/T                                    agent.py:167
+__global__ void __launch_bounds__(256) td3_actor_loss_kernel(const float* __restrict__ q1, float* __restrict__ dq, float* __restrict__ loss, int T) {
+  __shared__ float red[8];
+  float acc = 0.f;
+  const float invT = 1.f / (float)T;
+  for (int t = blockIdx.x * 256 + threadIdx.x; t < T; t += gridDim.x * 256) { dq[t] = -invT; acc += q1[t]; }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    float s = red[threadIdx.x];
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) s += __shfl_xor_sync(0xffu, s, o);
+    if (threadIdx.x == 0) atomicAdd(loss, -s * invT);
+  }
+}
+
+// sum of squares of a flat gradient buffer -> *out (pre-zeroed)                            clip_grad_norm_, agent.py:152-155
+__global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, long long n, float* __restrict__ out) {
+  __shared__ float red[8];
+  float acc = 0.f;
+  const long long n4 = n >> 2;
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n4; i += gridDim.x * 256LL) {
+    const float4 v = ldg4(g + i * 4);
+    acc += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) { const float v = g[n4 * 4 + threadIdx.x]; acc += v * v; }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    float s = red[threadIdx.x];
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) s += __shfl_xor_sync(0xffu, s, o);
+    if (threadIdx.x == 0) atomicAdd(out, s);
+  }
+}
+
+struct AdamCfg { float lr, beta1, beta2, eps, max_norm; float grad_scale; };
+
+// One pass over the live arena: clip coefficient from the global norm, Adam moment update,
+// parameter step.  `step` lives on the device so the pass can be replayed from a CUDA graph.
+//   coef = min(1, max_norm / (||g|| + 1e-6))     (torch.nn.utils.clip_grad_norm_)
+//   m = m + (1-b1)(g - m);  v = b2 v + (1-b2) g^2;  p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps)
+// grad_scale pre-multiplies g (1/world_size after a sum all-reduce).
+__global__ void __launch_bounds__(256) adam_clip_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                        float* __restrict__ v, long long n, const float* __restrict__ sumsq,
+                                                        const int* __restrict__ step, AdamCfg c) {
+  __shared__ float sh[3];
+  if (threadIdx.x == 0) {
+    const float nrm = sqrtf(*sumsq) * c.grad_scale;
+    float coef = 1.f;
+    if (c.max_norm > 0.f) { coef = c.max_norm / (nrm + 1e-6f); coef = coef > 1.f ? 1.f : coef; }
+    const double t = (double)(*step);
+    sh[0] = coef * c.grad_scale;
+    sh[1] = (float)((double)c.lr / (1.0 - pow((double)c.beta1, t)));
+    sh[2] = (float)sqrt(1.0 - pow((double)c.beta2, t));
+  }
+  __syncthreads();
+  const float gs = sh[0], step_size = sh[1], bc2s = sh[2];
+  const long long n4 = n >> 2;
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n4; i += gridDim.x * 256LL) {
+    float4 pv = *reinterpret_cast<float4*>(p + i * 4);
+    const float4 gv = ldg4(g + i * 4);
+    float4 mv = *reinterpret_cast<float4*>(m + i * 4), vv = *reinterpret_cast<float4*>(v + i * 4);
+    float* pp = &pv.x; const float* gg = &gv.x; float* mm = &mv.x; float* vq = &vv.x;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float gk = gg[k] * gs;
+      mm[k] = mm[k] + (gk - mm[k]) * (1.f - c.beta1);
+      vq[k] = vq[k] * c.beta2 + (1.f - c.beta2) * gk * gk;
+      pp[k] -= step_size * (mm[k] / (sqrtf(vq[k]) / bc2s + c.eps));
+    }
+    stg4(p + i * 4, pv); stg4(m + i * 4, mv); stg4(v + i * 4, vv);
+  }
+}
+
+__global__ void bump_step_kernel(int* step) { *step += 1; }
+
+// theta_t <- tau*theta + (1-tau)*theta_t                                                    functional.py:7-10
+__global__ void __launch_bounds__(256) polyak_kernel(float* __restrict__ tgt, const float* __restrict__ src, long long n, float tau) {
+  const long long n4 = n >> 2;
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n4; i += gridDim.x * 256LL) {
+    float4 t = *reinterpret_cast<float4*>(tgt + i * 4);
+    const float4 s = ldg4(src + i * 4);
+    t.x = tau * s.x + (1.f - tau) * t.x; t.y = tau * s.y + (1.f - tau) * t.y;
+    t.z = tau * s.z + (1.f - tau) * t.z; t.w = tau * s.w + (1.f - tau) * t.w;
+    stg4(tgt + i * 4, t);
+  }
+}
+
+inline int grid_for_flat(long long n) {
+  long long b = (n / 4 + 255) / 256;
+  if (b > 8LL * NUM_SMS) b = 8LL * NUM_SMS;
+  return b < 1 ? 1 : (int)b;
+}
+
+}  // namespace sgrl

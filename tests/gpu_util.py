@@ -1,0 +1,57 @@
+"""Helpers for the -m gpu parity tests (CUDA path through the C ABI vs the oracle)."""
+import torch
+
+from oracle import ref_loader, set_oracle as O
+import parity
+
+
+def make_modules(seed=parity.WEIGHT_SEED, use_tc=0):
+    from sgrl_b200.modules import SEPolicy, SECritic
+    args = ref_loader.default_args()
+    actor = SEPolicy(41, 3, 32, 100, 1.0, None, False, False, False, args)
+    critic = SECritic(41, 3, 32, 100, None, False, False, False, args)
+    pa = {"actor." + k: v for k, v in O.synth_params("actor", seed).items()}
+    pc = {"critic1." + k: v for k, v in O.synth_params("critic", seed + 1).items()}
+    pc.update({"critic2." + k: v for k, v in O.synth_params("critic", seed + 2).items()})
+    actor.load_state_dict(pa)
+    critic.load_state_dict(pc)
+    actor.use_tc = critic.use_tc = use_tc
+    return actor, critic, pa, pc
+
+
+def to_cuda(d):
+    return {k: (v.cuda() if torch.is_tensor(v) else [t.cuda() for t in v] if isinstance(v, list) and v and torch.is_tensor(v[0]) else v) for k, v in d.items()}
+
+
+def stash_view(mod, stash, tb, nb, z, name, layer=-1, keep=1):
+    """(T, per_token) view of a named stash buffer of net instance z."""
+    from sgrl_b200 import _lib
+    off, per = _lib.stash_info(mod._kind, mod._n_layers, tb.T, keep, name, layer)
+    stride = stash.numel() // nb
+    return stash[z * stride + off: z * stride + off + per * tb.T].view(tb.T, per)
+
+
+def compare_stash(mod, stash, tb, nb, z, trace, n_layers=3, tol=2e-5, skip=()):
+    """Return [(name, rel_err)] of every traced intermediate vs the CUDA stash."""
+    out = []
+    for key, ref in trace.items():
+        if "." in key:
+            l, name = key.split(".")
+            l = int(l)
+        else:
+            l, name = -1, key
+        if name in skip:
+            continue
+        got = stash_view(mod, stash, tb, nb, z, name, l)
+        ref = ref.detach()
+        if name == "P":     # (B,N,H,N) -> (T,H,16) zero padded
+            B, N = ref.shape[0], ref.shape[1]
+            pad = torch.zeros(B, N, 2, 16, device=ref.device, dtype=ref.dtype)
+            pad[..., :N] = ref
+            ref = pad
+        if name == "UA" and False:
+            pass
+        ref = ref.reshape(tb.T, -1).to(got.device)
+        assert ref.shape == got.shape, (key, ref.shape, got.shape)
+        out.append((key, parity.rel_err(got, ref)))
+    return out
