@@ -1,0 +1,112 @@
+"""Agent.update / select_action on the GPU vs the TD3 oracle (torch Adam + clip_grad_norm_)
+and vs the reference's recorded update steps."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_loader, set_oracle as O
+from sgrl_b200 import graph as G, morphologies as M, synth
+import parity
+
+pytestmark = pytest.mark.gpu
+
+
+def make_agent(use_tc=0):
+    from sgrl_b200.agent import Agent
+    ag = Agent(ref_loader.default_args())
+    a = O.synth_params("actor", parity.WEIGHT_SEED)
+    c1 = O.synth_params("critic", parity.WEIGHT_SEED + 1)
+    c2 = O.synth_params("critic", parity.WEIGHT_SEED + 2)
+    sd = {}
+    for pre in ("actor.actor.", "actor_target.actor."):
+        sd.update({pre + k: v for k, v in a.items()})
+    for pre in ("critic.", "critic_target."):
+        sd.update({pre + "critic1." + k: v for k, v in c1.items()})
+        sd.update({pre + "critic2." + k: v for k, v in c2.items()})
+    ag.load_state_dict(sd)
+    for m in (ag.actor, ag.actor_target, ag.critic, ag.critic_target):
+        m.use_tc = use_tc
+    pa = {"actor." + k: v for k, v in a.items()}
+    pc = {"critic1." + k: v for k, v in c1.items()}
+    pc.update({"critic2." + k: v for k, v in c2.items()})
+    return ag, pa, pc
+
+
+def agent_state(ag):
+    return {k: v.detach().clone() for k, v in ag.state_dict().items()}
+
+
+def test_state_dict_has_reference_keys():
+    ag, _, _ = make_agent()
+    gold = parity.load_golden()
+    assert list(ag.state_dict().keys()) == [str(s) for s in gold["state_names"]]
+    assert len(ag.state_dict()) == 818
+
+
+@pytest.mark.parametrize("name,B", [parity.CASES[1], parity.CASES[3]])
+def test_update_matches_reference_golden(name, B):
+    gold = parity.load_golden()
+    ag, _, _ = make_agent()
+    g = parity.golden_graph(gold, name, M.ALL[name], device="cuda")
+    b = parity.golden_batch(gold, name, device="cuda")
+    ag.change_morphology(g)
+    names = [str(s) for s in gold["state_names"]]
+    for it in range(2):
+        before = agent_state(ag)
+        ld = ag.update(b, it, noise=torch.tensor(gold[name + "/noise"][it], device="cuda"))
+        want = float(gold[name + f"/upd{it}/critic_loss"])
+        assert abs(ld["loss/critic_loss"].item() - want) < 1e-4 * want
+        assert ("loss/actor_loss" in ld) == (it == 0)
+        if it == 0:
+            wa = float(gold[name + "/upd0/actor_loss"])
+            assert abs(ld["loss/actor_loss"].item() - wa) < 1e-4 * abs(wa)
+        assert abs(ld["misc/train_reward_mean"] - float(gold[name + f"/upd{it}/reward_mean"])) < 1e-6
+        assert abs(ld["misc/train_reward_var"] - float(gold[name + f"/upd{it}/reward_var"])) < 1e-6
+        after = agent_state(ag)
+        step = {n: after[n] - before[n] for n in names}
+        parity.check_summary(parity.summarize(step), gold[name + f"/upd{it}/step"], rtol=2e-3, floor=1e-3, what=f"step it={it}")
+    with torch.no_grad():
+        assert parity.rel_err(ag.actor(b["obs"]), gold[name + "/actions_after"]) < parity.RTOL
+        assert parity.rel_err(ag.critic_target.Q1(b["obs"], b["action"]), gold[name + "/tq1_after"]) < parity.RTOL
+
+
+def test_four_updates_match_oracle_humanoid_b100():
+    """k=4 consecutive updates at a BASELINE size vs the oracle TD3 step run on the same GPU in fp64."""
+    ag, pa, pc = make_agent()
+    par = M.ALL["3d_humanoid_9_full"]
+    g = G.build_graph(par, device="cuda")
+    ag.change_morphology(g)
+    B = 100
+    g64 = dict(g); g64["relation"] = g["relation"].double()
+    td3 = O.TD3Oracle({k: v.cuda().double() for k, v in pa.items()}, {k: v.cuda().double() for k, v in pc.items()})
+    for it in range(4):
+        b = {k: v.cuda() for k, v in synth.make_batch(B, len(par), seed=20 + it).items()}
+        noise = torch.randn(B, 27, generator=torch.Generator().manual_seed(it)).cuda() * 0.2
+        ld = ag.update(b, it, noise=noise)
+        ref = td3.update({k: v.double() for k, v in b.items()}, it, noise.double(), g64)
+        assert abs(ld["loss/critic_loss"].item() - ref["loss/critic_loss"].item()) < 1e-4 * ref["loss/critic_loss"].item()
+        assert parity.rel_err(ag._last_target, ref["target_Q"].reshape(-1)) < parity.RTOL
+        if it % 2 == 0:
+            assert abs(ld["loss/actor_loss"].item() - ref["loss/actor_loss"].item()) < 2e-4 * abs(ref["loss/actor_loss"].item())
+    # parameters after 4 steps: compare the accumulated step (theta_4 - theta_0) with the oracle's
+    for mod, ref_p, init in ((ag.critic, td3.critic, pc), (ag.actor, td3.actor, pa), (ag.critic_target, td3.critic_t, pc), (ag.actor_target, td3.actor_t, pa)):
+        num = den = 0.0
+        for k, p in mod.named_parameters():
+            d0 = init[k].cuda().double()
+            num += ((p.double() - d0) - (ref_p[k].detach() - d0)).pow(2).sum().item()
+            den += (ref_p[k].detach() - d0).pow(2).sum().item()
+        assert (num / den) ** 0.5 < 5e-3, (num / den) ** 0.5      # Adam's sign-like steps amplify tiny-gradient noise
+    # optimizer bookkeeping
+    assert int(ag.critic_optimizer.step_count.item()) == 4 and int(ag.actor_optimizer.step_count.item()) == 2
+
+
+def test_select_action_matches_forward():
+    ag, pa, _ = make_agent()
+    par = M.ALL["3d_walker_7_full"]
+    g = G.build_graph(par, device="cuda")
+    ag.change_morphology(g)
+    obs = synth.make_obs(1, len(par), seed=4)[0].numpy().astype(np.float64)
+    a = ag.select_action(obs)
+    assert isinstance(a, np.ndarray) and a.shape == (1, 3 * len(par)) and a.dtype == np.float32
+    ref = O.actor_forward(pa, torch.tensor(obs, dtype=torch.float32)[None], G.build_graph(par))
+    assert parity.rel_err(a, ref) < parity.RTOL
