@@ -34,6 +34,21 @@ __device__ __forceinline__ float warp_max(float v) {
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ void stg4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 
+// 4 consecutive floats with one vector access when (pointer, leading dimension, z-stride) allow it.
+// The decision is taken on the HOST and passed in as a kernel argument: when it is derived from the
+// pointer bits inside the kernel nvcc folds the scalar path away and emits an unconditional 128-bit access.
+inline int host_vec_ok(const void* p, long long ld, long long zs = 0) {
+  return p != nullptr && ((reinterpret_cast<uintptr_t>(p) & 15u) == 0) && ((ld & 3) == 0) && ((zs & 3) == 0);
+}
+__device__ __forceinline__ float4 load4(const float* p, bool vec) {
+  if (vec) return *reinterpret_cast<const float4*>(p);
+  return make_float4(p[0], p[1], p[2], p[3]);
+}
+__device__ __forceinline__ void store4(float* p, float4 v, bool vec) {
+  if (vec) { *reinterpret_cast<float4*>(p) = v; return; }
+  p[0] = v.x; p[1] = v.y; p[2] = v.z; p[3] = v.w;
+}
+
 inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 

@@ -29,6 +29,7 @@ struct GemmP {
   int accumulate;                           // C += v instead of C = v
   int splitk;                               // >1: split K over blockIdx.y, atomicAdd (implies accumulate)
   int nb;                                   // instances (blockIdx.z)
+  int vecA, vecB;                           // set by the launcher: operand rows may be fetched as float4
 };
 
 inline GemmP gemm_defaults() {
@@ -86,8 +87,7 @@ __global__ void __launch_bounds__(G_THREADS) gemm_simt_kernel(GemmP p) {
   const int ktiles = (p.K + GB_K - 1) / GB_K;
   const int per = (ktiles + p.splitk - 1) / p.splitk;
   const int kt0 = blockIdx.y * per, kt1 = min(ktiles, kt0 + per);
-  const bool vecA = ((p.lda & 3) == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0);
-  const bool vecB = ((p.ldb & 3) == 0) && ((reinterpret_cast<uintptr_t>(B) & 15) == 0);
+  const bool vecA = p.vecA != 0, vecB = p.vecB != 0;
   const int tx = tid & 15, ty = tid >> 4;
   float acc[4][4];
 #pragma unroll
@@ -161,7 +161,10 @@ __global__ void __launch_bounds__(G_THREADS) gemm_simt_kernel(GemmP p) {
   }
 }
 
-inline int gemm_simt(const GemmP& p, cudaStream_t st) {
+inline int gemm_simt(const GemmP& p_in, cudaStream_t st) {
+  GemmP p = p_in;
+  p.vecA = host_vec_ok(p.A, p.lda, p.zsA);
+  p.vecB = host_vec_ok(p.B, p.ldb, p.zsB);
   if (p.M <= 0 || p.N <= 0 || p.nb <= 0) return 0;
   SGRL_CHECK(p.K > 0, "gemm: K must be positive");
   SGRL_CHECK(p.splitk >= 1, "gemm: splitk");

@@ -103,15 +103,16 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(
     const float* __restrict__ a, int lda, const float* __restrict__ b, int ldb,
     const float* __restrict__ gamma, const float* __restrict__ beta, long long zsP,
     float* __restrict__ x, float* __restrict__ y, int ldy, float* __restrict__ y2, int ldy2,
-    float* __restrict__ stats, long long zsS, int T) {
+    float* __restrict__ stats, long long zsS, int T, int vflags) {
   const int lane = threadIdx.x & 31, z = blockIdx.y;
   a += z * zsS; if (b) b += z * zsS; if (x) x += z * zsS; y += z * zsS; if (y2) y2 += z * zsS; stats += z * zsS;
   gamma += z * zsP; beta += z * zsP;
   const float4 g = ldg4(gamma + lane * 4), be = ldg4(beta + lane * 4);
+  const bool va = vflags & 1, vb = vflags & 2, vy = vflags & 4, vy2 = vflags & 8;
   for (int t = blockIdx.x * 8 + (threadIdx.x >> 5); t < T; t += gridDim.x * 8) {
-    float4 v = *reinterpret_cast<const float4*>(a + (long long)t * lda + lane * 4);
+    float4 v = load4(a + (long long)t * lda + lane * 4, va);
     if (b) {
-      const float4 w = *reinterpret_cast<const float4*>(b + (long long)t * ldb + lane * 4);
+      const float4 w = load4(b + (long long)t * ldb + lane * 4, vb);
       v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
     }
     if (x) stg4(x + (long long)t * 128 + lane * 4, v);
@@ -120,8 +121,8 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(
     const float var = warp_sum(d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3) * (1.f / 128.f);
     const float rstd = rsqrtf(var + 1e-5f);
     const float4 o = make_float4(d0 * rstd * g.x + be.x, d1 * rstd * g.y + be.y, d2 * rstd * g.z + be.z, d3 * rstd * g.w + be.w);
-    stg4(y + (long long)t * ldy + lane * 4, o);
-    if (y2) stg4(y2 + (long long)t * ldy2 + lane * 4, o);
+    store4(y + (long long)t * ldy + lane * 4, o, vy);
+    if (y2) store4(y2 + (long long)t * ldy2 + lane * 4, o, vy2);
     if (lane == 0) { stats[(long long)t * 2] = mean; stats[(long long)t * 2 + 1] = rstd; }
   }
 }
@@ -131,20 +132,22 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(
     const float* __restrict__ dy1, int ld1, const float* __restrict__ dy2, int ld2,
     const float* __restrict__ x, int ldx, const float* __restrict__ stats, long long zsS,
     const float* __restrict__ gamma, long long zsP,
-    float* __restrict__ dx, int lddx, long long zsW, float* __restrict__ dgamma, float* __restrict__ dbeta, long long zsG, int T) {
+    float* __restrict__ dx, int lddx, long long zsW, float* __restrict__ dgamma, float* __restrict__ dbeta, long long zsG, int T, int vflags) {
   __shared__ float red[2][8][128];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, z = blockIdx.y;
   dy1 += z * zsW; if (dy2) dy2 += z * zsW; dx += z * zsW;
-  x += z * zsS; stats += z * zsS; gamma += z * zsP; dgamma += z * zsG; dbeta += z * zsG;
+  x += z * zsS; stats += z * zsS; gamma += z * zsP;
+  if (dgamma) { dgamma += z * zsG; dbeta += z * zsG; }
   const float4 g = ldg4(gamma + lane * 4);
   float ag[4] = {0, 0, 0, 0}, ab[4] = {0, 0, 0, 0};
+  const bool v1 = vflags & 1, v2 = vflags & 2, vx = vflags & 4, vo = vflags & 8;
   for (int t = blockIdx.x * 8 + warp; t < T; t += gridDim.x * 8) {
-    float4 d = *reinterpret_cast<const float4*>(dy1 + (long long)t * ld1 + lane * 4);
+    float4 d = load4(dy1 + (long long)t * ld1 + lane * 4, v1);
     if (dy2) {
-      const float4 e = *reinterpret_cast<const float4*>(dy2 + (long long)t * ld2 + lane * 4);
+      const float4 e = load4(dy2 + (long long)t * ld2 + lane * 4, v2);
       d.x += e.x; d.y += e.y; d.z += e.z; d.w += e.w;
     }
-    const float4 xv = *reinterpret_cast<const float4*>(x + (long long)t * ldx + lane * 4);
+    const float4 xv = load4(x + (long long)t * ldx + lane * 4, vx);
     const float mean = stats[(long long)t * 2], rstd = stats[(long long)t * 2 + 1];
     const float xh[4] = {(xv.x - mean) * rstd, (xv.y - mean) * rstd, (xv.z - mean) * rstd, (xv.w - mean) * rstd};
     const float dv[4] = {d.x, d.y, d.z, d.w}, gv[4] = {g.x, g.y, g.z, g.w};
@@ -155,8 +158,9 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(
     float4 o;
     o.x = rstd * (gd[0] - s1 - xh[0] * s2); o.y = rstd * (gd[1] - s1 - xh[1] * s2);
     o.z = rstd * (gd[2] - s1 - xh[2] * s2); o.w = rstd * (gd[3] - s1 - xh[3] * s2);
-    stg4(dx + (long long)t * lddx + lane * 4, o);
+    store4(dx + (long long)t * lddx + lane * 4, o, vo);
   }
+  if (!dgamma) return;   // data-only backward
 #pragma unroll
   for (int i = 0; i < 4; ++i) { red[0][warp][lane * 4 + i] = ag[i]; red[1][warp][lane * 4 + i] = ab[i]; }
   __syncthreads();

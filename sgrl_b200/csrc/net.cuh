@@ -107,16 +107,18 @@ inline int block_copy(const NetCtx& c, float* dst, int ldd, long long zsD, const
 }
 inline int layernorm_fwd(const NetCtx& c, const float* a, int lda, const float* b, int ldb, long long g_off, long long b_off,
                          float* x, float* y, int ldy, float* stats) {
+  const int vf = host_vec_ok(a, lda, c.zsS) | (host_vec_ok(b, ldb, c.zsS) << 1) | (host_vec_ok(y, ldy, c.zsS) << 2);
   layernorm_fwd_kernel<<<dim3(grid_for_warps(c.T), c.nb), 256, 0, c.stream>>>(a, lda, b, ldb, c.P(g_off), c.P(b_off), c.zsP, x, y, ldy,
-                                                                              nullptr, 0, stats, c.zsS, c.T);
+                                                                              nullptr, 0, stats, c.zsS, c.T, vf);
   SGRL_LAUNCH_OK();
   return 0;
 }
 inline int layernorm_bwd(const NetCtx& c, const float* dy1, int ld1, const float* dy2, int ld2, const float* x, int ldx,
-                         const float* stats, long long g_off, long long b_off, float* dx, int lddx) {
+                         const float* stats, long long g_off, long long b_off, float* dx, int lddx, bool wg) {
   int gx = grid_for_warps(c.T); if (gx > 2 * NUM_SMS) gx = 2 * NUM_SMS;
+  const int vf = host_vec_ok(dy1, ld1, c.zsW) | (host_vec_ok(dy2, ld2, c.zsW) << 1) | (host_vec_ok(x, ldx, c.zsS) << 2) | (host_vec_ok(dx, lddx, c.zsW) << 3);
   layernorm_bwd_kernel<<<dim3(gx, c.nb), 256, 0, c.stream>>>(dy1, ld1, dy2, ld2, x, ldx, stats, c.zsS, c.P(g_off), c.zsP, dx, lddx, c.zsW,
-                                                             c.Gr(g_off), c.Gr(b_off), c.zsG, c.T);
+                                                             wg ? c.Gr(g_off) : nullptr, wg ? c.Gr(b_off) : nullptr, c.zsG, c.T, vf);
   SGRL_LAUNCH_OK();
   return 0;
 }
@@ -332,7 +334,7 @@ inline int net_backward(const NetCtx& c, const float* dOut, long long zsDo, int 
   SGRL_TRY(run_gemm(c, g));
   if (dact) SGRL_TRY(block_copy(c, dact, 3, zsDact, c.W(W_DSH) + 17, KS, zW, T, 3, 0));
   // final LayerNorm
-  SGRL_TRY(layernorm_bwd(c, c.W(W_DSH) + ng, KS, nullptr, 0, c.S(T_HL), 128, c.S(T_STF), Y.gp[G_NORM_W], Y.gp[G_NORM_B], c.W(W_DH), 128));
+  SGRL_TRY(layernorm_bwd(c, c.W(W_DSH) + ng, KS, nullptr, 0, c.S(T_HL), 128, c.S(T_STF), Y.gp[G_NORM_W], Y.gp[G_NORM_B], c.W(W_DH), 128, wg));
 
   for (int l = c.L - 1; l >= 0; --l) {
     const long long* lp = Y.lp[l];
@@ -343,7 +345,7 @@ inline int net_backward(const NetCtx& c, const float* dOut, long long zsDo, int 
     SGRL_TRY(zero_ws(c, W_DF1));
     SGRL_TRY(zero_ws(c, W_DF2));
     // LN2 and f = linear2(relu(linear1(u')))/F2
-    SGRL_TRY(layernorm_bwd(c, c.W(W_DH), 128, nullptr, 0, c.SL(l, S_X2), 128, c.SL(l, S_ST2), lp[L_N2_W], lp[L_N2_B], c.W(W_DX), 128));
+    SGRL_TRY(layernorm_bwd(c, c.W(W_DH), 128, nullptr, 0, c.SL(l, S_X2), 128, c.SL(l, S_ST2), lp[L_N2_W], lp[L_N2_B], c.W(W_DX), 128, wg));
     SGRL_TRY(block_copy(c, c.W(W_DFF), 128, zW, c.W(W_DX), 128, zW, T, 128, 0));
     SGRL_TRY(rowdiv_bwd(c, c.W(W_DFF), 128, c.SL(l, S_FF), 128, c.SL(l, S_F2), c.W(W_DF2), 128, 1.f, 0));
     if (wg) {
@@ -404,7 +406,7 @@ inline int net_backward(const NetCtx& c, const float* dOut, long long zsDo, int 
     g = dgrad(c, c.W(W_DDV), 128, lp[L_GO_W], 256, c.W(W_DOG), 256, T3, 128, 256);
     SGRL_TRY(run_gemm(c, g));
     // LN1: dy = dx2 (residual of LN2) + du'[:, 128:]
-    SGRL_TRY(layernorm_bwd(c, c.W(W_DX), 128, c.W(W_DUB) + 128, 256, c.SL(l, S_X1), 128, c.SL(l, S_ST1), lp[L_N1_W], lp[L_N1_B], c.W(W_DH), 128));
+    SGRL_TRY(layernorm_bwd(c, c.W(W_DX), 128, c.W(W_DUB) + 128, 256, c.SL(l, S_X1), 128, c.SL(l, S_ST1), lp[L_N1_W], lp[L_N1_B], c.W(W_DH), 128, wg));
     // dh = ng_out(o)
     if (wg) {
       SGRL_TRY(run_gemm(c, wgrad(c, c.W(W_DH), 128, c.SL(l, S_O), 256, zS, lp[L_NGO_W], 256, T, 128, 256)));

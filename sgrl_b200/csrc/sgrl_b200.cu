@@ -191,7 +191,7 @@ int sgrl_bump_step(int32_t* step, sgrl_stream_t stream) {
 int sgrl_polyak(float* target, const float* source, int64_t n, float tau, sgrl_stream_t stream) {
   SGRL_CHECK(target && source, "null pointer");
   SGRL_CHECK((n & 3) == 0 && aligned16(target) && aligned16(source), "arenas must be 16-byte aligned, n % 4 == 0");
-  polyak_kernel<<<grid_for_flat(n), 256, 0, ST(stream)>>>(target, source, n, tau);
+  polyak_kernel<<<grid_for_flat(n), 256, 0, ST(stream)>>>(target, source, n, tau, (float)(1.0 - (double)tau));
   SGRL_LAUNCH_OK();
   return 0;
 }

@@ -122,13 +122,18 @@ __global__ void __launch_bounds__(256) adam_clip_kernel(float* __restrict__ p, c
 __global__ void bump_step_kernel(int* step) { *step += 1; }
 
 // theta_t <- tau*theta + (1-tau)*theta_t                                                    functional.py:7-10
-__global__ void __launch_bounds__(256) polyak_kernel(float* __restrict__ tgt, const float* __restrict__ src, long long n, float tau) {
+// Rounded exactly like the reference's three fp32 tensor ops (mul, mul, add — no FMA contraction):
+// the per-step change tau*(theta-theta_t) ~ 5e-7 is a few ulps of O(1) weights, so op order is visible.
+__global__ void __launch_bounds__(256) polyak_kernel(float* __restrict__ tgt, const float* __restrict__ src, long long n,
+                                                     float tau, float one_minus_tau) {
   const long long n4 = n >> 2;
   for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n4; i += gridDim.x * 256LL) {
     float4 t = *reinterpret_cast<float4*>(tgt + i * 4);
     const float4 s = ldg4(src + i * 4);
-    t.x = tau * s.x + (1.f - tau) * t.x; t.y = tau * s.y + (1.f - tau) * t.y;
-    t.z = tau * s.z + (1.f - tau) * t.z; t.w = tau * s.w + (1.f - tau) * t.w;
+    t.x = __fadd_rn(__fmul_rn(tau, s.x), __fmul_rn(one_minus_tau, t.x));
+    t.y = __fadd_rn(__fmul_rn(tau, s.y), __fmul_rn(one_minus_tau, t.y));
+    t.z = __fadd_rn(__fmul_rn(tau, s.z), __fmul_rn(one_minus_tau, t.z));
+    t.w = __fadd_rn(__fmul_rn(tau, s.w), __fmul_rn(one_minus_tau, t.w));
     stg4(tgt + i * 4, t);
   }
 }
