@@ -1,0 +1,332 @@
+#!/usr/bin/env python
+"""Benchmark of the SET TD3 hot path (BASELINE.json: "SET TD3 update samples/sec and rollout
+limb-tokens/sec at 1/2/4/8 B200").
+
+  python bench.py --gpus N --steps K --warmup W            # our arm (CUDA kernels via the C ABI)
+  python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on the host CPU
+
+A "step" is one `Agent.update` (TD3 update, src/agent.py:117-183) on one synthetic replay
+minibatch of the named morphology (default: 3d_humanoid_9_full, N=9 limbs, B=256 — the batch
+start_humanoid.sh really samples, src/configs/default.py:61); even `it` includes the delayed
+actor step + Polyak, so K is rounded up to an even number.  N>1: one process per GPU (torchrun),
+every rank draws its own minibatch (weak scaling) and the flat gradient arena is all-reduced
+over NCCL before the fused clip+Adam pass.  One JSON line is printed by rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+FLOP_PER_TOKEN_UPDATE = 115.1e6      # SURVEY.md §8d / BASELINE.md §3 (reference-executed work, policy_freq=2 average)
+FLOP_PER_TOKEN_ACTOR_FWD = 10.14e6
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=6)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--morph", default="3d_humanoid_9_full")
+    ap.add_argument("--batch", type=int, default=256)
+    ap.add_argument("--rollout-envs", type=int, default=16384)
+    ap.add_argument("--use-tc", type=int, default=-1, help="1: tcgen05 3xTF32 projections, 0: fp32 SIMT, -1: library default")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-rollout", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "tflops_burst": d["bf16_tflops"], "tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "src": "measured"}
+    return {"hbm_gbs": 6650.0, "tflops_burst": 1590.0, "tflops_sustained": 1400.0, "src": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled every 200 ms during the timed region."""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.lines, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------
+def cpu_reference_rate(morph, batch, budget_s=20.0, steps=None, warmup=1, threads=None):
+    """The reference algorithm (oracle port of Agent.update: torch CPU ops + torch Adam +
+    clip_grad_norm_) timed on this host's cores.  Returns samples/s and a description."""
+    import torch
+    from oracle import set_oracle as O
+    from sgrl_b200 import graph as G, morphologies as M, synth
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    par = M.ALL[morph]
+    g = G.build_graph(par)
+    pa = {"actor." + k: v for k, v in O.synth_params("actor", 11).items()}
+    pc = {"critic1." + k: v for k, v in O.synth_params("critic", 12).items()}
+    pc.update({"critic2." + k: v for k, v in O.synth_params("critic", 13).items()})
+    td3 = O.TD3Oracle(pa, pc)
+    b = synth.make_batch(batch, len(par), seed=1)
+    noise = torch.randn(batch, 3 * len(par)) * 0.2
+    it = 0
+    for _ in range(max(warmup, 1)):
+        t0 = time.perf_counter(); td3.update(b, it, noise, g); it += 1
+        one = time.perf_counter() - t0
+    if steps is None:
+        steps = max(2, int(budget_s / max(one, 1e-3)) // 2 * 2)
+        steps = min(steps, 20)
+    steps += steps % 2
+    it = 0
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        td3.update(b, it, noise, g); it += 1
+    dt = time.perf_counter() - t0
+    return {"value": batch * steps / dt, "unit": "samples/s", "cores": threads, "kind": "port",
+            "sample": f"{steps} TD3 updates (policy_freq=2) of {morph} B={batch} with the oracle port of src/agent.py:117-183 on {threads} host threads, {dt:.1f}s",
+            "ms_per_update": 1e3 * dt / steps}
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = a.steps + a.steps % 2
+    # bound the sample so the whole run ends within a few minutes: shrink the per-step batch if needed
+    probe = cpu_reference_rate(a.morph, a.batch, steps=2, warmup=1)
+    batch = a.batch
+    est = probe["ms_per_update"] * 1e-3 * (steps + a.warmup)
+    while est > 240 and batch > 16:
+        batch //= 2; est /= 2
+    r = cpu_reference_rate(a.morph, batch, steps=steps, warmup=max(a.warmup, 1))
+    from sgrl_b200 import morphologies as M
+    line = {"impl": "reference", "metric": "SET TD3 update samples/sec", "value": r["value"], "unit": "samples/s", "n_gpus": a.gpus,
+            "steps": steps, "warmup": a.warmup, "ms_per_step": r["ms_per_update"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{a.morph} TD3 Agent.update, B={a.batch}, N={len(M.ALL[a.morph])} limbs, policy_freq=2", "cpu_sample_batch": batch},
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": r["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+    from sgrl_b200 import _lib, graph as G, morphologies as M, synth
+    from sgrl_b200.agent import Agent
+    from sgrl_b200.config import default_args
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    K = a.steps + a.steps % 2
+    W = max(a.warmup, 3)
+    W += W % 2
+    par = M.ALL[a.morph]
+    N, B = len(par), a.batch
+    torch.manual_seed(0)
+    agent = Agent(default_args())
+    if a.use_tc >= 0:
+        for m in (agent.actor, agent.actor_target, agent.critic, agent.critic_target):
+            m.use_tc = a.use_tc
+    use_tc = int(agent.actor.use_tc)
+    if world > 1:                                   # identical replicas: broadcast rank 0's weights
+        for m in (agent.actor, agent.actor_target, agent.critic, agent.critic_target):
+            dist.broadcast(m.full_arena, 0)
+    g = G.build_graph(par, device=dev)
+    agent.change_morphology(g)
+    nbat = 8
+    host = [synth.make_batch(B, N, seed=100 + 17 * rank + i) for i in range(nbat)]
+    host = [{k: v.pin_memory() for k, v in b.items()} for b in host]
+    devb = [{k: v.to(dev) for k, v in b.items()} for b in host]
+    noise = [torch.randn(B, 3 * N, device=dev) * 0.2 for _ in range(nbat)]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    agent.lazy_stats = True
+    for i in range(W):
+        agent.update(devb[i % nbat], i, noise=noise[i % nbat])
+    barrier()
+    # ---- timed: K updates, inputs resident in HBM, L2 flushed between steps (outside the event pairs)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    l0 = _lib.lib.sgrl_launch_count()
+    barrier()
+    for i in range(K):
+        flush.zero_()
+        ev[i][0].record()
+        agent.update(devb[i % nbat], i, noise=noise[i % nbat])
+        ev[i][1].record()
+    barrier()
+    launches = (_lib.lib.sgrl_launch_count() - l0) / K
+    clk = clocks.stop() if rank == 0 else None
+    total_ms = sum(s.elapsed_time(e) for s, e in ev)
+    t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = t.item()
+    value = world * B * K / (total_ms * 1e-3)
+
+    # ---- e2e: the public call with HOST (pinned) buffers, result read back every step
+    agent.lazy_stats = False
+    for i in range(2):
+        agent.update(host[i % nbat], i)["loss/critic_loss"].item()
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(K):
+        ld = agent.update(host[i % nbat], i)
+        ld["loss/critic_loss"].item()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_val = world * B * K / t.item()
+    h2d = sum(v.numel() * 4 for v in host[0].values())
+
+    line = {"metric": "SET TD3 update samples/sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 (3xTF32 tensor-core projections, fp32 accumulate)" if use_tc else "f32", "data": "synthetic",
+            "config": {"workload": f"{a.morph} TD3 Agent.update, B={B} per GPU, N={N} limbs, policy_freq=2 (Humanoid++ of start_humanoid.sh)",
+                       "l2": "256 MiB buffer written between timed steps (L2 flushed); working set (4 nets + Adam state + grads ~ 300 MB) exceeds L2 anyway",
+                       "use_tc": use_tc, "updates_per_s": world * K / (total_ms * 1e-3), "limb_tokens_per_s": value * N},
+            "e2e": {"value": e2e_val, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                    "how": "Agent.update(batch of pinned host tensors, it) + critic_loss.item(), wall clock, max over ranks"},
+            "gpu_launches": launches}
+    if rank == 0:
+        line["clocks"] = clk
+
+    # ---- roofline pass: device time per kernel class (CUDA events on the launching stream), 2 updates
+    pk = peaks()
+    barrier()
+    _lib.lib.sgrl_profile(1)
+    for i in range(2):
+        agent.update(devb[i % nbat], i, noise=noise[i % nbat])
+    torch.cuda.synchronize()
+    prof = _lib.profile_collect()
+    _lib.lib.sgrl_profile(0)
+    step_ms = total_ms / K
+    classes = {}
+    for name, (ms, work, cnt) in prof.items():
+        if cnt:
+            classes[name] = {"ms_per_step": ms / 2, "launches_per_step": cnt / 2, "share_of_step": (ms / 2) / step_ms}
+            if name.startswith("gemm"):
+                classes[name]["tflops"] = work / (ms * 1e-3) / 1e12
+            else:
+                classes[name]["gbs"] = work / (ms * 1e-3) / 1e9
+    dom = max(classes, key=lambda k: classes[k]["ms_per_step"]) if classes else None
+    if dom and dom.startswith("gemm"):
+        ach = classes[dom]["tflops"]
+        line["roofline"] = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": pk["tflops_sustained"], "unit": "TFLOP/s",
+                            "frac": ach / pk["tflops_sustained"], "traffic": None, "peak_src": pk["src"] + " bf16 sustained",
+                            "algorithmic_flops_per_step": FLOP_PER_TOKEN_UPDATE * B * N,
+                            "whole_step_tflops": FLOP_PER_TOKEN_UPDATE * B * N / (step_ms * 1e-3) / 1e12}
+    elif dom:
+        ach = classes[dom]["gbs"]
+        line["roofline"] = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
+                            "traffic": None, "peak_src": pk["src"]}
+    line["kernel_classes"] = classes
+
+    # ---- rollout: SEPolicy.forward under no_grad over many parallel envs (inputs resident)
+    if not a.no_rollout:
+        E = a.rollout_envs
+        obs = synth.make_obs(min(E, 4096), N, seed=7).to(dev)
+        obs = obs.repeat((E + obs.shape[0] - 1) // obs.shape[0], 1)[:E].contiguous()
+        with torch.no_grad():
+            for _ in range(3):
+                agent.actor(obs)
+            barrier()
+            R = 10
+            evr = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(R)]
+            for i in range(R):
+                flush.zero_()
+                evr[i][0].record(); agent.actor(obs); evr[i][1].record()
+            barrier()
+            ms = sum(s.elapsed_time(e) for s, e in evr)
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            tok = world * E * N * R / (t.item() * 1e-3)
+            _lib.lib.sgrl_profile(1)
+            agent.actor(obs)
+            torch.cuda.synchronize()
+            rp = _lib.profile_collect()
+            _lib.lib.sgrl_profile(0)
+        line["rollout"] = {"value": tok, "unit": "limb-tokens/s", "envs_per_gpu": E, "ms_per_forward": t.item() / R,
+                           "tflops": tok * FLOP_PER_TOKEN_ACTOR_FWD / 1e12,
+                           "feature_k1_gbs": rp["feature_k1"][1] / max(rp["feature_k1"][0], 1e-9) / 1e6,
+                           "attention_k2_gbs": rp["attention_k2"][1] / max(rp["attention_k2"][0], 1e-9) / 1e6,
+                           "gemm_tflops": (rp["gemm_simt"][1] + rp["gemm_tcgen05"][1]) / max(rp["gemm_simt"][0] + rp["gemm_tcgen05"][0], 1e-9) / 1e9,
+                           "hbm_peak_gbs": pk["hbm_gbs"]}
+
+    # ---- reference algorithm on this box's host cores (rank 0, N=1 only; bounded sample)
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        cb = cpu_reference_rate(a.morph, B, budget_s=15.0)
+        line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)

@@ -27,6 +27,14 @@ enum { SGRL_ACTOR = 0, SGRL_CRITIC = 1 };
 
 int sgrl_version(void);
 const char* sgrl_last_error(void);
+/* kernels launched by the library so far in this process (bench.py reports the per-step delta) */
+long long sgrl_launch_count(void);
+/* bench-only device timing of kernel classes [simt gemm, tcgen05 gemm, feature (K1), attention (K2), other]:
+ * sgrl_profile(1) brackets every launch of the first four classes with CUDA events on its stream (adds
+ * ~2 us per launch: never enabled inside a timed throughput pass); sgrl_profile_collect() after a
+ * synchronize returns per class the summed milliseconds, work (flops or algorithmic bytes) and launches. */
+int sgrl_profile(int enable);
+int sgrl_profile_collect(double* ms, double* work, long long* count, int ncls);
 
 /* ---- layouts ------------------------------------------------------------------------
  * One "net" = one reference TransformerModel (SEActor.py:170-287).  A module's arena holds

@@ -47,6 +47,9 @@ class NetCall(C.Structure):
 _PROTOS = {
     "sgrl_version": (c_int, []),
     "sgrl_last_error": (C.c_char_p, []),
+    "sgrl_launch_count": (C.c_longlong, []),
+    "sgrl_profile": (c_int, [c_int]),
+    "sgrl_profile_collect": (c_int, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_longlong), c_int]),
     "sgrl_param_count": (c_int, [c_int, c_int]),
     "sgrl_param_info": (c_int, [c_int, c_int, c_int, C.c_char_p, c_int, C.POINTER(c_int), C.POINTER(c_int), C.POINTER(c_i64), C.POINTER(c_int)]),
     "sgrl_arena_floats": (c_int, [c_int, c_int, C.POINTER(c_i64), C.POINTER(c_i64)]),
@@ -93,6 +96,17 @@ def ptr(t):
 
 def stream():
     return torch.cuda.current_stream().cuda_stream
+
+
+PROF_CLASSES = ("gemm_simt", "gemm_tcgen05", "feature_k1", "attention_k2", "other")
+
+
+def profile_collect():
+    """{class: (ms, work, launches)} since sgrl_profile(1); call after torch.cuda.synchronize()."""
+    n = len(PROF_CLASSES)
+    ms, work, cnt = (C.c_double * n)(), (C.c_double * n)(), (C.c_longlong * n)()
+    check(lib.sgrl_profile_collect(ms, work, cnt, n), "sgrl_profile_collect")
+    return {PROF_CLASSES[i]: (ms[i], work[i], cnt[i]) for i in range(n)}
 
 
 def param_table(kind: int, n_layers: int):

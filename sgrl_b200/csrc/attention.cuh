@@ -26,6 +26,7 @@ struct AttnGraphs {
   const int* rel_off;     // (G) float offset of each graph's (n,n,3) relation table, or nullptr (all 0)
   const float* relation;  // packed relation tables
   int G;
+  int T;                  // total tokens (profiling/bookkeeping only)
 };
 
 __device__ __forceinline__ void attn_stage_common(float* qs, float* vs, const float* __restrict__ QKV,
@@ -277,7 +278,10 @@ inline int attention_fwd(const float* QKV, const float* VGP, const float* GD, fl
     attr_done = true;
   }
   const int gx = gr.G < 4 * NUM_SMS ? gr.G : 4 * NUM_SMS;
+  // algorithmic bytes per token: read q|k|v 3072 + vg 3024 + gd 24, write o 1024 + og 3072 (+ P 128)
+  prof_begin(PC_ATTENTION, (double)gr.T * nb * (3072.0 + 3024 + 24 + 1024 + 3072 + 128), st);
   attention_fwd_kernel<<<dim3(gx, nb), A_FWD_THREADS, attn_fwd_smem(), st>>>(QKV, VGP, GD, O, OG, P, zsS, Wrel, brel, zsP, gr);
+  prof_end(st);
   SGRL_LAUNCH_OK();
   return 0;
 }

@@ -15,10 +15,36 @@ inline int fail(int code, const char* what, const char* file, int line) {
 }
 #define SGRL_CHECK(cond, msg) do { if (!(cond)) return ::sgrl::fail(-2, msg, __FILE__, __LINE__); } while (0)
 #define SGRL_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return ::sgrl::fail(-3, cudaGetErrorString(e__), __FILE__, __LINE__); } while (0)
-#define SGRL_LAUNCH_OK() do { cudaError_t e__ = cudaPeekAtLastError(); if (e__ != cudaSuccess) return ::sgrl::fail(-4, cudaGetErrorString(e__), __FILE__, __LINE__); } while (0)
+extern long long g_launches;   // kernels launched by this library (bench.py's gpu_launches)
+#define SGRL_LAUNCH_OK() do { ++::sgrl::g_launches; cudaError_t e__ = cudaPeekAtLastError(); if (e__ != cudaSuccess) return ::sgrl::fail(-4, cudaGetErrorString(e__), __FILE__, __LINE__); } while (0)
 #define SGRL_TRY(call) do { int r__ = (call); if (r__ != 0) return r__; } while (0)
 
 constexpr int NUM_SMS = 148;  // B200
+
+// ---- optional per-kernel-class device timing (bench.py roofline pass): CUDA events around
+// the launches of one class on the launching stream, collected after a synchronize.
+enum ProfClass { PC_GEMM = 0, PC_GEMM_TC, PC_FEATURE, PC_ATTENTION, PC_OTHER, PC_COUNT };
+struct Prof {
+  bool on = false;
+  static constexpr int CAP = 8192;
+  cudaEvent_t ev[2 * CAP];
+  int cls[CAP]; double work[CAP];
+  int n = 0; bool made = false;
+};
+extern Prof g_prof;
+inline void prof_begin(int cls, double work, cudaStream_t st) {
+  Prof& p = g_prof;
+  if (!p.on || p.n >= Prof::CAP) return;
+  if (!p.made) { for (int i = 0; i < 2 * Prof::CAP; ++i) cudaEventCreate(&p.ev[i]); p.made = true; }
+  p.cls[p.n] = cls; p.work[p.n] = work;
+  cudaEventRecord(p.ev[2 * p.n], st);
+}
+inline void prof_end(cudaStream_t st) {
+  Prof& p = g_prof;
+  if (!p.on || p.n >= Prof::CAP) return;
+  cudaEventRecord(p.ev[2 * p.n + 1], st);
+  ++p.n;
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

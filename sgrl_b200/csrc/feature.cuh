@@ -171,8 +171,11 @@ inline int inv_feature_fwd_launch(const FeatFwdP& p, cudaStream_t st) {
   }
   const int ntiles = ceil_div(p.T, F_TT);
   const int gx = ntiles < 2 * NUM_SMS ? ntiles : 2 * NUM_SMS;
+  // algorithmic bytes per token: read X (12*C) + gd (24), write G (4096) + F (4) + Z (384 per projection)
+  prof_begin(PC_FEATURE, (double)p.T * p.nb * (12.0 * S::C + 24 + 4096 + 4 + 384.0 * NPROJ), st);
   kern<<<dim3(gx, p.nb), F_THREADS, S::bytes, st>>>(p.Xg, p.zsXg, p.V0, p.zsV0, p.gd, p.zsGd, p.P1, p.P2, p.zsP,
                                                    p.Z, p.Z2, p.G, p.Fn, p.zsAct, p.T);
+  prof_end(st);
   SGRL_LAUNCH_OK();
   return 0;
 }

@@ -172,7 +172,9 @@ inline int gemm_simt(const GemmP& p_in, cudaStream_t st) {
              "gemm: split-K only with a linear epilogue");
   const int tiles = ceil_div(p.M, GB_M) * ceil_div(p.N, GB_N);
   dim3 grid(tiles, p.splitk, p.nb);
+  prof_begin(PC_GEMM, 2.0 * p.M * p.N * (double)p.K * p.nb, st);
   gemm_simt_kernel<<<grid, G_THREADS, 0, st>>>(p);
+  prof_end(st);
   SGRL_LAUNCH_OK();
   return 0;
 }

@@ -4,7 +4,11 @@
 #include "net.cuh"
 #include "td3.cuh"
 
-namespace sgrl { thread_local char g_err[512] = ""; }
+namespace sgrl {
+thread_local char g_err[512] = "";
+long long g_launches = 0;
+Prof g_prof;
+}
 using namespace sgrl;
 
 #define ST(s) reinterpret_cast<cudaStream_t>(s)
@@ -13,6 +17,28 @@ extern "C" {
 
 int sgrl_version(void) { return 1; }
 const char* sgrl_last_error(void) { return g_err; }
+
+long long sgrl_launch_count(void) { return g_launches; }
+
+int sgrl_profile(int enable) {
+  g_prof.on = enable != 0;
+  g_prof.n = 0;
+  return 0;
+}
+
+/* after a stream/device synchronize: per class c, ms[c] = summed device time, work[c] = summed
+ * flops (GEMM classes) or algorithmic bytes (feature/attention), count[c] = launches */
+int sgrl_profile_collect(double* ms, double* work, long long* count, int ncls) {
+  SGRL_CHECK(ncls >= PC_COUNT, "need room for every class");
+  for (int c = 0; c < ncls; ++c) { ms[c] = 0; work[c] = 0; count[c] = 0; }
+  for (int i = 0; i < g_prof.n; ++i) {
+    float t = 0.f;
+    SGRL_CUDA(cudaEventElapsedTime(&t, g_prof.ev[2 * i], g_prof.ev[2 * i + 1]));
+    ms[g_prof.cls[i]] += t; work[g_prof.cls[i]] += g_prof.work[i]; count[g_prof.cls[i]] += 1;
+  }
+  g_prof.n = 0;
+  return 0;
+}
 
 int sgrl_param_count(int kind, int n_layers) {
   if (n_layers < 1 || n_layers > MAX_LAYERS || (kind != ACTOR && kind != CRITIC)) return fail(-2, "bad kind/n_layers", __FILE__, __LINE__);
@@ -68,7 +94,7 @@ static int make_ctx(const SgrlNetCall* k, cudaStream_t st, NetCtx& c) {
   c.stash = k->stash; c.zsS = k->stash_stride;
   c.wl = make_ws(k->T);
   c.ws = k->ws; c.zsW = k->ws_stride;
-  c.gr.cu_limbs = k->cu_limbs; c.gr.rel_off = k->rel_off; c.gr.relation = k->relation; c.gr.G = k->G;
+  c.gr.cu_limbs = k->cu_limbs; c.gr.rel_off = k->rel_off; c.gr.relation = k->relation; c.gr.G = k->G; c.gr.T = k->T;
   c.rank3 = k->rank3; c.max_action = k->max_action; c.use_tc = k->use_tc; c.stream = st;
   return 0;
 }
@@ -110,7 +136,7 @@ int sgrl_attention_fwd(const float* qkv, const float* vgp, const float* gd, cons
                        sgrl_stream_t stream) {
   SGRL_CHECK(qkv && vgp && gd && cu_limbs && o && og && p, "null pointer");
   SGRL_CHECK((rel_w == nullptr) || (rel_b && relation), "bias needs rel_b and relation");
-  AttnGraphs gr{cu_limbs, rel_off, relation, G};
+  AttnGraphs gr{cu_limbs, rel_off, relation, G, 0};
   return attention_fwd(qkv, vgp, gd, o, og, p, 0, rel_w, rel_b, 0, gr, 1, ST(stream));
 }
 
@@ -118,7 +144,7 @@ int sgrl_attention_bwd(const float* qkv, const float* vgp, const float* gd, cons
                        const int32_t* cu_limbs, const int32_t* rel_off, const float* relation, int G, float* dqkv, float* dvgp,
                        float* drel_w, sgrl_stream_t stream) {
   SGRL_CHECK(qkv && vgp && gd && p && d_o && d_og && cu_limbs && dqkv && dvgp, "null pointer");
-  AttnGraphs gr{cu_limbs, rel_off, relation, G};
+  AttnGraphs gr{cu_limbs, rel_off, relation, G, 0};
   return attention_bwd(qkv, vgp, gd, p, 0, d_o, d_og, dqkv, dvgp, 0, drel_w, 0, gr, 1, ST(stream));
 }
 
