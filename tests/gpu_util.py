@@ -5,7 +5,7 @@ from oracle import ref_loader, set_oracle as O
 import parity
 
 
-def make_modules(seed=parity.WEIGHT_SEED, use_tc=0):
+def make_modules(seed=parity.WEIGHT_SEED, use_tc=1):
     from sgrl_b200.modules import SEPolicy, SECritic
     args = ref_loader.default_args()
     actor = SEPolicy(41, 3, 32, 100, 1.0, None, False, False, False, args)

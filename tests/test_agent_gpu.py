@@ -11,7 +11,7 @@ import parity
 pytestmark = pytest.mark.gpu
 
 
-def make_agent(use_tc=0):
+def make_agent(use_tc=1):
     from sgrl_b200.agent import Agent
     ag = Agent(ref_loader.default_args())
     a = O.synth_params("actor", parity.WEIGHT_SEED)
@@ -43,10 +43,11 @@ def test_state_dict_has_reference_keys():
     assert len(ag.state_dict()) == 818
 
 
+@pytest.mark.parametrize("use_tc", [1, 0], ids=["tcgen05", "simt"])
 @pytest.mark.parametrize("name,B", [parity.CASES[1], parity.CASES[3]])
-def test_update_matches_reference_golden(name, B):
+def test_update_matches_reference_golden(name, B, use_tc):
     gold = parity.load_golden()
-    ag, _, _ = make_agent()
+    ag, _, _ = make_agent(use_tc)
     g = parity.golden_graph(gold, name, M.ALL[name], device="cuda")
     b = parity.golden_batch(gold, name, device="cuda")
     ag.change_morphology(g)

@@ -9,10 +9,10 @@ import parity
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module")
-def mods():
+@pytest.fixture(scope="module", params=[1, 0], ids=["tcgen05", "simt"])
+def mods(request):
     import gpu_util
-    return gpu_util.make_modules()
+    return gpu_util.make_modules(use_tc=request.param)
 
 
 @pytest.fixture(scope="module")

@@ -1,0 +1,77 @@
+"""K3 projections through the C ABI: fp32 SIMT kernel and the tcgen05 3xTF32 kernel vs fp64 torch.
+Covers the three contraction forms of the hot path (Y=XW^T, dX=dYW, dW=dY^T X), ragged tails,
+sub-matrix leading dimensions and the fused epilogue options the ABI exposes."""
+import ctypes as C
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def run_gemm(A, lda, ta, B, ldb, tb, Cm, ldc, M, N, K, alpha=1.0, bias=None, rowdiv=None, relu=0, acc=0, splitk=1, use_tc=0):
+    from sgrl_b200._lib import lib, ptr, stream, check
+    check(lib.sgrl_gemm(ptr(A), lda, ta, ptr(B), ldb, tb, ptr(Cm), ldc, M, N, K, alpha, ptr(bias), ptr(rowdiv), relu, acc, splitk, use_tc, stream()), "sgrl_gemm")
+    torch.cuda.synchronize()
+
+
+def rel(a, b):
+    return ((a.double() - b.double()).norm() / b.double().norm()).item()
+
+
+TOL = {0: 2e-6, 1: 2e-5}   # tcgen05 accumulates with truncation: ~5e-6 at K=1024, still 20x inside the 1e-4 budget
+FWD = [(300, 256, 1024), (2304, 768, 256), (77, 252, 128), (128, 128, 32), (1000, 1024, 256), (129, 130, 100)]
+
+
+@pytest.mark.parametrize("use_tc", [0, 1])
+@pytest.mark.parametrize("M,N,K", FWD)
+def test_forward_linear(use_tc, M, N, K):
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + N)
+    ldk = (K + 3) // 4 * 4
+    X = torch.randn(M, ldk, device="cuda", generator=g)
+    W = torch.randn(N, ldk, device="cuda", generator=g) / K ** 0.5
+    b = torch.randn(N, device="cuda", generator=g)
+    F = torch.rand(M, device="cuda", generator=g) * 500 + 100
+    if use_tc and M * N * K < (1 << 21):
+        pytest.skip("below the tcgen05 eligibility threshold (launch-bound sizes stay on the SIMT kernel)")
+    Y = torch.full((M, N + 3), 7.0, device="cuda")                    # ldc > N: neighbours must stay untouched
+    run_gemm(X, ldk, 0, W, ldk, 0, Y, N + 3, M, N, K, bias=b, rowdiv=F, relu=1, use_tc=use_tc)
+    ref = torch.relu(X[:, :K].double() @ W[:, :K].double().T + b.double()) / F.double()[:, None]
+    assert rel(Y[:, :N], ref) < TOL[use_tc]
+    assert torch.all(Y[:, N:] == 7.0)
+
+
+@pytest.mark.parametrize("use_tc", [0, 1])
+@pytest.mark.parametrize("M,Nw,Kw", [(900, 768, 256), (2700, 252, 128), (600, 256, 1024), (2700, 30, 128)])
+def test_data_gradient(use_tc, M, Nw, Kw):
+    g = torch.Generator(device="cuda").manual_seed(Nw)
+    ldn = (Nw + 3) // 4 * 4 if Nw != 30 else 32
+    dY = torch.randn(M, ldn, device="cuda", generator=g)
+    W = torch.randn(Nw, Kw, device="cuda", generator=g)
+    dX = torch.randn(M, Kw, device="cuda", generator=g)
+    base = dX.clone()
+    run_gemm(dY, ldn, 0, W, Kw, 1, dX, Kw, M, Kw, Nw, acc=1, use_tc=use_tc)       # dX += dY W
+    ref = base.double() + dY[:, :Nw].double() @ W.double()
+    assert rel(dX, ref) < TOL[use_tc]
+
+
+@pytest.mark.parametrize("use_tc", [0, 1])
+@pytest.mark.parametrize("T,Nw,Kw,splitk", [(900, 256, 1024, 3), (2304, 1024, 256, 4), (6912, 128, 256, 8), (700, 30, 128, 2), (333, 512, 256, 1)])
+def test_weight_gradient(use_tc, T, Nw, Kw, splitk):
+    g = torch.Generator(device="cuda").manual_seed(T)
+    ldn = (Nw + 3) // 4 * 4 if Nw != 30 else 32
+    dY = torch.randn(T, ldn, device="cuda", generator=g)
+    X = torch.randn(T, Kw, device="cuda", generator=g)
+    dW = torch.zeros(Nw, Kw, device="cuda")
+    run_gemm(dY, ldn, 1, X, Kw, 1, dW, Kw, Nw, Kw, T, alpha=0.5, acc=1, splitk=splitk, use_tc=use_tc)   # dW += 0.5 dY^T X
+    ref = 0.5 * dY[:, :Nw].double().T @ X.double()
+    assert rel(dW, ref) < TOL[use_tc]
+
+
+def test_tc_rejects_unaligned_operands():
+    from sgrl_b200._lib import SgrlError
+    X = torch.randn(256, 145, device="cuda"); W = torch.randn(128, 145, device="cuda"); Y = torch.empty(256, 128, device="cuda")
+    with pytest.raises(SgrlError, match="tcgen05"):
+        run_gemm(X, 145, 0, W, 145, 0, Y, 128, 256, 128, 145, use_tc=1)
+    run_gemm(X, 145, 0, W, 145, 0, Y, 128, 256, 128, 145, use_tc=0)
+    assert rel(Y, X.double() @ W.double().T) < 2e-6
