@@ -34,6 +34,12 @@ template <int BN> struct TcCfg {
   static constexpr int B_BYTES = BN * TC_BK * 4;
   static constexpr int STAGE_BYTES = 2 * (TC_A_BYTES + B_BYTES);
   static constexpr int STAGES = BN == 128 ? 3 : 4;
+  // The tensor core ACCUMULATES WITH TRUNCATION (measured on B200: signed bias -3e-8 per add, i.e.
+  // -1.1e-5 relative at K=1024 with one accumulator; profiles/r01_accumulator_probe.txt).  The k-steps are
+  // therefore dealt round-robin onto NMAIN independent TMEM accumulators for the hi*hi terms, plus one for
+  // the small lo*hi + hi*lo terms (whose truncation is 2^-11 smaller), and summed in fp32 RN in the epilogue.
+  static constexpr int NMAIN = BN == 128 ? 3 : 6;
+  static constexpr int TMEM_COLS = 512;             // (NMAIN + 1) * BN <= 512
   static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
@@ -128,7 +134,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)BN) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
@@ -174,9 +180,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
           for (int k = 0; k < TC_BK / 8; ++k) {
             const uint64_t dah = umma_desc(a_hi + k * A_KSTEP, A_LBO, A_SBO, A_LAY), dal = umma_desc(a_lo + k * A_KSTEP, A_LBO, A_SBO, A_LAY);
             const uint64_t dbh = umma_desc(b_hi + k * B_KSTEP, B_LBO, B_SBO, B_LAY), dbl = umma_desc(b_lo + k * B_KSTEP, B_LBO, B_SBO, B_LAY);
-            tc_mma_tf32(tmem_base, dal, dbh, idesc, (i > 0 || k > 0) ? 1u : 0u);   // small terms first
-            tc_mma_tf32(tmem_base, dah, dbl, idesc, 1u);
-            tc_mma_tf32(tmem_base, dah, dbh, idesc, 1u);
+            const int j = i * (TC_BK / 8) + k;                                  // k-step index within this CTA
+            const uint32_t acc_lo = tmem_base + Cfg::NMAIN * BN, acc_hi = tmem_base + (j % Cfg::NMAIN) * BN;
+            tc_mma_tf32(acc_lo, dal, dbh, idesc, j > 0 ? 1u : 0u);
+            tc_mma_tf32(acc_lo, dah, dbl, idesc, 1u);
+            tc_mma_tf32(acc_hi, dah, dbh, idesc, j >= Cfg::NMAIN ? 1u : 0u);
           }
           tc_commit(empty_bar(s));          // smem stage reusable once these MMAs retire
         }
@@ -220,25 +228,34 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
       const bool first_split = blockIdx.y == 0;
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t r[32];
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
-        asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-              "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
-              "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
-              "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-            : "r"(taddr)
-            : "memory");
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        float sum[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) sum[j] = 0.f;
+        const int nused = min(Cfg::NMAIN, nloc * (TC_BK / 8));      // accumulators that received at least one k-step
+#pragma unroll 1
+        for (int a = 0; a <= nused; ++a) {                          // a == nused: the lo accumulator
+          uint32_t r[32];
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((a == nused ? Cfg::NMAIN : a) * BN + c0);
+          asm volatile(
+              "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+              "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+              "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+              : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+                "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+                "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+                "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+              : "r"(taddr)
+              : "memory");
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int j = 0; j < 32; ++j) sum[j] += __uint_as_float(r[j]);
+        }
         if (m < p.M) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const int n = n0 + c0 + j;
             if (n < p.N) {
-              float v = p.alpha * __uint_as_float(r[j]);
+              float v = p.alpha * sum[j];
               if (bias && first_split) v += bias[n];
               if (p.relu) v = fmaxf(v, 0.f);
               if (p.rowdiv) v = v / rd;
@@ -260,7 +277,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
   }
 }
 
@@ -319,7 +336,7 @@ inline int make_tmap(CUtensorMap* out, const float* ptr, long long inner, long l
 
 inline bool gemm_tc_eligible(const GemmP& p) {
   if (p.M < 1 || p.N < 16 || p.K < 16) return false;
-  if ((long long)p.M * p.N * p.K * p.nb < (1 << 21)) return false;                   // tiny: launch-bound either way
+  if ((long long)p.M * p.N * p.K < (1 << 21)) return false;   // tiny: launch-bound either way (per net: Q1 == forward()[0] bit for bit)
   if (!host_vec_ok(p.A, p.lda, p.zsA) || !host_vec_ok(p.B, p.ldb, p.zsB)) return false;   // TMA: 16 B aligned base and strides
   if (p.nb > 1 && ((p.zsA != 0 && p.zsA < 4) || (p.zsB != 0 && p.zsB < 4))) return false;
   return true;
