@@ -35,6 +35,9 @@ long long sgrl_launch_count(void);
  * synchronize returns per class the summed milliseconds, work (flops or algorithmic bytes) and launches. */
 int sgrl_profile(int enable);
 int sgrl_profile_collect(double* ms, double* work, long long* count, int ncls);
+/* developer aid (tools/gemm_trace.py): while buf64 (device, 64 x int64) is set, CTA 0 of every tcgen05 GEMM writes
+ * SM-clock timestamps of its pipeline phases there; NULL switches it off */
+int sgrl_gemm_trace(long long* buf64);
 
 /* ---- layouts ------------------------------------------------------------------------
  * One "net" = one reference TransformerModel (SEActor.py:170-287).  A module's arena holds
@@ -75,6 +78,10 @@ typedef struct {
   const int32_t* rank3;    /* (T,3) traversal ranks of each token's limb, utils.py:368-409 */
   float max_action;
   float pad_;
+  /* optional (both or neither): tf32 hi/lo split of `params` (same layout; sgrl_split_tf32, or kept fresh by
+   * sgrl_adam_clip / sgrl_polyak) so the tcgen05 projections stream pre-split weights by TMA */
+  const float* params_hi;
+  const float* params_lo;
 } SgrlNetCall;
 
 /* SEPolicy.forward (SEActor.py:334-347) / SECritic.forward, Q1 (SECritic.py:66-104), all of
@@ -116,6 +123,14 @@ int sgrl_gemm(const float* A, int lda, int trans_a, const float* B, int ldb, int
               int M, int N, int K, float alpha, const float* bias, const float* rowdiv, int relu, int accumulate,
               int splitk, int use_tc, sgrl_stream_t stream);
 
+/* same with the weight operand B pre-split into its tf32 hi/lo parts (tcgen05 path only) */
+int sgrl_gemm_presplit(const float* A, int lda, int trans_a, const float* B_hi, const float* B_lo, int ldb, int trans_b, float* C,
+                       int ldc, int M, int N, int K, float alpha, const float* bias, const float* rowdiv, int relu, int accumulate,
+                       int splitk, sgrl_stream_t stream);
+/* hi = tf32_rna(w), lo = tf32_rna(w - hi): the operand split of the 3xTF32 tensor-core projections, done once per
+ * optimizer step for weights instead of once per tile load */
+int sgrl_split_tf32(const float* w, float* hi, float* lo, int64_t n, sgrl_stream_t stream);
+
 /* ---- K5: TD3 glue (agent.py:127-148,167) -------------------------------------------------- */
 int sgrl_td3_smooth_action(const float* pi_target, const float* noise, float* next_action, float noise_clip,
                            float max_action, int64_t n, sgrl_stream_t stream);
@@ -132,9 +147,11 @@ int sgrl_sumsq(const float* g, int64_t n, float* out /*accumulates*/, sgrl_strea
  * scalar with sum(g^2) (after the all-reduce); step: device int, the 1-based step count to apply;
  * grad_scale multiplies g first (1/world_size). */
 int sgrl_adam_clip(float* p, const float* g, float* m, float* v, int64_t n, const float* sumsq, const int32_t* step,
-                   float lr, float beta1, float beta2, float eps, float max_norm, float grad_scale, sgrl_stream_t stream);
+                   float lr, float beta1, float beta2, float eps, float max_norm, float grad_scale,
+                   float* p_hi /*nullable: refreshed tf32 split of p*/, float* p_lo, sgrl_stream_t stream);
 int sgrl_bump_step(int32_t* step, sgrl_stream_t stream);
-int sgrl_polyak(float* target, const float* source, int64_t n, float tau, sgrl_stream_t stream);
+int sgrl_polyak(float* target, const float* source, int64_t n, float tau,
+                float* t_hi /*nullable: refreshed tf32 split of target[0:n_split]*/, float* t_lo, int64_t n_split, sgrl_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -41,6 +41,7 @@ class NetCall(C.Structure):
         ("ws", c_f), ("ws_stride", c_i64),
         ("cu_limbs", c_f), ("rel_off", c_f), ("relation", c_f), ("rank3", c_f),
         ("max_action", C.c_float), ("pad_", C.c_float),
+        ("params_hi", c_f), ("params_lo", c_f),
     ]
 
 
@@ -50,6 +51,7 @@ _PROTOS = {
     "sgrl_launch_count": (C.c_longlong, []),
     "sgrl_profile": (c_int, [c_int]),
     "sgrl_profile_collect": (c_int, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_longlong), c_int]),
+    "sgrl_gemm_trace": (c_int, [c_f]),
     "sgrl_param_count": (c_int, [c_int, c_int]),
     "sgrl_param_info": (c_int, [c_int, c_int, c_int, C.c_char_p, c_int, C.POINTER(c_int), C.POINTER(c_int), C.POINTER(c_i64), C.POINTER(c_int)]),
     "sgrl_arena_floats": (c_int, [c_int, c_int, C.POINTER(c_i64), C.POINTER(c_i64)]),
@@ -64,13 +66,16 @@ _PROTOS = {
     "sgrl_attention_bwd": (c_int, [c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_int, c_f, c_f, c_f, c_f]),
     "sgrl_gemm": (c_int, [c_f, c_int, c_int, c_f, c_int, c_int, c_f, c_int, c_int, c_int, c_int, C.c_float, c_f, c_f,
                           c_int, c_int, c_int, c_int, c_f]),
+    "sgrl_gemm_presplit": (c_int, [c_f, c_int, c_int, c_f, c_f, c_int, c_int, c_f, c_int, c_int, c_int, c_int, C.c_float, c_f, c_f,
+                                   c_int, c_int, c_int, c_f]),
+    "sgrl_split_tf32": (c_int, [c_f, c_f, c_f, c_i64, c_f]),
     "sgrl_td3_smooth_action": (c_int, [c_f, c_f, c_f, C.c_float, C.c_float, c_i64, c_f]),
     "sgrl_td3_critic_loss": (c_int, [c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, C.c_float, C.c_float, c_int, c_f]),
     "sgrl_td3_actor_loss": (c_int, [c_f, c_f, c_f, c_int, c_f]),
     "sgrl_sumsq": (c_int, [c_f, c_i64, c_f, c_f]),
-    "sgrl_adam_clip": (c_int, [c_f, c_f, c_f, c_f, c_i64, c_f, c_f, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, c_f]),
+    "sgrl_adam_clip": (c_int, [c_f, c_f, c_f, c_f, c_i64, c_f, c_f, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, c_f, c_f, c_f]),
     "sgrl_bump_step": (c_int, [c_f, c_f]),
-    "sgrl_polyak": (c_int, [c_f, c_f, c_i64, C.c_float, c_f]),
+    "sgrl_polyak": (c_int, [c_f, c_f, c_i64, C.c_float, c_f, c_f, c_i64, c_f]),
 }
 EXPORTS = tuple(_PROTOS)
 

@@ -60,8 +60,11 @@ class FusedAdam:
         if max_norm > 0:
             check(lib.sgrl_sumsq(ptr(g), n, ptr(self.sumsq), st), "sgrl_sumsq")
         check(lib.sgrl_bump_step(ptr(self.step_count), st), "sgrl_bump_step")
+        fresh = m._split is not None and m._split_fresh and m._split_version == m._arena._version
+        hi, lo = (m._split[0], m._split[1]) if fresh else (None, None)     # keep a valid tf32 split valid (else it is rebuilt lazily)
         check(lib.sgrl_adam_clip(ptr(p), ptr(g), ptr(self.exp_avg), ptr(self.exp_avg_sq), n, ptr(self.sumsq), ptr(self.step_count),
-                                 self.lr, self.betas[0], self.betas[1], self.eps, float(max_norm), 1.0 / world_size, st), "sgrl_adam_clip")
+                                 self.lr, self.betas[0], self.betas[1], self.eps, float(max_norm), 1.0 / world_size, ptr(hi), ptr(lo), st),
+              "sgrl_adam_clip")
 
     def state_dict(self):
         return {"step": self.step_count.clone(), "exp_avg": self.exp_avg.clone(), "exp_avg_sq": self.exp_avg_sq.clone(),
@@ -81,7 +84,9 @@ def soft_update_network(source: SetNetModule, target: SetNetModule, tau: float):
         with torch.no_grad():
             t.mul_(1 - tau).add_(s, alpha=tau)
         return
-    check(lib.sgrl_polyak(ptr(t), ptr(s), s.numel(), float(tau), stream()), "sgrl_polyak")
+    fresh = target._split is not None and target._split_fresh and target._split_version == target._arena._version
+    hi, lo = (target._split[0], target._split[1]) if fresh else (None, None)
+    check(lib.sgrl_polyak(ptr(t), ptr(s), s.numel(), float(tau), ptr(hi), ptr(lo), target.live_arena.numel(), stream()), "sgrl_polyak")
 
 
 class Agent(nn.Module):
@@ -142,19 +147,19 @@ class Agent(nn.Module):
         else:
             noise = _to_dev(noise, dev)
         # ---- target:  y = r + (1-d) * gamma * min_i Q_i'(s', clip(pi'(s') + clip(eps)))       agent.py:127-139
-        a_t, _ = self.actor_target.forward_raw(tb, nobs, None, keep=False)
+        a_t, _ = self.actor_target.forward_raw(tb, nobs, None, keep=False, trusted_split=True)
         next_action = torch.empty(T, 3, device=dev)
         check(lib.sgrl_td3_smooth_action(ptr(a_t), ptr(noise), ptr(next_action), float(a.noise_clip), float(a.max_action), T * 3, st))
-        tq, _ = self.critic_target.forward_raw(tb, nobs, next_action, keep=False, nb=2)
+        tq, _ = self.critic_target.forward_raw(tb, nobs, next_action, keep=False, nb=2, trusted_split=True)
         # ---- critic step                                                                       agent.py:142-156
-        q, stash = self.critic.forward_raw(tb, obs, act, keep=True, nb=2)
+        q, stash = self.critic.forward_raw(tb, obs, act, keep=True, nb=2, trusted_split=True)
         scal = torch.zeros(2, device=dev)            # [critic_loss, actor_loss]
         target = torch.empty(T, device=dev)
         dq = torch.empty(2, T, 1, device=dev)
         check(lib.sgrl_td3_critic_loss(ptr(q[0]), ptr(q[1]), ptr(tq[0]), ptr(tq[1]), ptr(rew), ptr(done), ptr(tb.tok_graph), ptr(target),
                                        ptr(dq[0]), ptr(dq[1]), ptr(scal), float(a.discount), float(self.reward_scale), T, st))
         self.critic_optimizer.zero_grad()
-        self.critic.backward_raw(tb, stash, dq, 2, self.critic.grad_arena(), False)
+        self.critic.backward_raw(tb, stash, dq, 2, self.critic.grad_arena(), False, trusted_split=True)
         del stash
         self._allreduce(self.critic.grad_arena(), world)
         self.critic_optimizer.step(max_norm=float(a.grad_clipping_value), world_size=world)
@@ -162,13 +167,13 @@ class Agent(nn.Module):
         loss_dict.update(self._reward_stats(reward_in, rew))
         # ---- delayed actor step + Polyak                                                       agent.py:165-180
         if it % a.policy_freq == 0:
-            pi, stash_a = self.actor.forward_raw(tb, obs, None, keep=True)
-            q1, stash_c = self.critic.forward_raw(tb, obs, pi[0], keep=True, nb=1)
+            pi, stash_a = self.actor.forward_raw(tb, obs, None, keep=True, trusted_split=True)
+            q1, stash_c = self.critic.forward_raw(tb, obs, pi[0], keep=True, nb=1, trusted_split=True)
             dq1 = torch.empty(1, T, 1, device=dev)
             check(lib.sgrl_td3_actor_loss(ptr(q1), ptr(dq1), ptr(scal[1:]), T, st))
-            dact = self.critic.backward_raw(tb, stash_c, dq1, 1, None, True)     # only d/d(action) is needed
+            dact = self.critic.backward_raw(tb, stash_c, dq1, 1, None, True, trusted_split=True)     # only d/d(action) is needed
             self.actor_optimizer.zero_grad()
-            self.actor.backward_raw(tb, stash_a, dact, 1, self.actor.grad_arena(), False)
+            self.actor.backward_raw(tb, stash_a, dact, 1, self.actor.grad_arena(), False, trusted_split=True)
             del stash_a, stash_c
             self._allreduce(self.actor.grad_arena(), world)
             self.actor_optimizer.step(max_norm=float(a.grad_clipping_value), world_size=world)

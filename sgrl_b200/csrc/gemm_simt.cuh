@@ -30,6 +30,10 @@ struct GemmP {
   int splitk;                               // >1: split K over blockIdx.y, atomicAdd (implies accumulate)
   int nb;                                   // instances (blockIdx.z)
   int vecA, vecB;                           // set by the launcher: operand rows may be fetched as float4
+  const float* Bhi; const float* Blo;       // tcgen05 path only, optional: B pre-split into tf32 hi/lo parts (same layout/strides as B)
+  int vecE;                                 // set by the tcgen05 launcher: C/mask/res rows allow float4 access
+  int sched;                                // tcgen05 MMA issue order experiment knob (SGRL_TC_SCHED)
+  long long* dbg;                           // optional (tools/gemm_trace.py): SM-clock timestamps of CTA 0's pipeline phases
 };
 
 inline GemmP gemm_defaults() {

@@ -21,6 +21,8 @@
 #pragma once
 #include <cuda.h>
 
+#include <cstdlib>
+
 #include <unordered_map>
 
 #include "gemm_simt.cuh"
@@ -83,6 +85,22 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t adesc, uin
       ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// descriptors passed as {lo word, hi word}; scale_d (accumulate) as a runtime flag
+__device__ __forceinline__ void tc_mma_tf32_w(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -100,10 +118,169 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes
          (1ull << 46) | ((uint64_t)layout << 61);
 }
 
+// explicit shared-space vector access by 32-bit shared address: the tile base comes out of integer alignment
+// arithmetic, so the compiler cannot prove the address space and would emit slow generic LD/ST (measured:
+// ~850 cycles per dependent generic load in the epilogue, 7 us per 128x64 tile)
+__device__ __forceinline__ float4 lds128(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t a, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts128u(uint32_t a, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
 // ---------------------------------------------------------------------------- kernel
-template <int BN, bool AMN, bool BMN>
+// x -> hi = tf32_rna(x) (integer round-half-away on the bit pattern: 2 ALU ops), lo = tf32_rna(x - hi)
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+  hi = (__float_as_uint(x) + 0x1000u) & 0xFFFFE000u;
+  lo = (__float_as_uint(x - __uint_as_float(hi)) + 0x1000u) & 0xFFFFE000u;
+}
+// split NCH 16-byte chunks of a TMA-landed tile in place: hi overwrites the tile, lo goes LO_OFF bytes further.
+// The split is elementwise, so the swizzled placement is preserved without knowing the swizzle.
+template <int NCH, int LO_OFF>
+__device__ __forceinline__ void split_tile(uint32_t tile, int ct) {     // tile: shared address
+  static_assert(NCH % 128 == 0, "chunks per converter thread");
+  constexpr int PER = NCH / 128;
+  float4 v[PER];
+#pragma unroll
+  for (int i = 0; i < PER; ++i) v[i] = lds128(tile + (uint32_t)(ct + i * 128) * 16u);
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    uint4 h, l;
+    split_tf32(v[i].x, h.x, l.x); split_tf32(v[i].y, h.y, l.y); split_tf32(v[i].z, h.z, l.z); split_tf32(v[i].w, h.w, l.w);
+    sts128u(tile + (uint32_t)(ct + i * 128) * 16u, h);
+    sts128u(tile + LO_OFF + (uint32_t)(ct + i * 128) * 16u, l);
+  }
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+
+constexpr int TC_EPI_LD = 36;     // floats per staged accumulator row (32 + 4: 16 B aligned, conflict-free float4 access)
+
+enum { EM_STORE = 0, EM_ACCUM = 1, EM_ATOMIC = 2 };
+struct EpiArgs {
+  float* C; const float* bias; const float* mask; const float* res1; const float* res2;   // lane-offset row pointers (chunk 0)
+  float rd[8];        // rowdiv of this lane's 8 rows (1 when absent)
+  int mrow, rows, vec;
+};
+
+// One 32-column chunk of one warp's 32-row slab: staged fp32 accumulators (shared) -> fused epilogue -> global, each
+// warp store covering four 128-byte row segments.  Specialised at compile time on the epilogue class so that the
+// common cases cost a few instructions per float4 (the first version tested every option per element and spent
+// 7 us per 128x64 tile in dependent integer/branch latency).
+template <bool ROWDIV, bool MASK, int NRES, int MODE>
+__device__ __forceinline__ void tc_epi_chunk(const GemmP& p, const EpiArgs& ea, uint32_t stg, int rsub, int cq, int n, int c0) {
+  if (n >= p.N) return;
+  float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  const bool full4 = ea.vec && (n + 3 < p.N);
+  if (MODE == EM_STORE && ea.bias) {
+    if (full4) b4 = ldg4(ea.bias + n);
+    else {
+      b4.x = __ldg(ea.bias + n);
+      if (n + 1 < p.N) b4.y = __ldg(ea.bias + n + 1);
+      if (n + 2 < p.N) b4.z = __ldg(ea.bias + n + 2);
+      if (n + 3 < p.N) b4.w = __ldg(ea.bias + n + 3);
+    }
+  }
+  const float cs = (ROWDIV && n < p.colscale_n) ? p.colscale : 1.f;
+  const float alpha = p.alpha;
+  const bool relu = MODE == EM_STORE && p.relu;
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int r = it * 4 + rsub;
+    if (r >= ea.rows) break;
+    float4 v = lds128(stg + (r * TC_EPI_LD + cq * 4) * 4);
+    v.x = fmaf(alpha, v.x, b4.x); v.y = fmaf(alpha, v.y, b4.y); v.z = fmaf(alpha, v.z, b4.z); v.w = fmaf(alpha, v.w, b4.w);
+    if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+    if (ROWDIV) {
+      const float rd = ea.rd[it];
+      v.x = v.x / rd * cs; v.y = v.y / rd * cs; v.z = v.z / rd * cs; v.w = v.w / rd * cs;
+    }
+    const long long roff = (long long)(4 * it) * p.ldc + c0;
+    float* c = ea.C + roff;
+    if (full4) {
+      if (MASK) {
+        const float4 t = *reinterpret_cast<const float4*>(ea.mask + (long long)(4 * it) * p.ldmask + c0);
+        v.x = t.x > 0.f ? v.x : 0.f; v.y = t.y > 0.f ? v.y : 0.f; v.z = t.z > 0.f ? v.z : 0.f; v.w = t.w > 0.f ? v.w : 0.f;
+      }
+      if (NRES >= 1) {
+        const float4 t = *reinterpret_cast<const float4*>(ea.res1 + (long long)(4 * it) * p.ldr1 + c0);
+        v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+        if (ea.res2) {
+          const float4 u = *reinterpret_cast<const float4*>(ea.res2 + (long long)(4 * it) * p.ldr2 + c0);
+          v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
+        }
+      }
+      if (MODE == EM_ATOMIC) {
+        atomicAdd(c, v.x); atomicAdd(c + 1, v.y); atomicAdd(c + 2, v.z); atomicAdd(c + 3, v.w);
+      } else {
+        if (MODE == EM_ACCUM) { const float4 t = *reinterpret_cast<const float4*>(c); v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w; }
+        *reinterpret_cast<float4*>(c) = v;
+      }
+    } else {
+      float o[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        if (n + e >= p.N) break;
+        if (MASK) o[e] = ea.mask[(long long)(4 * it) * p.ldmask + c0 + e] > 0.f ? o[e] : 0.f;
+        if (NRES >= 1) {
+          o[e] += ea.res1[(long long)(4 * it) * p.ldr1 + c0 + e];
+          if (ea.res2) o[e] += ea.res2[(long long)(4 * it) * p.ldr2 + c0 + e];
+        }
+        if (MODE == EM_ATOMIC) atomicAdd(c + e, o[e]);
+        else if (MODE == EM_ACCUM) c[e] += o[e];
+        else c[e] = o[e];
+      }
+    }
+  }
+}
+
+// any other combination of epilogue options (same op order as gemm_simt_kernel), element by element
+__device__ __noinline__ void tc_epi_generic(const GemmP& p, const EpiArgs& ea, uint32_t stg, int rsub, int cq, int n, int c0) {
+  if (n >= p.N) return;
+  for (int it = 0; it < 8; ++it) {
+    const int r = it * 4 + rsub;
+    if (r >= ea.rows) break;
+    const float4 a4 = lds128(stg + (r * TC_EPI_LD + cq * 4) * 4);
+    const float av[4] = {a4.x, a4.y, a4.z, a4.w};
+    for (int e = 0; e < 4 && n + e < p.N; ++e) {
+      float v = p.alpha * av[e];
+      if (ea.bias) v += __ldg(ea.bias + n + e);
+      if (p.relu) v = fmaxf(v, 0.f);
+      if (p.rowdiv) v = v / ea.rd[it];
+      if (n + e < p.colscale_n) v *= p.colscale;
+      if (ea.mask) v = ea.mask[(long long)(4 * it) * p.ldmask + c0 + e] > 0.f ? v : 0.f;
+      if (ea.res1) v += ea.res1[(long long)(4 * it) * p.ldr1 + c0 + e];
+      if (ea.res2) v += ea.res2[(long long)(4 * it) * p.ldr2 + c0 + e];
+      float* c = ea.C + (long long)(4 * it) * p.ldc + c0 + e;
+      if (p.splitk > 1) atomicAdd(c, v);
+      else if (p.accumulate) *c += v;
+      else *c = v;
+    }
+  }
+}
+
+// BPRE: the B operand arrives already split (hi/lo tensor maps over the pre-split weight arenas), so the
+// converter warps only touch the activation operand A.
+template <int BN, bool AMN, bool BMN, bool BPRE>
 __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA,
-                                                                const __grid_constant__ CUtensorMap mapB, GemmP p) {
+                                                                const __grid_constant__ CUtensorMap mapB,
+                                                                const __grid_constant__ CUtensorMap mapBlo, GemmP p) {
   using Cfg = TcCfg<BN>;
   constexpr int STAGES = Cfg::STAGES, B_BYTES = Cfg::B_BYTES, STAGE_BYTES = Cfg::STAGE_BYTES;
   extern __shared__ uint8_t smem_raw[];
@@ -125,6 +302,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
   const int kb0 = blockIdx.y * per, kb1 = min(nkb, kb0 + per);
   const int nloc = kb1 - kb0;
   const int zA = p.zsA ? z : 0, zB = p.zsB ? z : 0;
+  long long* dbg = (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && z == 0) ? p.dbg : nullptr;
+#define TC_STAMP(slot) do { if (dbg) dbg[slot] = clock64(); } while (0)
+  if (tid == 0) TC_STAMP(0);
 
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(ready_bar(s), 128); mbar_init(empty_bar(s), 1); }
@@ -132,6 +312,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
+    if (BPRE) asm volatile("prefetch.tensormap [%0];" ::"l"(&mapBlo) : "memory");
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
@@ -141,140 +322,173 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (tid == 0) TC_STAMP(1);
 
   if (nloc > 0) {
     if (warp == 0) {
-      // ===================== TMA producer =====================
-      if (lane == 0) {
-        for (int i = 0; i < nloc; ++i) {
-          const int s = i % STAGES, ph = (i / STAGES) & 1, k0 = (kb0 + i) * TC_BK;
-          mbar_wait(empty_bar(s), ph ^ 1);
-          mbar_arrive_expect_tx(full_bar(s), TC_A_BYTES + B_BYTES);
+      // ===================== TMA producer (warp-uniform loop, one elected lane issues) =====================
+      for (int i = 0; i < nloc; ++i) {
+        const int s = i % STAGES, ph = (i / STAGES) & 1, k0 = (kb0 + i) * TC_BK;
+        mbar_wait(empty_bar(s), ph ^ 1);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(full_bar(s), TC_A_BYTES + (BPRE ? 2 : 1) * B_BYTES);
           const uint32_t a_dst = smem_base + s * STAGE_BYTES, b_dst = a_dst + 2 * TC_A_BYTES;
           if (!AMN) tma_load_3d(a_dst, &mapA, full_bar(s), k0, m0, zA);
-          else
+          else {
+#pragma unroll
             for (int j = 0; j < TC_BM / 32; ++j) tma_load_3d(a_dst + j * 4096, &mapA, full_bar(s), m0 + 32 * j, k0, zA);
-          if (!BMN) tma_load_3d(b_dst, &mapB, full_bar(s), k0, n0, zB);
-          else
+          }
+          if (!BMN) {
+            tma_load_3d(b_dst, &mapB, full_bar(s), k0, n0, zB);
+            if (BPRE) tma_load_3d(b_dst + B_BYTES, &mapBlo, full_bar(s), k0, n0, zB);
+          } else {
+#pragma unroll
             for (int j = 0; j < BN / 32; ++j) tma_load_3d(b_dst + j * 4096, &mapB, full_bar(s), n0 + 32 * j, k0, zB);
+            if (BPRE) {
+#pragma unroll
+              for (int j = 0; j < BN / 32; ++j) tma_load_3d(b_dst + B_BYTES + j * 4096, &mapBlo, full_bar(s), n0 + 32 * j, k0, zB);
+            }
+          }
+          if (i < 12) TC_STAMP(8 + i);
         }
+        __syncwarp();
       }
     } else if (warp == 1) {
-      // ===================== MMA issuer (one thread) =====================
-      if (lane == 0) {
-        // instruction descriptor: D=f32, A=B=tf32, majors, N>>3, M>>4 (cute/arch/mma_sm100_desc.hpp InstrDescriptor)
-        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((AMN ? 1u : 0u) << 15) | ((BMN ? 1u : 0u) << 16) |
-                               ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-        // K-major tile: 128 B rows (32 k), 8-row swizzle atoms 1024 B apart (SBO); one MMA (K=8) = 32 B along the row.
-        // MN-major tile: 32-wide MN chunks as TMA boxes of [32 k-rows x 128 B] 4096 B apart (LBO), 4-row atoms
-        // 512 B apart (SBO); one MMA (K=8) = 8 k-rows = 1024 B.
-        constexpr uint32_t A_LBO = AMN ? 4096u : 16u, A_SBO = AMN ? 512u : 1024u, A_KSTEP = AMN ? 1024u : 32u, A_LAY = AMN ? 1u : 2u;
-        constexpr uint32_t B_LBO = BMN ? 4096u : 16u, B_SBO = BMN ? 512u : 1024u, B_KSTEP = BMN ? 1024u : 32u, B_LAY = BMN ? 1u : 2u;
-        for (int i = 0; i < nloc; ++i) {
-          const int s = i % STAGES, ph = (i / STAGES) & 1;
-          mbar_wait(ready_bar(s), ph);
-          tc_fence_after();
-          const uint32_t a_hi = smem_base + s * STAGE_BYTES, a_lo = a_hi + TC_A_BYTES;
-          const uint32_t b_hi = a_hi + 2 * TC_A_BYTES, b_lo = b_hi + B_BYTES;
+      // ===================== MMA issuer =====================
+      // The whole warp walks the pipeline in warp-uniform control flow (loop state and descriptors stay in uniform
+      // registers); one elected lane issues the MMAs and commits of a k-block.  Measured on B200: with the loop inside
+      // `if (lane == 0)` every tcgen05.mma cost ~100 cycles of single-thread issue work (waterfall R2UR loops +
+      // descriptor arithmetic) against 32-64 cycles of tensor-pipe time.
+      // instruction descriptor: D=f32, A=B=tf32, majors, N>>3, M>>4 (cute/arch/mma_sm100_desc.hpp InstrDescriptor)
+      constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((AMN ? 1u : 0u) << 15) | ((BMN ? 1u : 0u) << 16) |
+                                 ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      // K-major tile: 128 B rows (32 k), 8-row swizzle atoms 1024 B apart (SBO); one MMA (K=8) = 32 B along the row.
+      // MN-major tile: 32-wide MN chunks as TMA boxes of [32 k-rows x 128 B] 4096 B apart (LBO), 4-row atoms
+      // 512 B apart (SBO); one MMA (K=8) = 8 k-rows = 1024 B.
+      constexpr uint32_t A_LBO = AMN ? 4096u : 16u, A_SBO = AMN ? 512u : 1024u, A_KSTEP = AMN ? 1024u : 32u, A_LAY = AMN ? 1u : 2u;
+      constexpr uint32_t B_LBO = BMN ? 4096u : 16u, B_SBO = BMN ? 512u : 1024u, B_KSTEP = BMN ? 1024u : 32u, B_LAY = BMN ? 1u : 2u;
+      // 64-bit descriptor = {lo word: addr>>4 | (LBO>>4)<<16, hi word: SBO>>4 | version 1<<14 | layout<<29}; only the
+      // address field changes between MMAs (smem < 256 KB: adding (bytes>>4) never carries out of the 14-bit field)
+      constexpr uint32_t A_HIW = (A_SBO >> 4) | (1u << 14) | (A_LAY << 29), B_HIW = (B_SBO >> 4) | (1u << 14) | (B_LAY << 29);
+      constexpr uint32_t A_LOW = (A_LBO >> 4) << 16, B_LOW = (B_LBO >> 4) << 16;
+      const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
+      const uint32_t acc_lo = tb + Cfg::NMAIN * BN;
+      for (int i = 0; i < nloc; ++i) {
+        const int s = i % STAGES, ph = (i / STAGES) & 1;
+        mbar_wait(ready_bar(s), ph);
+        tc_fence_after();
+        if (i < 12 && lane == 0) TC_STAMP(44 + i);
+        const uint32_t a_hi = (((smem_base + s * STAGE_BYTES) >> 4) & 0x3FFFu) | A_LOW, a_lo = a_hi + (TC_A_BYTES >> 4);
+        const uint32_t b_hi = a_hi - A_LOW + B_LOW + (2 * TC_A_BYTES >> 4), b_lo = b_hi + (B_BYTES >> 4);
+        const uint32_t acc_hi = tb + (i % Cfg::NMAIN) * BN;       // main accumulators rotate per k-block
+        const uint32_t first_hi = i >= Cfg::NMAIN ? 1u : 0u, first_lo = i > 0 ? 1u : 0u;
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < TC_BK / 8; ++k)
+            tc_mma_tf32_w(acc_hi, a_hi + k * (A_KSTEP >> 4), A_HIW, b_hi + k * (B_KSTEP >> 4), B_HIW, idesc, k > 0 ? 1u : first_hi);
 #pragma unroll
           for (int k = 0; k < TC_BK / 8; ++k) {
-            const uint64_t dah = umma_desc(a_hi + k * A_KSTEP, A_LBO, A_SBO, A_LAY), dal = umma_desc(a_lo + k * A_KSTEP, A_LBO, A_SBO, A_LAY);
-            const uint64_t dbh = umma_desc(b_hi + k * B_KSTEP, B_LBO, B_SBO, B_LAY), dbl = umma_desc(b_lo + k * B_KSTEP, B_LBO, B_SBO, B_LAY);
-            const int j = i * (TC_BK / 8) + k;                                  // k-step index within this CTA
-            const uint32_t acc_lo = tmem_base + Cfg::NMAIN * BN, acc_hi = tmem_base + (j % Cfg::NMAIN) * BN;
-            tc_mma_tf32(acc_lo, dal, dbh, idesc, j > 0 ? 1u : 0u);
-            tc_mma_tf32(acc_lo, dah, dbl, idesc, 1u);
-            tc_mma_tf32(acc_hi, dah, dbh, idesc, j >= Cfg::NMAIN ? 1u : 0u);
+            tc_mma_tf32_w(acc_lo, a_lo + k * (A_KSTEP >> 4), A_HIW, b_hi + k * (B_KSTEP >> 4), B_HIW, idesc, k > 0 ? 1u : first_lo);
+            tc_mma_tf32_w(acc_lo, a_hi + k * (A_KSTEP >> 4), A_HIW, b_lo + k * (B_KSTEP >> 4), B_HIW, idesc, 1u);
           }
-          tc_commit(empty_bar(s));          // smem stage reusable once these MMAs retire
+          tc_commit(empty_bar(s));                     // smem stage reusable once these MMAs retire
+          if (i == nloc - 1) tc_commit(acc_bar);       // accumulators complete
         }
-        tc_commit(acc_bar);                 // accumulator complete
+        __syncwarp();
       }
-      __syncwarp();
     } else {
       // ===================== converters: x -> (hi, lo) in shared memory =====================
       const int ct = tid - 64;
       for (int i = 0; i < nloc; ++i) {
         const int s = i % STAGES, ph = (i / STAGES) & 1;
         mbar_wait(full_bar(s), ph);
-        uint8_t* st = smem + s * STAGE_BYTES;
-#pragma unroll 4
-        for (int c = ct; c < (TC_A_BYTES + B_BYTES) / 16; c += 128) {
-          const bool isA = c < TC_A_BYTES / 16;
-          float4* hi = reinterpret_cast<float4*>(st + (isA ? 0 : 2 * TC_A_BYTES)) + (isA ? c : c - TC_A_BYTES / 16);
-          float4* lo = reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(hi) + (isA ? TC_A_BYTES : B_BYTES));
-          const float4 v = *hi;
-          uint4 h, l;
-          h.x = to_tf32(v.x); h.y = to_tf32(v.y); h.z = to_tf32(v.z); h.w = to_tf32(v.w);
-          l.x = to_tf32(v.x - __uint_as_float(h.x)); l.y = to_tf32(v.y - __uint_as_float(h.y));
-          l.z = to_tf32(v.z - __uint_as_float(h.z)); l.w = to_tf32(v.w - __uint_as_float(h.w));
-          *reinterpret_cast<uint4*>(hi) = h;
-          *reinterpret_cast<uint4*>(lo) = l;
-        }
+        if (ct == 0 && i < 12) TC_STAMP(20 + i);
+        const uint32_t st = smem_base + s * STAGE_BYTES;
+        split_tile<TC_A_BYTES / 16, TC_A_BYTES>(st, ct);
+        if (!BPRE) split_tile<B_BYTES / 16, B_BYTES>(st + 2 * TC_A_BYTES, ct);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
         mbar_arrive(ready_bar(s));
+        if (ct == 0 && i < 12) TC_STAMP(32 + i);
       }
-      // ===================== epilogue: TMEM -> registers -> global =====================
+      // ===================== epilogue: TMEM -> registers -> smem transpose -> coalesced global =====================
       mbar_wait(acc_bar, 0);
       tc_fence_after();
+      if (ct == 0) TC_STAMP(2);
       const int q = warp & 3;                      // TMEM lane quarter this warp may access
-      const int m = m0 + q * 32 + lane;
-      float* C = p.C + z * p.zsC;
-      const float* bias = p.bias ? p.bias + z * p.zsBias : nullptr;
-      const float* mask = p.mask ? p.mask + z * p.zsMask : nullptr;
-      const float* res1 = p.res1 ? p.res1 + z * p.zsR1 : nullptr;
-      const float* res2 = p.res2 ? p.res2 + z * p.zsR2 : nullptr;
-      const float rd = (p.rowdiv && m < p.M) ? (p.rowdiv + z * p.zsRow)[m] : 1.f;
-      const bool first_split = blockIdx.y == 0;
+      const uint32_t stg = smem_base + q * (32 * TC_EPI_LD * 4);            // pipeline stages are idle now (shared address)
+      const int cq = lane & 7, rsub = lane >> 3;
+      EpiArgs ea;
+      ea.mrow = m0 + q * 32 + rsub;                                // first row this lane stores (then +4 per iteration)
+      ea.rows = min(32, p.M - (m0 + q * 32));                      // valid rows of this warp's 32-row slab
+      ea.C = p.C + z * p.zsC + (long long)ea.mrow * p.ldc + n0 + cq * 4;
+      ea.bias = (p.bias && blockIdx.y == 0) ? p.bias + z * p.zsBias : nullptr;
+      ea.mask = p.mask ? p.mask + z * p.zsMask + (long long)ea.mrow * p.ldmask + n0 + cq * 4 : nullptr;
+      ea.res1 = p.res1 ? p.res1 + z * p.zsR1 + (long long)ea.mrow * p.ldr1 + n0 + cq * 4 : nullptr;
+      ea.res2 = p.res2 ? p.res2 + z * p.zsR2 + (long long)ea.mrow * p.ldr2 + n0 + cq * 4 : nullptr;
+      ea.vec = p.vecE != 0;
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int m = ea.mrow + 4 * it;
+        ea.rd[it] = (p.rowdiv && m < p.M) ? __ldg(p.rowdiv + z * p.zsRow + m) : 1.f;
+      }
+      // which specialised epilogue (all warp-uniform): 0 plain, 1 /F (+column scale), 2 relu-mask, 3 residuals,
+      // 4 accumulate, 5 split-K atomics, 6 anything else
+      int ekind;
+      {
+        const bool lin = !p.rowdiv && !p.mask && !p.res1 && !p.res2 && p.colscale_n == 0;
+        if (p.splitk > 1) ekind = 5;
+        else if (p.accumulate) ekind = (lin && !p.relu && !p.bias) ? 4 : 6;
+        else if (lin) ekind = 0;
+        else if (p.rowdiv && !p.mask && !p.res1 && !p.res2) ekind = 1;
+        else if (p.mask && !p.rowdiv && !p.res1 && !p.res2 && p.colscale_n == 0 && !p.relu && !p.bias) ekind = 2;
+        else if (p.res1 && !p.rowdiv && !p.mask && p.colscale_n == 0 && !p.relu && !p.bias) ekind = 3;
+        else ekind = 6;
+      }
+      const int nused = min(Cfg::NMAIN, nloc);      // main accumulators that received at least one k-block
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
+        if (n0 + c0 >= p.N) break;
         float sum[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) sum[j] = 0.f;
-        const int nused = min(Cfg::NMAIN, nloc * (TC_BK / 8));      // accumulators that received at least one k-step
-#pragma unroll 1
-        for (int a = 0; a <= nused; ++a) {                          // a == nused: the lo accumulator
+        {
           uint32_t r[32];
-          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((a == nused ? Cfg::NMAIN : a) * BN + c0);
-          asm volatile(
-              "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-              "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-              "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-              : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-                "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
-                "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
-                "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-              : "r"(taddr)
-              : "memory");
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(Cfg::NMAIN * BN + c0), r);     // lo accumulator
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int j = 0; j < 32; ++j) sum[j] = __uint_as_float(r[j]);
+        }
+#pragma unroll 1
+        for (int a = 0; a < nused; ++a) {
+          uint32_t r[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * BN + c0), r);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
           for (int j = 0; j < 32; ++j) sum[j] += __uint_as_float(r[j]);
         }
-        if (m < p.M) {
+        if (ct == 0 && c0 == 0) TC_STAMP(5);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int n = n0 + c0 + j;
-            if (n < p.N) {
-              float v = p.alpha * sum[j];
-              if (bias && first_split) v += bias[n];
-              if (p.relu) v = fmaxf(v, 0.f);
-              if (p.rowdiv) v = v / rd;
-              if (n < p.colscale_n) v *= p.colscale;
-              if (mask) v = mask[(long long)m * p.ldmask + n] > 0.f ? v : 0.f;
-              if (res1) v += res1[(long long)m * p.ldr1 + n];
-              if (res2) v += res2[(long long)m * p.ldr2 + n];
-              float* c = C + (long long)m * p.ldc + n;
-              if (p.splitk > 1) atomicAdd(c, v);
-              else if (p.accumulate) *c += v;
-              else *c = v;
-            }
-          }
+        for (int k = 0; k < 8; ++k)
+          sts128(stg + (lane * TC_EPI_LD + 4 * k) * 4, make_float4(sum[4 * k], sum[4 * k + 1], sum[4 * k + 2], sum[4 * k + 3]));
+        __syncwarp();
+        if (ct == 0 && c0 == 0) TC_STAMP(6);
+        const int n = n0 + c0 + cq * 4;
+        switch (ekind) {
+          case 0: tc_epi_chunk<false, false, 0, EM_STORE>(p, ea, stg, rsub, cq, n, c0); break;
+          case 1: tc_epi_chunk<true, false, 0, EM_STORE>(p, ea, stg, rsub, cq, n, c0); break;
+          case 2: tc_epi_chunk<false, true, 0, EM_STORE>(p, ea, stg, rsub, cq, n, c0); break;
+          case 3: tc_epi_chunk<false, false, 2, EM_STORE>(p, ea, stg, rsub, cq, n, c0); break;
+          case 4: tc_epi_chunk<false, false, 0, EM_ACCUM>(p, ea, stg, rsub, cq, n, c0); break;
+          case 5: tc_epi_chunk<false, false, 0, EM_ATOMIC>(p, ea, stg, rsub, cq, n, c0); break;
+          default: tc_epi_generic(p, ea, stg, rsub, cq, n, c0); break;
         }
+        __syncwarp();
+        if (ct == 0 && c0 == 0) TC_STAMP(7);
       }
     }
   }
+  if (tid == 64) TC_STAMP(3);
   tc_fence_before();
   __syncthreads();
+  if (tid == 0) TC_STAMP(4);
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
@@ -342,9 +556,9 @@ inline bool gemm_tc_eligible(const GemmP& p) {
   return true;
 }
 
-template <int BN, bool AMN, bool BMN>
-inline int gemm_tc_launch(const GemmP& p, const CUtensorMap& ma, const CUtensorMap& mb, cudaStream_t st) {
-  auto kern = gemm_tc_kernel<BN, AMN, BMN>;
+template <int BN, bool AMN, bool BMN, bool BPRE>
+inline int gemm_tc_launch(const GemmP& p, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mbl, cudaStream_t st) {
+  auto kern = gemm_tc_kernel<BN, AMN, BMN, BPRE>;
   static bool attr_done = false;
   if (!attr_done) {
     SGRL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN>::SMEM));
@@ -352,42 +566,54 @@ inline int gemm_tc_launch(const GemmP& p, const CUtensorMap& ma, const CUtensorM
   }
   dim3 grid(ceil_div(p.M, TC_BM) * ceil_div(p.N, BN), p.splitk, p.nb);
   prof_begin(PC_GEMM_TC, 2.0 * p.M * p.N * (double)p.K * p.nb, st);
-  kern<<<grid, TC_THREADS, TcCfg<BN>::SMEM, st>>>(ma, mb, p);
+  kern<<<grid, TC_THREADS, TcCfg<BN>::SMEM, st>>>(ma, mb, mbl, p);
   prof_end(st);
   SGRL_LAUNCH_OK();
   return 0;
 }
 
+template <int BN, bool BPRE>
+inline int gemm_tc_dispatch(const GemmP& p, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mbl, cudaStream_t st) {
+  if (!p.transA && !p.transB) return gemm_tc_launch<BN, false, false, BPRE>(p, ma, mb, mbl, st);
+  if (!p.transA && p.transB) return gemm_tc_launch<BN, false, true, BPRE>(p, ma, mb, mbl, st);
+  if (p.transA && p.transB) return gemm_tc_launch<BN, true, true, BPRE>(p, ma, mb, mbl, st);
+  return gemm_tc_launch<BN, true, false, BPRE>(p, ma, mb, mbl, st);
+}
+
+extern long long* g_gemm_trace;   // sgrl_gemm_trace(): device buffer of 64 int64 for TC_STAMP, or nullptr
+
 inline int gemm_tc(const GemmP& p_in, cudaStream_t st) {
   GemmP p = p_in;
+  p.dbg = g_gemm_trace;
+  static const int sched_env = getenv("SGRL_TC_SCHED") ? atoi(getenv("SGRL_TC_SCHED")) : 0;
+  p.sched = sched_env;
   if (p.M <= 0 || p.N <= 0 || p.nb <= 0) return 0;
   SGRL_CHECK(gemm_tc_eligible(p), "gemm_tc: operands not TMA-compatible");
   SGRL_CHECK(p.splitk == 1 || (!p.relu && !p.rowdiv && !p.mask && !p.res1 && !p.res2 && p.colscale_n == 0), "gemm_tc: split-K only with a linear epilogue");
+  SGRL_CHECK((p.Blo == nullptr) == (p.Bhi == nullptr), "gemm_tc: Bhi and Blo go together");
+  SGRL_CHECK(p.Blo == nullptr || (host_vec_ok(p.Blo, p.ldb, p.zsB) && host_vec_ok(p.Bhi, p.ldb, p.zsB)), "gemm_tc: pre-split B parts not TMA-compatible");
+  const float* Bsrc = p.Blo ? p.Bhi : p.B;
   // tile width: 128 unless that leaves most SMs idle
   const long long ctas128 = (long long)ceil_div(p.M, TC_BM) * ceil_div(p.N, 128) * p.nb * p.splitk;
   const int BN = (p.N > 64 && ctas128 >= 100) ? 128 : 64;
   const int nkb = ceil_div(p.K, TC_BK);
   if (p.splitk > nkb) p.splitk = nkb;
+  p.vecE = host_vec_ok(p.C, p.ldc, p.zsC) && (!p.mask || host_vec_ok(p.mask, p.ldmask, p.zsMask)) &&
+           (!p.res1 || host_vec_ok(p.res1, p.ldr1, p.zsR1)) && (!p.res2 || host_vec_ok(p.res2, p.ldr2, p.zsR2));
   const long long nzA = p.zsA ? p.nb : 1, nzB = p.zsB ? p.nb : 1;
-  CUtensorMap ma, mb;
+  CUtensorMap ma, mb, mbl;
   // K-major operand: inner = K (contiguous), outer = rows; MN-major: inner = rows (contiguous), outer = K
   if (!p.transA) SGRL_TRY(make_tmap(&ma, p.A, p.K, p.M, nzA, p.lda, p.zsA, 32, TC_BM, 0));
   else SGRL_TRY(make_tmap(&ma, p.A, p.M, p.K, nzA, p.lda, p.zsA, 32, 32, 1));
-  if (!p.transB) SGRL_TRY(make_tmap(&mb, p.B, p.K, p.N, nzB, p.ldb, p.zsB, 32, BN, 0));
-  else SGRL_TRY(make_tmap(&mb, p.B, p.N, p.K, nzB, p.ldb, p.zsB, 32, 32, 1));
-#define SGRL_TC_CASE(bn, amn, bmn) return gemm_tc_launch<bn, amn, bmn>(p, ma, mb, st)
-  if (BN == 128) {
-    if (!p.transA && !p.transB) SGRL_TC_CASE(128, false, false);
-    if (!p.transA && p.transB) SGRL_TC_CASE(128, false, true);
-    if (p.transA && p.transB) SGRL_TC_CASE(128, true, true);
-    SGRL_TC_CASE(128, true, false);
-  } else {
-    if (!p.transA && !p.transB) SGRL_TC_CASE(64, false, false);
-    if (!p.transA && p.transB) SGRL_TC_CASE(64, false, true);
-    if (p.transA && p.transB) SGRL_TC_CASE(64, true, true);
-    SGRL_TC_CASE(64, true, false);
+  if (!p.transB) SGRL_TRY(make_tmap(&mb, Bsrc, p.K, p.N, nzB, p.ldb, p.zsB, 32, BN, 0));
+  else SGRL_TRY(make_tmap(&mb, Bsrc, p.N, p.K, nzB, p.ldb, p.zsB, 32, 32, 1));
+  mbl = mb;
+  if (p.Blo) {
+    if (!p.transB) SGRL_TRY(make_tmap(&mbl, p.Blo, p.K, p.N, nzB, p.ldb, p.zsB, 32, BN, 0));
+    else SGRL_TRY(make_tmap(&mbl, p.Blo, p.N, p.K, nzB, p.ldb, p.zsB, 32, 32, 1));
   }
-#undef SGRL_TC_CASE
+  if (BN == 128) return p.Blo ? gemm_tc_dispatch<128, true>(p, ma, mb, mbl, st) : gemm_tc_dispatch<128, false>(p, ma, mb, mbl, st);
+  return p.Blo ? gemm_tc_dispatch<64, true>(p, ma, mb, mbl, st) : gemm_tc_dispatch<64, false>(p, ma, mb, mbl, st);
 }
 
 }  // namespace sgrl

@@ -39,6 +39,7 @@ struct NetCtx {
   int kind, L, nb, T;
   NetLayout lay;
   const float* params; long long zsP;     // live arena; z-stride = lay.live_floats
+  const float* phi; const float* plo;     // optional tf32 hi/lo split of the live arena (same layout) for the tcgen05 GEMMs
   float* grads; long long zsG;            // gradient arena (same layout) or nullptr
   StashLayout st; float* stash; long long zsS;
   WsLayout wl; float* ws; long long zsW;
@@ -67,6 +68,7 @@ inline GemmP lin(const NetCtx& c, const float* X, int ldx, long long zsX, long l
   GemmP g = gemm_defaults();
   g.A = X; g.zsA = zsX; g.lda = ldx; g.transA = 0;
   g.B = c.P(w_off); g.zsB = c.zsP; g.ldb = K; g.transB = 0;
+  if (c.phi) { g.Bhi = c.phi + w_off; g.Blo = c.plo + w_off; }
   g.C = Y; g.zsC = zsY; g.ldc = ldy;
   g.M = M; g.N = N; g.K = K; g.nb = c.nb;
   if (b_off >= 0) { g.bias = c.P(b_off); g.zsBias = c.zsP; }
@@ -77,6 +79,7 @@ inline GemmP dgrad(const NetCtx& c, const float* dY, int lddy, long long w_off, 
   GemmP g = gemm_defaults();
   g.A = dY; g.zsA = c.zsW; g.lda = lddy; g.transA = 0;
   g.B = c.P(w_off); g.zsB = c.zsP; g.ldb = ldw; g.transB = 1;
+  if (c.phi) { g.Bhi = c.phi + w_off; g.Blo = c.plo + w_off; }
   g.C = dX; g.zsC = c.zsW; g.ldc = lddx;
   g.M = M; g.N = Kw; g.K = Nw; g.nb = c.nb;
   return g;

@@ -8,6 +8,7 @@ namespace sgrl {
 thread_local char g_err[512] = "";
 long long g_launches = 0;
 Prof g_prof;
+long long* g_gemm_trace = nullptr;
 }
 using namespace sgrl;
 
@@ -15,7 +16,7 @@ using namespace sgrl;
 
 extern "C" {
 
-int sgrl_version(void) { return 1; }
+int sgrl_version(void) { return 2; }
 const char* sgrl_last_error(void) { return g_err; }
 
 long long sgrl_launch_count(void) { return g_launches; }
@@ -39,6 +40,8 @@ int sgrl_profile_collect(double* ms, double* work, long long* count, int ncls) {
   g_prof.n = 0;
   return 0;
 }
+
+int sgrl_gemm_trace(long long* buf64) { g_gemm_trace = buf64; return 0; }
 
 int sgrl_param_count(int kind, int n_layers) {
   if (n_layers < 1 || n_layers > MAX_LAYERS || (kind != ACTOR && kind != CRITIC)) return fail(-2, "bad kind/n_layers", __FILE__, __LINE__);
@@ -88,6 +91,8 @@ static int make_ctx(const SgrlNetCall* k, cudaStream_t st, NetCtx& c) {
   c.kind = k->kind; c.L = k->n_layers; c.nb = k->nb; c.T = k->T;
   c.lay = make_layout(k->kind, k->n_layers);
   c.params = k->params; c.zsP = c.lay.live_floats;
+  SGRL_CHECK((k->params_hi == nullptr) == (k->params_lo == nullptr), "params_hi and params_lo go together");
+  c.phi = k->params_hi; c.plo = k->params_lo;
   c.grads = k->grads; c.zsG = c.lay.live_floats;
   c.st = make_stash(k->kind, k->n_layers, k->T, k->keep);
   SGRL_CHECK(k->stash_stride >= c.st.total, "stash_stride smaller than sgrl_stash_floats()");
@@ -163,6 +168,18 @@ int sgrl_gemm(const float* A, int lda, int trans_a, const float* B, int ldb, int
   return gemm_simt(g, ST(stream));
 }
 
+int sgrl_gemm_presplit(const float* A, int lda, int trans_a, const float* B_hi, const float* B_lo, int ldb, int trans_b, float* C, int ldc,
+                       int M, int N, int K, float alpha, const float* bias, const float* rowdiv, int relu, int accumulate, int splitk,
+                       sgrl_stream_t stream) {
+  SGRL_CHECK(A && B_hi && B_lo && C, "null pointer");
+  GemmP g = gemm_defaults();
+  g.A = A; g.lda = lda; g.transA = trans_a; g.B = B_hi; g.Bhi = B_hi; g.Blo = B_lo; g.ldb = ldb; g.transB = trans_b; g.C = C; g.ldc = ldc;
+  g.M = M; g.N = N; g.K = K; g.alpha = alpha; g.bias = bias; g.rowdiv = rowdiv; g.relu = relu; g.accumulate = accumulate;
+  g.splitk = splitk < 1 ? 1 : splitk;
+  SGRL_CHECK(gemm_tc_eligible(g), "shape/epilogue not eligible for the tcgen05 path");
+  return gemm_tc(g, ST(stream));
+}
+
 int sgrl_td3_smooth_action(const float* pi_target, const float* noise, float* next_action, float noise_clip, float max_action,
                            int64_t n, sgrl_stream_t stream) {
   SGRL_CHECK(pi_target && noise && next_action, "null pointer");
@@ -197,12 +214,22 @@ int sgrl_sumsq(const float* g, int64_t n, float* out, sgrl_stream_t stream) {
   return 0;
 }
 
+int sgrl_split_tf32(const float* w, float* hi, float* lo, int64_t n, sgrl_stream_t stream) {
+  SGRL_CHECK(w && hi && lo, "null pointer");
+  SGRL_CHECK((n & 3) == 0 && aligned16(w) && aligned16(hi) && aligned16(lo), "arenas must be 16-byte aligned, n % 4 == 0");
+  split_tf32_kernel<<<grid_for_flat(n), 256, 0, ST(stream)>>>(w, hi, lo, n);
+  SGRL_LAUNCH_OK();
+  return 0;
+}
+
 int sgrl_adam_clip(float* p, const float* g, float* m, float* v, int64_t n, const float* sumsq, const int32_t* step, float lr,
-                   float beta1, float beta2, float eps, float max_norm, float grad_scale, sgrl_stream_t stream) {
+                   float beta1, float beta2, float eps, float max_norm, float grad_scale, float* p_hi, float* p_lo,
+                   sgrl_stream_t stream) {
   SGRL_CHECK(p && g && m && v && sumsq && step, "null pointer");
+  SGRL_CHECK((p_hi == nullptr) == (p_lo == nullptr) && (!p_hi || (aligned16(p_hi) && aligned16(p_lo))), "p_hi/p_lo go together, 16-byte aligned");
   SGRL_CHECK((n & 3) == 0 && aligned16(p) && aligned16(g) && aligned16(m) && aligned16(v), "arenas must be 16-byte aligned, n % 4 == 0");
   AdamCfg c{lr, beta1, beta2, eps, max_norm, grad_scale};
-  adam_clip_kernel<<<grid_for_flat(n), 256, 0, ST(stream)>>>(p, g, m, v, n, sumsq, step, c);
+  adam_clip_kernel<<<grid_for_flat(n), 256, 0, ST(stream)>>>(p, g, m, v, n, sumsq, step, c, p_hi, p_lo);
   SGRL_LAUNCH_OK();
   return 0;
 }
@@ -214,10 +241,13 @@ int sgrl_bump_step(int32_t* step, sgrl_stream_t stream) {
   return 0;
 }
 
-int sgrl_polyak(float* target, const float* source, int64_t n, float tau, sgrl_stream_t stream) {
+int sgrl_polyak(float* target, const float* source, int64_t n, float tau, float* t_hi, float* t_lo, int64_t n_split,
+                sgrl_stream_t stream) {
   SGRL_CHECK(target && source, "null pointer");
+  SGRL_CHECK((t_hi == nullptr) == (t_lo == nullptr) && (!t_hi || (aligned16(t_hi) && aligned16(t_lo) && (n_split & 3) == 0 && n_split <= n)),
+             "t_hi/t_lo go together, 16-byte aligned, n_split % 4 == 0");
   SGRL_CHECK((n & 3) == 0 && aligned16(target) && aligned16(source), "arenas must be 16-byte aligned, n % 4 == 0");
-  polyak_kernel<<<grid_for_flat(n), 256, 0, ST(stream)>>>(target, source, n, tau, (float)(1.0 - (double)tau));
+  polyak_kernel<<<grid_for_flat(n), 256, 0, ST(stream)>>>(target, source, n, tau, (float)(1.0 - (double)tau), t_hi, t_lo, n_split);
   SGRL_LAUNCH_OK();
   return 0;
 }

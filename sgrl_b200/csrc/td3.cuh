@@ -87,9 +87,27 @@ struct AdamCfg { float lr, beta1, beta2, eps, max_norm; float grad_scale; };
 //   coef = min(1, max_norm / (||g|| + 1e-6))     (torch.nn.utils.clip_grad_norm_)
 //   m = m + (1-b1)(g - m);  v = b2 v + (1-b2) g^2;  p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps)
 // grad_scale pre-multiplies g (1/world_size after a sum all-reduce).
+// hi/lo (nullable): the refreshed tf32 split of the parameters for the tcgen05 projections (csrc/gemm_tc.cuh).
+__device__ __forceinline__ void split_store4(float4 pv, float* hi, float* lo, long long i4) {
+  float4 h, l;
+  const float* x = &pv.x; float* hh = &h.x; float* ll = &l.x;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const unsigned hb = (__float_as_uint(x[k]) + 0x1000u) & 0xFFFFE000u;
+    hh[k] = __uint_as_float(hb);
+    ll[k] = __uint_as_float((__float_as_uint(x[k] - hh[k]) + 0x1000u) & 0xFFFFE000u);
+  }
+  stg4(hi + i4 * 4, h); stg4(lo + i4 * 4, l);
+}
+
+__global__ void __launch_bounds__(256) split_tf32_kernel(const float* __restrict__ w, float* __restrict__ hi, float* __restrict__ lo, long long n) {
+  const long long n4 = n >> 2;
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n4; i += gridDim.x * 256LL) split_store4(ldg4(w + i * 4), hi, lo, i);
+}
+
 __global__ void __launch_bounds__(256) adam_clip_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                                         float* __restrict__ v, long long n, const float* __restrict__ sumsq,
-                                                        const int* __restrict__ step, AdamCfg c) {
+                                                        const int* __restrict__ step, AdamCfg c, float* __restrict__ hi, float* __restrict__ lo) {
   __shared__ float sh[3];
   if (threadIdx.x == 0) {
     const float nrm = sqrtf(*sumsq) * c.grad_scale;
@@ -116,6 +134,7 @@ __global__ void __launch_bounds__(256) adam_clip_kernel(float* __restrict__ p, c
       pp[k] -= step_size * (mm[k] / (sqrtf(vq[k]) / bc2s + c.eps));
     }
     stg4(p + i * 4, pv); stg4(m + i * 4, mv); stg4(v + i * 4, vv);
+    if (hi) split_store4(pv, hi, lo, i);
   }
 }
 
@@ -124,8 +143,9 @@ __global__ void bump_step_kernel(int* step) { *step += 1; }
 // theta_t <- tau*theta + (1-tau)*theta_t                                                    functional.py:7-10
 // Rounded exactly like the reference's three fp32 tensor ops (mul, mul, add — no FMA contraction):
 // the per-step change tau*(theta-theta_t) ~ 5e-7 is a few ulps of O(1) weights, so op order is visible.
+// hi/lo (nullable) cover the first n_split floats (the live prefix of the arena).
 __global__ void __launch_bounds__(256) polyak_kernel(float* __restrict__ tgt, const float* __restrict__ src, long long n,
-                                                     float tau, float one_minus_tau) {
+                                                     float tau, float one_minus_tau, float* __restrict__ hi, float* __restrict__ lo, long long n_split) {
   const long long n4 = n >> 2;
   for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n4; i += gridDim.x * 256LL) {
     float4 t = *reinterpret_cast<float4*>(tgt + i * 4);
@@ -135,6 +155,7 @@ __global__ void __launch_bounds__(256) polyak_kernel(float* __restrict__ tgt, co
     t.z = __fadd_rn(__fmul_rn(tau, s.z), __fmul_rn(one_minus_tau, t.z));
     t.w = __fadd_rn(__fmul_rn(tau, s.w), __fmul_rn(one_minus_tau, t.w));
     stg4(tgt + i * 4, t);
+    if (hi && i * 4 < n_split) split_store4(t, hi, lo, i);
   }
 }
 

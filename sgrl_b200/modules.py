@@ -122,6 +122,8 @@ class SetNetModule(nn.Module):
                 self._slots.append((p, a, n))
         self._arena = arena
         self._garena: Optional[torch.Tensor] = None
+        self._split: Optional[torch.Tensor] = None     # (2, nb*live): tf32 hi / lo parts of the live arena
+        self._split_fresh = False                      # True only while the agent's fused kernels keep it in sync
         self._anchor = torch.zeros((), device=device, requires_grad=True)
 
     def _ordered_table(self):
@@ -180,6 +182,7 @@ class SetNetModule(nn.Module):
                 p.grad = None
         self._arena = arena
         self._garena = None
+        self._split, self._split_fresh = None, False
         self._anchor = torch.zeros((), device=dev, requires_grad=True)
         self._tables_cache.clear()
 
@@ -196,6 +199,36 @@ class SetNetModule(nn.Module):
         if self._garena is None or self._garena.device != self._arena.device:
             self._garena = torch.zeros(self._nb * self._live, dtype=torch.float32, device=self._arena.device)
         return self._garena
+
+    # ------------------------------------------------------------------ pre-split weights for the tcgen05 projections
+    SPLIT_MIN_TOKENS = 64      # below this every projection is launch-bound: not worth a pass over the arena
+
+    def split_arena(self) -> torch.Tensor:
+        if self._split is None or self._split.device != self._arena.device:
+            self._split = torch.empty(2, self._nb * self._live, dtype=torch.float32, device=self._arena.device)
+            self._split_fresh = False
+        return self._split
+
+    def refresh_split(self):
+        """hi = tf32(w), lo = tf32(w - hi) over the live arena (one streaming pass)."""
+        sp = self.split_arena()
+        check(lib.sgrl_split_tf32(ptr(self.live_arena), ptr(sp[0]), ptr(sp[1]), sp.shape[1], stream()), "sgrl_split_tf32")
+        self.mark_split_fresh()
+
+    def mark_split_fresh(self):
+        """Called after a kernel (split / fused Adam / Polyak) rewrote the split from the current arena contents.
+        torch-side in-place writes to the parameters bump the arena's version counter and invalidate the mark."""
+        self._split_fresh, self._split_version = True, self._arena._version
+
+    def _split_for(self, T: int, trusted: bool):
+        """(hi, lo) to hand to the kernels, or (None, None).  Only a caller that owns every write to the arena
+        (Agent.update: fused Adam / Polyak keep the split in sync) may pass trusted=True; everyone else gets a
+        split recomputed from the current parameter values, because nn.Parameters can be modified behind our back."""
+        if not self.use_tc or T < self.SPLIT_MIN_TOKENS or self._arena.device.type != "cuda":
+            return None, None
+        if not (trusted and self._split is not None and self._split_fresh and self._split_version == self._arena._version):
+            self.refresh_split()
+        return self._split[0], self._split[1]
 
     # ------------------------------------------------------------------ morphology protocol
     def change_morphology(self, graph):
@@ -220,11 +253,12 @@ class SetNetModule(nn.Module):
         return t
 
     # ------------------------------------------------------------------ raw kernel passes
-    def _call(self, tb: GraphTables, nb: int, keep: int, stash, grads=None, ws=None) -> NetCall:
+    def _call(self, tb: GraphTables, nb: int, keep: int, stash, grads=None, ws=None, split=(None, None)) -> NetCall:
         k = NetCall()
         k.kind, k.n_layers, k.nb, k.T, k.G = self._kind, self._n_layers, nb, tb.T, tb.G
         k.keep, k.use_tc = keep, int(self.use_tc)
         k.params = ptr(self.live_arena)
+        k.params_hi, k.params_lo = ptr(split[0]), ptr(split[1])
         k.grads = ptr(grads)
         k.stash = ptr(stash)
         k.stash_stride = stash.numel() // nb
@@ -236,7 +270,7 @@ class SetNetModule(nn.Module):
         return k
 
     def forward_raw(self, tb: GraphTables, obs: torch.Tensor, act: Optional[torch.Tensor], keep: bool, nb: Optional[int] = None,
-                    out: Optional[torch.Tensor] = None):
+                    out: Optional[torch.Tensor] = None, trusted_split: bool = False):
         """Run nb nets on tokens obs (T,41) [act (T,3)].  Returns (out (nb,T,od), stash)."""
         nb = self._nb if nb is None else nb
         od = 3 if self._kind == ACTOR else 1
@@ -247,18 +281,18 @@ class SetNetModule(nn.Module):
         stash = torch.empty(nb * per, dtype=torch.float32, device=dev)
         if out is None:
             out = torch.empty(nb, tb.T, od, dtype=torch.float32, device=dev)
-        k = self._call(tb, nb, int(keep), stash)
+        k = self._call(tb, nb, int(keep), stash, split=self._split_for(tb.T, trusted_split))
         check(lib.sgrl_set_forward(C.byref(k), ptr(obs), 0, ptr(act), 0, ptr(out), tb.T * od, stream()), "sgrl_set_forward")
         return out, stash
 
     def backward_raw(self, tb: GraphTables, stash: torch.Tensor, dout: torch.Tensor, nb: int, grads: Optional[torch.Tensor],
-                     want_dact: bool):
+                     want_dact: bool, trusted_split: bool = False):
         """dout (nb,T,od).  Accumulates parameter gradients into `grads` (None: data-only)."""
         dev = self._arena.device
         ws = torch.empty(nb * lib.sgrl_ws_floats(tb.T), dtype=torch.float32, device=dev)
         dact = torch.empty(nb, tb.T, 3, dtype=torch.float32, device=dev) if want_dact else None
         od = 3 if self._kind == ACTOR else 1
-        k = self._call(tb, nb, 1, stash, grads=grads, ws=ws)
+        k = self._call(tb, nb, 1, stash, grads=grads, ws=ws, split=self._split_for(tb.T, trusted_split))
         check(lib.sgrl_set_backward(C.byref(k), ptr(dout), tb.T * od, 1 if grads is not None else 0, ptr(dact), tb.T * 3, stream()),
               "sgrl_set_backward")
         return dact

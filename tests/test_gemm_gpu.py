@@ -75,3 +75,24 @@ def test_tc_rejects_unaligned_operands():
         run_gemm(X, 145, 0, W, 145, 0, Y, 128, 256, 128, 145, use_tc=1)
     run_gemm(X, 145, 0, W, 145, 0, Y, 128, 256, 128, 145, use_tc=0)
     assert rel(Y, X.double() @ W.double().T) < 2e-6
+
+
+@pytest.mark.parametrize("M,N,K,tb", [(300, 256, 1024, 0), (2304, 768, 256, 0), (77, 252, 128, 0), (900, 256, 768, 1), (2700, 128, 252, 1), (600, 1024, 256, 1)])
+def test_presplit_weights(M, N, K, tb):
+    """tcgen05 path with the weight operand pre-split into tf32 hi/lo arenas (sgrl_split_tf32): Y = X W^T (tb=0) and
+    dX = dY W (tb=1, W is (K,N) row-major read MN-major)."""
+    from sgrl_b200._lib import lib, ptr, stream, check
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    X = torch.randn(M, K, device="cuda", generator=g)
+    W = (torch.randn(N, K, device="cuda", generator=g) if not tb else torch.randn(K, N, device="cuda", generator=g)) / K ** 0.5
+    hi, lo = torch.empty_like(W), torch.empty_like(W)
+    check(lib.sgrl_split_tf32(ptr(W), ptr(hi), ptr(lo), W.numel(), stream()))
+    assert torch.all((hi.view(torch.int32) & 0x1FFF) == 0) and torch.all((lo.view(torch.int32) & 0x1FFF) == 0)
+    assert rel(hi.double() + lo.double(), W) < 3e-7
+    b = torch.randn(N, device="cuda", generator=g)
+    Y = torch.full((M, N + 4), 7.0, device="cuda")
+    check(lib.sgrl_gemm_presplit(ptr(X), K, 0, ptr(hi), ptr(lo), W.shape[1], tb, ptr(Y), N + 4, M, N, K, 1.0, ptr(b), None, 0, 0, 1, stream()))
+    torch.cuda.synchronize()
+    ref = X.double() @ (W.double().T if not tb else W.double()) + b.double()
+    assert rel(Y[:, :N], ref) < TOL[1]
+    assert torch.all(Y[:, N:] == 7.0)
