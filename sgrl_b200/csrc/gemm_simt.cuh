@@ -33,6 +33,7 @@ struct GemmP {
   const float* Bhi; const float* Blo;       // tcgen05 path only, optional: B pre-split into tf32 hi/lo parts (same layout/strides as B)
   int vecE;                                 // set by the tcgen05 launcher: C/mask/res rows allow float4 access
   int sched;                                // tcgen05 MMA issue order experiment knob (SGRL_TC_SCHED)
+  int rawhi;                                // tcgen05: hi operand = the raw fp32 tile (tensor core truncates), converters write lo only
   long long* dbg;                           // optional (tools/gemm_trace.py): SM-clock timestamps of CTA 0's pipeline phases
 };
 

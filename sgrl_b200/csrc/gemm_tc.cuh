@@ -29,7 +29,10 @@
 
 namespace sgrl {
 
-constexpr int TC_BM = 128, TC_BK = 32, TC_THREADS = 192;
+constexpr int TC_BM = 128, TC_BK = 32;
+constexpr int TC_CONV_WARPS = 8;                              // converter warps (also the epilogue warps)
+constexpr int TC_CONV_THREADS = 32 * TC_CONV_WARPS;
+constexpr int TC_THREADS = 64 + TC_CONV_THREADS;              // warp0 TMA, warp1 MMA, warps 2.. converters/epilogue
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;                 // 16 KiB per A tile (hi or lo)
 
 template <int BN> struct TcCfg {
@@ -40,8 +43,8 @@ template <int BN> struct TcCfg {
   // -1.1e-5 relative at K=1024 with one accumulator; profiles/r01_accumulator_probe.txt).  The k-steps are
   // therefore dealt round-robin onto NMAIN independent TMEM accumulators for the hi*hi terms, plus one for
   // the small lo*hi + hi*lo terms (whose truncation is 2^-11 smaller), and summed in fp32 RN in the epilogue.
-  static constexpr int NMAIN = BN == 128 ? 3 : 6;
-  static constexpr int TMEM_COLS = 512;             // (NMAIN + 1) * BN <= 512
+  static constexpr int NMAIN = 3;
+  static constexpr int TMEM_COLS = BN == 128 ? 512 : 256;             // (NMAIN + 1) * BN
   static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
@@ -143,17 +146,38 @@ __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) 
 // The split is elementwise, so the swizzled placement is preserved without knowing the swizzle.
 template <int NCH, int LO_OFF>
 __device__ __forceinline__ void split_tile(uint32_t tile, int ct) {     // tile: shared address
-  static_assert(NCH % 128 == 0, "chunks per converter thread");
-  constexpr int PER = NCH / 128;
+  static_assert(NCH % TC_CONV_THREADS == 0, "chunks per converter thread");
+  constexpr int PER = NCH / TC_CONV_THREADS;
   float4 v[PER];
 #pragma unroll
-  for (int i = 0; i < PER; ++i) v[i] = lds128(tile + (uint32_t)(ct + i * 128) * 16u);
+  for (int i = 0; i < PER; ++i) v[i] = lds128(tile + (uint32_t)(ct + i * TC_CONV_THREADS) * 16u);
 #pragma unroll
   for (int i = 0; i < PER; ++i) {
     uint4 h, l;
     split_tf32(v[i].x, h.x, l.x); split_tf32(v[i].y, h.y, l.y); split_tf32(v[i].z, h.z, l.z); split_tf32(v[i].w, h.w, l.w);
-    sts128u(tile + (uint32_t)(ct + i * 128) * 16u, h);
-    sts128u(tile + LO_OFF + (uint32_t)(ct + i * 128) * 16u, l);
+    sts128u(tile + (uint32_t)(ct + i * TC_CONV_THREADS) * 16u, h);
+    sts128u(tile + LO_OFF + (uint32_t)(ct + i * TC_CONV_THREADS) * 16u, l);
+  }
+}
+// "raw-hi" split: the tensor core reads an fp32 word as tf32 by IGNORING its 13 low mantissa bits, so the landed
+// tile already is the hi part (hi = trunc(x)); only lo = tf32_rna(x - trunc(x)) (the subtraction is exact) has to be
+// written.  Halves the converters' shared-memory writes and lets the hi*hi MMAs start as soon as the tile lands.
+__device__ __forceinline__ uint32_t lo_of_trunc(float x) {
+  const float hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+  return (__float_as_uint(x - hi) + 0x1000u) & 0xFFFFE000u;
+}
+template <int NCH, int LO_OFF>
+__device__ __forceinline__ void split_tile_lo(uint32_t tile, int ct) {
+  static_assert(NCH % TC_CONV_THREADS == 0, "chunks per converter thread");
+  constexpr int PER = NCH / TC_CONV_THREADS;
+  float4 v[PER];
+#pragma unroll
+  for (int i = 0; i < PER; ++i) v[i] = lds128(tile + (uint32_t)(ct + i * TC_CONV_THREADS) * 16u);
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    uint4 l;
+    l.x = lo_of_trunc(v[i].x); l.y = lo_of_trunc(v[i].y); l.z = lo_of_trunc(v[i].z); l.w = lo_of_trunc(v[i].w);
+    sts128u(tile + LO_OFF + (uint32_t)(ct + i * TC_CONV_THREADS) * 16u, l);
   }
 }
 
@@ -275,9 +299,10 @@ __device__ __noinline__ void tc_epi_generic(const GemmP& p, const EpiArgs& ea, u
   }
 }
 
-// BPRE: the B operand arrives already split (hi/lo tensor maps over the pre-split weight arenas), so the
-// converter warps only touch the activation operand A.
-template <int BN, bool AMN, bool BMN, bool BPRE>
+// BPRE: the B operand arrives already split (raw/hi + lo tensor maps over the weight arenas), so the converter warps
+// only touch the activation operand A.  RAWHI: hi = the landed fp32 tile itself (see split_tile_lo); with RAWHI = false
+// the converters rewrite the tile as tf32_rna(x) in place (the reference point for the raw-hi numerics).
+template <int BN, bool AMN, bool BMN, bool BPRE, bool RAWHI>
 __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA,
                                                                 const __grid_constant__ CUtensorMap mapB,
                                                                 const __grid_constant__ CUtensorMap mapBlo, GemmP p) {
@@ -307,7 +332,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
   if (tid == 0) TC_STAMP(0);
 
   if (tid == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(ready_bar(s), 128); mbar_init(empty_bar(s), 1); }
+    // full: TMA landed (1 arrive + tx bytes) — with RAWHI the MMA warp AND the converters both wait on it;
+    // ready: lo parts written (one arrive per converter warp); empty: the MMAs reading the stage retired
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(ready_bar(s), TC_CONV_WARPS); mbar_init(empty_bar(s), 1); }
     mbar_init(acc_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
@@ -373,49 +400,95 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
       constexpr uint32_t A_LOW = (A_LBO >> 4) << 16, B_LOW = (B_LBO >> 4) << 16;
       const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
       const uint32_t acc_lo = tb + Cfg::NMAIN * BN;
-      for (int i = 0; i < nloc; ++i) {
-        const int s = i % STAGES, ph = (i / STAGES) & 1;
-        mbar_wait(ready_bar(s), ph);
-        tc_fence_after();
-        if (i < 12 && lane == 0) TC_STAMP(44 + i);
+      // hi*hi of k-block i goes to main accumulator i % NMAIN (rotation: see TcCfg), the two cross terms to acc_lo
+      auto issue_hh = [&](int i) {
+        const int s = i % STAGES;
+        const uint32_t a_hi = (((smem_base + s * STAGE_BYTES) >> 4) & 0x3FFFu) | A_LOW;
+        const uint32_t b_hi = a_hi - A_LOW + B_LOW + (2 * TC_A_BYTES >> 4);
+        const uint32_t acc_hi = tb + (i % Cfg::NMAIN) * BN;
+        const uint32_t first_hi = i >= Cfg::NMAIN ? 1u : 0u;
+#pragma unroll
+        for (int k = 0; k < TC_BK / 8; ++k)
+          tc_mma_tf32_w(acc_hi, a_hi + k * (A_KSTEP >> 4), A_HIW, b_hi + k * (B_KSTEP >> 4), B_HIW, idesc, k > 0 ? 1u : first_hi);
+      };
+      auto issue_lo = [&](int i) {
+        const int s = i % STAGES;
         const uint32_t a_hi = (((smem_base + s * STAGE_BYTES) >> 4) & 0x3FFFu) | A_LOW, a_lo = a_hi + (TC_A_BYTES >> 4);
         const uint32_t b_hi = a_hi - A_LOW + B_LOW + (2 * TC_A_BYTES >> 4), b_lo = b_hi + (B_BYTES >> 4);
-        const uint32_t acc_hi = tb + (i % Cfg::NMAIN) * BN;       // main accumulators rotate per k-block
-        const uint32_t first_hi = i >= Cfg::NMAIN ? 1u : 0u, first_lo = i > 0 ? 1u : 0u;
-        if (elect_one()) {
+        const uint32_t first_lo = i > 0 ? 1u : 0u;
 #pragma unroll
-          for (int k = 0; k < TC_BK / 8; ++k)
-            tc_mma_tf32_w(acc_hi, a_hi + k * (A_KSTEP >> 4), A_HIW, b_hi + k * (B_KSTEP >> 4), B_HIW, idesc, k > 0 ? 1u : first_hi);
-#pragma unroll
-          for (int k = 0; k < TC_BK / 8; ++k) {
-            tc_mma_tf32_w(acc_lo, a_lo + k * (A_KSTEP >> 4), A_HIW, b_hi + k * (B_KSTEP >> 4), B_HIW, idesc, k > 0 ? 1u : first_lo);
-            tc_mma_tf32_w(acc_lo, a_hi + k * (A_KSTEP >> 4), A_HIW, b_lo + k * (B_KSTEP >> 4), B_HIW, idesc, 1u);
-          }
-          tc_commit(empty_bar(s));                     // smem stage reusable once these MMAs retire
-          if (i == nloc - 1) tc_commit(acc_bar);       // accumulators complete
+        for (int k = 0; k < TC_BK / 8; ++k) {
+          tc_mma_tf32_w(acc_lo, a_lo + k * (A_KSTEP >> 4), A_HIW, b_hi + k * (B_KSTEP >> 4), B_HIW, idesc, k > 0 ? 1u : first_lo);
+          tc_mma_tf32_w(acc_lo, a_hi + k * (A_KSTEP >> 4), A_HIW, b_lo + k * (B_KSTEP >> 4), B_HIW, idesc, 1u);
         }
-        __syncwarp();
+      };
+      if (RAWHI) {
+        // software pipeline: hi*hi(i) is issued as soon as block i lands, lo(i-1) right behind it — the tensor pipe
+        // works on block i's main term while the converters are still producing block i's lo parts
+        for (int i = 0; i <= nloc; ++i) {
+          if (i < nloc) {
+            const int s = i % STAGES, ph = (i / STAGES) & 1;
+            mbar_wait(full_bar(s), ph);
+            tc_fence_after();
+            if (i < 12 && lane == 0) TC_STAMP(44 + i);
+            if (elect_one()) issue_hh(i);
+            __syncwarp();
+          }
+          if (i > 0) {
+            const int j = i - 1, s = j % STAGES, ph = (j / STAGES) & 1;
+            mbar_wait(ready_bar(s), ph);
+            tc_fence_after();
+            if (elect_one()) {
+              issue_lo(j);
+              tc_commit(empty_bar(s));                     // smem stage reusable once these MMAs retire
+              if (j == nloc - 1) tc_commit(acc_bar);       // accumulators complete
+            }
+            __syncwarp();
+          }
+        }
+      } else {
+        for (int i = 0; i < nloc; ++i) {
+          const int s = i % STAGES, ph = (i / STAGES) & 1;
+          mbar_wait(ready_bar(s), ph);
+          tc_fence_after();
+          if (i < 12 && lane == 0) TC_STAMP(44 + i);
+          if (elect_one()) {
+            issue_hh(i);
+            issue_lo(i);
+            tc_commit(empty_bar(s));
+            if (i == nloc - 1) tc_commit(acc_bar);
+          }
+          __syncwarp();
+        }
       }
     } else {
-      // ===================== converters: x -> (hi, lo) in shared memory =====================
+      // ===================== converters: lo parts (and, without RAWHI, the rounded hi parts) in shared memory =====================
       const int ct = tid - 64;
       for (int i = 0; i < nloc; ++i) {
         const int s = i % STAGES, ph = (i / STAGES) & 1;
         mbar_wait(full_bar(s), ph);
         if (ct == 0 && i < 12) TC_STAMP(20 + i);
         const uint32_t st = smem_base + s * STAGE_BYTES;
-        split_tile<TC_A_BYTES / 16, TC_A_BYTES>(st, ct);
-        if (!BPRE) split_tile<B_BYTES / 16, B_BYTES>(st + 2 * TC_A_BYTES, ct);
+        if (RAWHI) {
+          split_tile_lo<TC_A_BYTES / 16, TC_A_BYTES>(st, ct);
+          if (!BPRE) split_tile_lo<B_BYTES / 16, B_BYTES>(st + 2 * TC_A_BYTES, ct);
+        } else {
+          split_tile<TC_A_BYTES / 16, TC_A_BYTES>(st, ct);
+          if (!BPRE) split_tile<B_BYTES / 16, B_BYTES>(st + 2 * TC_A_BYTES, ct);
+        }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
-        mbar_arrive(ready_bar(s));
+        __syncwarp();
+        if (lane == 0) mbar_arrive(ready_bar(s));
         if (ct == 0 && i < 12) TC_STAMP(32 + i);
       }
       // ===================== epilogue: TMEM -> registers -> smem transpose -> coalesced global =====================
+      // 8 warps: warp w owns TMEM lane quarter w & 3 (hardware rule) and column half (w - 2) >> 2 of the tile
       mbar_wait(acc_bar, 0);
       tc_fence_after();
       if (ct == 0) TC_STAMP(2);
       const int q = warp & 3;                      // TMEM lane quarter this warp may access
-      const uint32_t stg = smem_base + q * (32 * TC_EPI_LD * 4);            // pipeline stages are idle now (shared address)
+      const int hf = (warp - 2) >> 2;              // column half
+      const uint32_t stg = smem_base + (warp - 2) * (32 * TC_EPI_LD * 4);   // pipeline stages are idle now (shared address)
       const int cq = lane & 7, rsub = lane >> 3;
       EpiArgs ea;
       ea.mrow = m0 + q * 32 + rsub;                                // first row this lane stores (then +4 per iteration)
@@ -445,24 +518,30 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
         else ekind = 6;
       }
       const int nused = min(Cfg::NMAIN, nloc);      // main accumulators that received at least one k-block
+      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+      for (int c0 = hf * (BN / 2); c0 < (hf + 1) * (BN / 2); c0 += 32) {
         if (n0 + c0 >= p.N) break;
         float sum[32];
         {
-          uint32_t r[32];
-          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(Cfg::NMAIN * BN + c0), r);     // lo accumulator
+          // two TMEM loads in flight per wait: (lo, main 0) then (main 1, main 2); summed in fp32 RN
+          uint32_t r0[32], r1[32];
+          tmem_ld32(trow + (uint32_t)(Cfg::NMAIN * BN + c0), r0);
+          tmem_ld32(trow + (uint32_t)c0, r1);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-          for (int j = 0; j < 32; ++j) sum[j] = __uint_as_float(r[j]);
-        }
-#pragma unroll 1
-        for (int a = 0; a < nused; ++a) {
-          uint32_t r[32];
-          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * BN + c0), r);
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          for (int j = 0; j < 32; ++j) sum[j] = __uint_as_float(r0[j]) + __uint_as_float(r1[j]);
+          if (nused > 1) {
+            tmem_ld32(trow + (uint32_t)(BN + c0), r0);
+            if (nused > 2) tmem_ld32(trow + (uint32_t)(2 * BN + c0), r1);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-          for (int j = 0; j < 32; ++j) sum[j] += __uint_as_float(r[j]);
+            for (int j = 0; j < 32; ++j) sum[j] += __uint_as_float(r0[j]);
+            if (nused > 2) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) sum[j] += __uint_as_float(r1[j]);
+            }
+          }
         }
         if (ct == 0 && c0 == 0) TC_STAMP(5);
 #pragma unroll
@@ -556,9 +635,9 @@ inline bool gemm_tc_eligible(const GemmP& p) {
   return true;
 }
 
-template <int BN, bool AMN, bool BMN, bool BPRE>
+template <int BN, bool AMN, bool BMN, bool BPRE, bool RAWHI>
 inline int gemm_tc_launch(const GemmP& p, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mbl, cudaStream_t st) {
-  auto kern = gemm_tc_kernel<BN, AMN, BMN, BPRE>;
+  auto kern = gemm_tc_kernel<BN, AMN, BMN, BPRE, RAWHI>;
   static bool attr_done = false;
   if (!attr_done) {
     SGRL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN>::SMEM));
@@ -572,12 +651,16 @@ inline int gemm_tc_launch(const GemmP& p, const CUtensorMap& ma, const CUtensorM
   return 0;
 }
 
+template <int BN, bool BPRE, bool RAWHI>
+inline int gemm_tc_dispatch2(const GemmP& p, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mbl, cudaStream_t st) {
+  if (!p.transA && !p.transB) return gemm_tc_launch<BN, false, false, BPRE, RAWHI>(p, ma, mb, mbl, st);
+  if (!p.transA && p.transB) return gemm_tc_launch<BN, false, true, BPRE, RAWHI>(p, ma, mb, mbl, st);
+  if (p.transA && p.transB) return gemm_tc_launch<BN, true, true, BPRE, RAWHI>(p, ma, mb, mbl, st);
+  return gemm_tc_launch<BN, true, false, BPRE, RAWHI>(p, ma, mb, mbl, st);
+}
 template <int BN, bool BPRE>
 inline int gemm_tc_dispatch(const GemmP& p, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mbl, cudaStream_t st) {
-  if (!p.transA && !p.transB) return gemm_tc_launch<BN, false, false, BPRE>(p, ma, mb, mbl, st);
-  if (!p.transA && p.transB) return gemm_tc_launch<BN, false, true, BPRE>(p, ma, mb, mbl, st);
-  if (p.transA && p.transB) return gemm_tc_launch<BN, true, true, BPRE>(p, ma, mb, mbl, st);
-  return gemm_tc_launch<BN, true, false, BPRE>(p, ma, mb, mbl, st);
+  return p.rawhi ? gemm_tc_dispatch2<BN, BPRE, true>(p, ma, mb, mbl, st) : gemm_tc_dispatch2<BN, BPRE, false>(p, ma, mb, mbl, st);
 }
 
 extern long long* g_gemm_trace;   // sgrl_gemm_trace(): device buffer of 64 int64 for TC_STAMP, or nullptr
@@ -587,6 +670,8 @@ inline int gemm_tc(const GemmP& p_in, cudaStream_t st) {
   p.dbg = g_gemm_trace;
   static const int sched_env = getenv("SGRL_TC_SCHED") ? atoi(getenv("SGRL_TC_SCHED")) : 0;
   p.sched = sched_env;
+  static const int rawhi_env = getenv("SGRL_TC_RAWHI") ? atoi(getenv("SGRL_TC_RAWHI")) : 1;
+  p.rawhi = rawhi_env;
   if (p.M <= 0 || p.N <= 0 || p.nb <= 0) return 0;
   SGRL_CHECK(gemm_tc_eligible(p), "gemm_tc: operands not TMA-compatible");
   SGRL_CHECK(p.splitk == 1 || (!p.relu && !p.rowdiv && !p.mask && !p.res1 && !p.res2 && p.colscale_n == 0), "gemm_tc: split-K only with a linear epilogue");
