@@ -56,6 +56,7 @@ __global__ void __launch_bounds__(A_FWD_THREADS) attention_fwd_kernel(
     float* __restrict__ O, float* __restrict__ OG, float* __restrict__ P, long long zsS,
     const float* __restrict__ Wrel, const float* __restrict__ brel, long long zsP,   // nullptr unless layer 0
     AttnGraphs gr) {
+  SGRL_PDL_ENTER();
   extern __shared__ __align__(16) float smem[];
   float* qs = smem;                     // [MAXN][A_RS]   q | k | v
   float* vs = qs + MAXN * A_RS;         // [MAXN][A_RS]   vgx: [r][h][128]
@@ -146,6 +147,7 @@ __global__ void __launch_bounds__(A_BWD_THREADS) attention_bwd_kernel(
     const float* __restrict__ QKV, const float* __restrict__ VGP, const float* __restrict__ GD, const float* __restrict__ P, long long zsS,
     const float* __restrict__ dO, const float* __restrict__ dOG, float* __restrict__ dQKV, float* __restrict__ dVGP, long long zsW,
     float* __restrict__ dWrel, long long zsG, AttnGraphs gr) {
+  SGRL_PDL_ENTER();
   extern __shared__ __align__(16) float smem[];
   float* qs = smem;
   float* vs = qs + MAXN * A_RS;
@@ -280,7 +282,7 @@ inline int attention_fwd(const float* QKV, const float* VGP, const float* GD, fl
   const int gx = gr.G < 4 * NUM_SMS ? gr.G : 4 * NUM_SMS;
   // algorithmic bytes per token: read q|k|v 3072 + vg 3024 + gd 24, write o 1024 + og 3072 (+ P 128)
   prof_begin(PC_ATTENTION, (double)gr.T * nb * (3072.0 + 3024 + 24 + 1024 + 3072 + 128), st);
-  attention_fwd_kernel<<<dim3(gx, nb), A_FWD_THREADS, attn_fwd_smem(), st>>>(QKV, VGP, GD, O, OG, P, zsS, Wrel, brel, zsP, gr);
+  launch_k(attention_fwd_kernel, dim3(gx, nb), A_FWD_THREADS, attn_fwd_smem(), st, QKV, VGP, GD, O, OG, P, zsS, Wrel, brel, zsP, gr);
   prof_end(st);
   SGRL_LAUNCH_OK();
   return 0;
@@ -296,7 +298,7 @@ inline int attention_bwd(const float* QKV, const float* VGP, const float* GD, co
     attr_done = true;
   }
   const int gx = gr.G < 2 * NUM_SMS ? gr.G : 2 * NUM_SMS;
-  attention_bwd_kernel<<<dim3(gx, nb), A_BWD_THREADS, attn_bwd_smem(), st>>>(QKV, VGP, GD, P, zsS, dO, dOG, dQKV, dVGP, zsW, dWrel, zsG, gr);
+  launch_k(attention_bwd_kernel, dim3(gx, nb), A_BWD_THREADS, attn_bwd_smem(), st, QKV, VGP, GD, P, zsS, dO, dOG, dQKV, dVGP, zsW, dWrel, zsG, gr);
   SGRL_LAUNCH_OK();
   return 0;
 }

@@ -4,6 +4,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 
 namespace sgrl {
 
@@ -20,6 +21,31 @@ extern long long g_launches;   // kernels launched by this library (bench.py's g
 #define SGRL_TRY(call) do { int r__ = (call); if (r__ != 0) return r__; } while (0)
 
 constexpr int NUM_SMS = 148;  // B200
+
+// ---- launches: every kernel of the library is launched with programmatic dependent launch (PDL) allowed, and begins
+// with SGRL_PDL_ENTER(): "my dependents may start launching" + "wait until the kernel before me has completed and its
+// memory is visible".  A kernel's CTAs therefore get scheduled (and the tcgen05 GEMM runs its barrier/TMEM/tensor-map
+// prologue) while its predecessor is still draining, instead of paying the ~3 us kernel-to-kernel launch gap after it.
+// Nothing is read or written before the wait, so stream order semantics are unchanged.  SGRL_PDL=0 disables.
+extern int g_pdl;
+inline bool pdl_enabled() {
+  if (g_pdl < 0) { const char* e = getenv("SGRL_PDL"); g_pdl = e ? atoi(e) : 1; }
+  return g_pdl != 0;
+}
+#define SGRL_PDL_TRIGGER() asm volatile("griddepcontrol.launch_dependents;" ::: "memory")
+#define SGRL_PDL_WAIT() asm volatile("griddepcontrol.wait;" ::: "memory")
+#define SGRL_PDL_ENTER() do { SGRL_PDL_TRIGGER(); SGRL_PDL_WAIT(); } while (0)
+template <typename... KArgs, typename... Args>
+inline void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
 
 // ---- optional per-kernel-class device timing (bench.py roofline pass): CUDA events around
 // the launches of one class on the launching stream, collected after a synchronize.

@@ -37,6 +37,7 @@ __global__ void __launch_bounds__(F_THREADS) inv_feature_fwd_kernel(
     const float* __restrict__ P1, const float* __restrict__ P2, long long zsP,
     float* __restrict__ Z, float* __restrict__ Z2, float* __restrict__ G, float* __restrict__ Fn, long long zsAct,
     int T) {
+  SGRL_PDL_ENTER();
   using S = FeatSmem<CE, NPROJ>;
   constexpr int C = S::C, PJ = S::PJ, XS = S::XS, JQ = PJ / 4;
   extern __shared__ __align__(16) float smem[];
@@ -173,7 +174,7 @@ inline int inv_feature_fwd_launch(const FeatFwdP& p, cudaStream_t st) {
   const int gx = ntiles < 2 * NUM_SMS ? ntiles : 2 * NUM_SMS;
   // algorithmic bytes per token: read X (12*C) + gd (24), write G (4096) + F (4) + Z (384 per projection)
   prof_begin(PC_FEATURE, (double)p.T * p.nb * (12.0 * S::C + 24 + 4096 + 4 + 384.0 * NPROJ), st);
-  kern<<<dim3(gx, p.nb), F_THREADS, S::bytes, st>>>(p.Xg, p.zsXg, p.V0, p.zsV0, p.gd, p.zsGd, p.P1, p.P2, p.zsP,
+  launch_k(kern, dim3(gx, p.nb), F_THREADS, S::bytes, st, p.Xg, p.zsXg, p.V0, p.zsV0, p.gd, p.zsGd, p.P1, p.P2, p.zsP,
                                                    p.Z, p.Z2, p.G, p.Fn, p.zsAct, p.T);
   prof_end(st);
   SGRL_LAUNCH_OK();
@@ -196,6 +197,7 @@ inline int inv_feature_fwd(const FeatFwdP& p, cudaStream_t st) {
 __global__ void __launch_bounds__(256) inv_feature_bwd_kernel(
     const float* __restrict__ dG, const float* __restrict__ dF, const float* __restrict__ Z,
     const float* __restrict__ Fn, float* __restrict__ dZ, long long zsAct, long long zsWs, int T) {
+  SGRL_PDL_ENTER();
   __shared__ float S[8][32][33];
   __shared__ float Zw[8][3][32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, z = blockIdx.y;
@@ -231,7 +233,7 @@ inline int inv_feature_bwd(const float* dG, const float* dF, const float* Z, con
   if (T <= 0) return 0;
   int gx = ceil_div(T, 8);
   if (gx > 8 * NUM_SMS) gx = 8 * NUM_SMS;
-  inv_feature_bwd_kernel<<<dim3(gx, nb), 256, 0, st>>>(dG, dF, Z, Fn, dZ, zsAct, zsWs, T);
+  launch_k(inv_feature_bwd_kernel, dim3(gx, nb), 256, 0, st, dG, dF, Z, Fn, dZ, zsAct, zsWs, T);
   SGRL_LAUNCH_OK();
   return 0;
 }

@@ -33,7 +33,6 @@ struct GemmP {
   const float* Bhi; const float* Blo;       // tcgen05 path only, optional: B pre-split into tf32 hi/lo parts (same layout/strides as B)
   int vecE;                                 // set by the tcgen05 launcher: C/mask/res rows allow float4 access
   int sched;                                // tcgen05 MMA issue order experiment knob (SGRL_TC_SCHED)
-  int rawhi;                                // tcgen05: hi operand = the raw fp32 tile (tensor core truncates), converters write lo only
   long long* dbg;                           // optional (tools/gemm_trace.py): SM-clock timestamps of CTA 0's pipeline phases
 };
 
@@ -81,6 +80,7 @@ __device__ __forceinline__ void gemm_stash(float (*s)[GB_M + G_PAD], const float
 }
 
 __global__ void __launch_bounds__(G_THREADS) gemm_simt_kernel(GemmP p) {
+  SGRL_PDL_ENTER();
   __shared__ __align__(16) float As[GB_K][GB_M + G_PAD];
   __shared__ __align__(16) float Bs[GB_K][GB_N + G_PAD];
   const int tid = threadIdx.x, z = blockIdx.z;
@@ -178,7 +178,7 @@ inline int gemm_simt(const GemmP& p_in, cudaStream_t st) {
   const int tiles = ceil_div(p.M, GB_M) * ceil_div(p.N, GB_N);
   dim3 grid(tiles, p.splitk, p.nb);
   prof_begin(PC_GEMM, 2.0 * p.M * p.N * (double)p.K * p.nb, st);
-  gemm_simt_kernel<<<grid, G_THREADS, 0, st>>>(p);
+  launch_k(gemm_simt_kernel, grid, G_THREADS, 0, st, p);
   prof_end(st);
   SGRL_LAUNCH_OK();
   return 0;

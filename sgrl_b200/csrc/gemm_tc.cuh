@@ -36,15 +36,21 @@ constexpr int TC_THREADS = 64 + TC_CONV_THREADS;              // warp0 TMA, warp
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;                 // 16 KiB per A tile (hi or lo)
 
 template <int BN> struct TcCfg {
-  static constexpr int B_BYTES = BN * TC_BK * 4;
-  static constexpr int STAGE_BYTES = 2 * (TC_A_BYTES + B_BYTES);
-  static constexpr int STAGES = BN == 128 ? 3 : 4;
+  static constexpr int B_BYTES = BN * TC_BK * 4;                    // one B tile (hi or lo)
+  static constexpr int STAGE_BYTES = TC_A_BYTES + 2 * B_BYTES;      // [A raw | B raw/hi | B lo]
+  static constexpr int STAGES = BN == 128 ? 4 : 6;                  // 192 KiB of operand ring either way
   // The tensor core ACCUMULATES WITH TRUNCATION (measured on B200: signed bias -3e-8 per add, i.e.
-  // -1.1e-5 relative at K=1024 with one accumulator; profiles/r01_accumulator_probe.txt).  The k-steps are
+  // -1.1e-5 relative at K=1024 with one accumulator; profiles/r01_accumulator_probe.txt).  The k-blocks are
   // therefore dealt round-robin onto NMAIN independent TMEM accumulators for the hi*hi terms, plus one for
   // the small lo*hi + hi*lo terms (whose truncation is 2^-11 smaller), and summed in fp32 RN in the epilogue.
-  static constexpr int NMAIN = 3;
-  static constexpr int TMEM_COLS = BN == 128 ? 512 : 256;             // (NMAIN + 1) * BN
+  static constexpr int NMAIN = BN == 128 ? 2 : 3;
+  static constexpr int ACC_COLS = (NMAIN + 1) * BN;                 // 384 | 256
+  // The A operand is fed from TENSOR MEMORY (tcgen05.mma "ts" form): with both operands in shared memory the
+  // 128 B/cycle shared-memory path bounds the mainloop (MMA operand reads + TMA writes + converter traffic =
+  // 136 KB per 12-MMA k-block at BN=64: 1100 cycles measured against a 384-cycle tensor-pipe floor;
+  // profiles/r01b_mma_probe.txt).  TA_STAGES slots of 64 columns hold [hi 32 | lo 32] of one k-block.
+  static constexpr int TA_STAGES = (512 - ACC_COLS) / 64;           // 2 | 4
+  static constexpr int TMEM_COLS = 512;
   static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
@@ -137,48 +143,57 @@ __device__ __forceinline__ void sts128u(uint32_t a, uint4 v) {
 }
 
 // ---------------------------------------------------------------------------- kernel
-// x -> hi = tf32_rna(x) (integer round-half-away on the bit pattern: 2 ALU ops), lo = tf32_rna(x - hi)
-__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
-  hi = (__float_as_uint(x) + 0x1000u) & 0xFFFFE000u;
-  lo = (__float_as_uint(x - __uint_as_float(hi)) + 0x1000u) & 0xFFFFE000u;
-}
-// split NCH 16-byte chunks of a TMA-landed tile in place: hi overwrites the tile, lo goes LO_OFF bytes further.
-// The split is elementwise, so the swizzled placement is preserved without knowing the swizzle.
-template <int NCH, int LO_OFF>
-__device__ __forceinline__ void split_tile(uint32_t tile, int ct) {     // tile: shared address
-  static_assert(NCH % TC_CONV_THREADS == 0, "chunks per converter thread");
-  constexpr int PER = NCH / TC_CONV_THREADS;
-  float4 v[PER];
-#pragma unroll
-  for (int i = 0; i < PER; ++i) v[i] = lds128(tile + (uint32_t)(ct + i * TC_CONV_THREADS) * 16u);
-#pragma unroll
-  for (int i = 0; i < PER; ++i) {
-    uint4 h, l;
-    split_tf32(v[i].x, h.x, l.x); split_tf32(v[i].y, h.y, l.y); split_tf32(v[i].z, h.z, l.z); split_tf32(v[i].w, h.w, l.w);
-    sts128u(tile + (uint32_t)(ct + i * TC_CONV_THREADS) * 16u, h);
-    sts128u(tile + LO_OFF + (uint32_t)(ct + i * TC_CONV_THREADS) * 16u, l);
-  }
-}
-// "raw-hi" split: the tensor core reads an fp32 word as tf32 by IGNORING its 13 low mantissa bits, so the landed
-// tile already is the hi part (hi = trunc(x)); only lo = tf32_rna(x - trunc(x)) (the subtraction is exact) has to be
-// written.  Halves the converters' shared-memory writes and lets the hi*hi MMAs start as soon as the tile lands.
+// lo part of the error-compensated split: the tensor core reads an fp32 word as tf32 by IGNORING its 13 low mantissa
+// bits (measured, profiles/r01b_mma_probe.txt and the parity tests), so the raw word already is hi = trunc(x); the
+// subtraction x - trunc(x) is exact and the result is rounded to tf32 (round half away, 2 integer ops).
 __device__ __forceinline__ uint32_t lo_of_trunc(float x) {
   const float hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
   return (__float_as_uint(x - hi) + 0x1000u) & 0xFFFFE000u;
 }
-template <int NCH, int LO_OFF>
+// lo parts of NCH 16-byte chunks of a TMA-landed (swizzled) B tile, written LO_OFF bytes further: elementwise, so the
+// swizzled placement is preserved without knowing the swizzle.  NT threads cooperate.
+template <int NCH, int LO_OFF, int NT>
 __device__ __forceinline__ void split_tile_lo(uint32_t tile, int ct) {
-  static_assert(NCH % TC_CONV_THREADS == 0, "chunks per converter thread");
-  constexpr int PER = NCH / TC_CONV_THREADS;
+  static_assert(NCH % NT == 0, "chunks per converter thread");
+  constexpr int PER = NCH / NT;
   float4 v[PER];
 #pragma unroll
-  for (int i = 0; i < PER; ++i) v[i] = lds128(tile + (uint32_t)(ct + i * TC_CONV_THREADS) * 16u);
+  for (int i = 0; i < PER; ++i) v[i] = lds128(tile + (uint32_t)(ct + i * NT) * 16u);
 #pragma unroll
   for (int i = 0; i < PER; ++i) {
     uint4 l;
     l.x = lo_of_trunc(v[i].x); l.y = lo_of_trunc(v[i].y); l.z = lo_of_trunc(v[i].z); l.w = lo_of_trunc(v[i].w);
-    sts128u(tile + LO_OFF + (uint32_t)(ct + i * TC_CONV_THREADS) * 16u, l);
+    sts128u(tile + LO_OFF + (uint32_t)(ct + i * NT) * 16u, l);
   }
+}
+
+__device__ __forceinline__ float lds32(uint32_t a) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory");
+  return v;
+}
+
+#define TC_R32(r) "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), \
+  "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]),          \
+  "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+// registers -> TMEM: lane l of the warp writes r[0..31] to TMEM lane (32*(warp%4) + l), columns [col, col+32)
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), TC_R32(r)
+      : "memory");
+}
+// A operand in TMEM (".ts" form): [d] (+)= [a_tmem] x b_desc
+__device__ __forceinline__ void tc_mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], db, %4, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
 }
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
@@ -299,25 +314,25 @@ __device__ __noinline__ void tc_epi_generic(const GemmP& p, const EpiArgs& ea, u
   }
 }
 
-// BPRE: the B operand arrives already split (raw/hi + lo tensor maps over the weight arenas), so the converter warps
-// only touch the activation operand A.  RAWHI: hi = the landed fp32 tile itself (see split_tile_lo); with RAWHI = false
-// the converters rewrite the tile as tf32_rna(x) in place (the reference point for the raw-hi numerics).
-template <int BN, bool AMN, bool BMN, bool BPRE, bool RAWHI>
+// BPRE: the B operand arrives already split (raw/hi + lo tensor maps over the weight arenas); otherwise the converter
+// warps also write B's lo part next to the landed tile.
+template <int BN, bool AMN, bool BMN, bool BPRE>
 __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA,
                                                                 const __grid_constant__ CUtensorMap mapB,
                                                                 const __grid_constant__ CUtensorMap mapBlo, GemmP p) {
   using Cfg = TcCfg<BN>;
-  constexpr int STAGES = Cfg::STAGES, B_BYTES = Cfg::B_BYTES, STAGE_BYTES = Cfg::STAGE_BYTES;
+  constexpr int STAGES = Cfg::STAGES, B_BYTES = Cfg::B_BYTES, STAGE_BYTES = Cfg::STAGE_BYTES, TA = Cfg::TA_STAGES, NMAIN = Cfg::NMAIN;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 1);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2 * TA + 1);
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t bar_base = smem_u32(bars);
-  auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto ready_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
-  const uint32_t acc_bar = bar_base + 8u * (3 * STAGES);
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };                       // TMA landed stage s (A raw + B)
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };           // MMAs reading stage s retired
+  auto ta_ready = [&](int t) { return bar_base + 8u * (2 * STAGES + t); };        // A hi|lo of a k-block stored in TMEM slot t
+  auto ta_empty = [&](int t) { return bar_base + 8u * (2 * STAGES + TA + t); };   // MMAs reading TMEM slot t retired
+  const uint32_t acc_bar = bar_base + 8u * (2 * STAGES + 2 * TA);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, z = blockIdx.z;
   const int tiles_n = (p.N + BN - 1) / BN;
@@ -330,11 +345,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
   long long* dbg = (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && z == 0) ? p.dbg : nullptr;
 #define TC_STAMP(slot) do { if (dbg) dbg[slot] = clock64(); } while (0)
   if (tid == 0) TC_STAMP(0);
+  SGRL_PDL_TRIGGER();      // the next kernel of the stream may begin its own prologue on idle SMs
 
   if (tid == 0) {
-    // full: TMA landed (1 arrive + tx bytes) — with RAWHI the MMA warp AND the converters both wait on it;
-    // ready: lo parts written (one arrive per converter warp); empty: the MMAs reading the stage retired
-    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(ready_bar(s), TC_CONV_WARPS); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int t = 0; t < TA; ++t) { mbar_init(ta_ready(t), TC_CONV_WARPS / 2); mbar_init(ta_empty(t), 1); }
     mbar_init(acc_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
@@ -349,6 +364,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const uint32_t ta_base = tmem_base + Cfg::ACC_COLS;          // TA slots of 64 columns: [raw/hi 32 | lo 32]
+  SGRL_PDL_WAIT();         // everything above overlapped the previous kernel's tail; its outputs are visible from here on
   if (tid == 0) TC_STAMP(1);
 
   if (nloc > 0) {
@@ -359,12 +376,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
         mbar_wait(empty_bar(s), ph ^ 1);
         if (elect_one()) {
           mbar_arrive_expect_tx(full_bar(s), TC_A_BYTES + (BPRE ? 2 : 1) * B_BYTES);
-          const uint32_t a_dst = smem_base + s * STAGE_BYTES, b_dst = a_dst + 2 * TC_A_BYTES;
-          if (!AMN) tma_load_3d(a_dst, &mapA, full_bar(s), k0, m0, zA);
-          else {
-#pragma unroll
-            for (int j = 0; j < TC_BM / 32; ++j) tma_load_3d(a_dst + j * 4096, &mapA, full_bar(s), m0 + 32 * j, k0, zA);
-          }
+          const uint32_t a_dst = smem_base + s * STAGE_BYTES, b_dst = a_dst + TC_A_BYTES;
+          if (!AMN) tma_load_3d(a_dst, &mapA, full_bar(s), k0, m0, zA);          // [128 rows][32 k], SWIZZLE_128B
+          else tma_load_3d(a_dst, &mapA, full_bar(s), m0, k0, zA);               // [32 k][128 rows], unswizzled
           if (!BMN) {
             tma_load_3d(b_dst, &mapB, full_bar(s), k0, n0, zB);
             if (BPRE) tma_load_3d(b_dst + B_BYTES, &mapBlo, full_bar(s), k0, n0, zB);
@@ -383,111 +397,85 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
     } else if (warp == 1) {
       // ===================== MMA issuer =====================
       // The whole warp walks the pipeline in warp-uniform control flow (loop state and descriptors stay in uniform
-      // registers); one elected lane issues the MMAs and commits of a k-block.  Measured on B200: with the loop inside
-      // `if (lane == 0)` every tcgen05.mma cost ~100 cycles of single-thread issue work (waterfall R2UR loops +
-      // descriptor arithmetic) against 32-64 cycles of tensor-pipe time.
-      // instruction descriptor: D=f32, A=B=tf32, majors, N>>3, M>>4 (cute/arch/mma_sm100_desc.hpp InstrDescriptor)
-      constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((AMN ? 1u : 0u) << 15) | ((BMN ? 1u : 0u) << 16) |
-                                 ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-      // K-major tile: 128 B rows (32 k), 8-row swizzle atoms 1024 B apart (SBO); one MMA (K=8) = 32 B along the row.
-      // MN-major tile: 32-wide MN chunks as TMA boxes of [32 k-rows x 128 B] 4096 B apart (LBO), 4-row atoms
+      // registers); one elected lane issues the MMAs and commits of a k-block.
+      // instruction descriptor: D=f32, A=B=tf32, A K-major (TMEM), B major, N>>3, M>>4 (cute/arch/mma_sm100_desc.hpp)
+      constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((BMN ? 1u : 0u) << 16) | ((uint32_t)(BN >> 3) << 17) |
+                                 ((uint32_t)(TC_BM >> 4) << 24);
+      // B K-major tile: 128 B rows (32 k), 8-row swizzle atoms 1024 B apart (SBO); one MMA (K=8) = 32 B along the row.
+      // B MN-major tile: 32-wide MN chunks as TMA boxes of [32 k-rows x 128 B] 4096 B apart (LBO), 4-row atoms
       // 512 B apart (SBO); one MMA (K=8) = 8 k-rows = 1024 B.
-      constexpr uint32_t A_LBO = AMN ? 4096u : 16u, A_SBO = AMN ? 512u : 1024u, A_KSTEP = AMN ? 1024u : 32u, A_LAY = AMN ? 1u : 2u;
       constexpr uint32_t B_LBO = BMN ? 4096u : 16u, B_SBO = BMN ? 512u : 1024u, B_KSTEP = BMN ? 1024u : 32u, B_LAY = BMN ? 1u : 2u;
-      // 64-bit descriptor = {lo word: addr>>4 | (LBO>>4)<<16, hi word: SBO>>4 | version 1<<14 | layout<<29}; only the
-      // address field changes between MMAs (smem < 256 KB: adding (bytes>>4) never carries out of the 14-bit field)
-      constexpr uint32_t A_HIW = (A_SBO >> 4) | (1u << 14) | (A_LAY << 29), B_HIW = (B_SBO >> 4) | (1u << 14) | (B_LAY << 29);
-      constexpr uint32_t A_LOW = (A_LBO >> 4) << 16, B_LOW = (B_LBO >> 4) << 16;
+      // 64-bit descriptor = {lo word: addr>>4 | (LBO>>4)<<16, hi word: SBO>>4 | version 1<<14 | layout<<29}
+      constexpr uint32_t B_HIW = (B_SBO >> 4) | (1u << 14) | (B_LAY << 29), B_LOW = (B_LBO >> 4) << 16;
       const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
-      const uint32_t acc_lo = tb + Cfg::NMAIN * BN;
-      // hi*hi of k-block i goes to main accumulator i % NMAIN (rotation: see TcCfg), the two cross terms to acc_lo
-      auto issue_hh = [&](int i) {
-        const int s = i % STAGES;
-        const uint32_t a_hi = (((smem_base + s * STAGE_BYTES) >> 4) & 0x3FFFu) | A_LOW;
-        const uint32_t b_hi = a_hi - A_LOW + B_LOW + (2 * TC_A_BYTES >> 4);
-        const uint32_t acc_hi = tb + (i % Cfg::NMAIN) * BN;
-        const uint32_t first_hi = i >= Cfg::NMAIN ? 1u : 0u;
+      const uint32_t acc_lo = tb + NMAIN * BN, tab = tb + Cfg::ACC_COLS;
+      for (int i = 0; i < nloc; ++i) {
+        const int s = i % STAGES, ph = (i / STAGES) & 1, t = i % TA, pht = (i / TA) & 1;
+        mbar_wait(full_bar(s), ph);
+        mbar_wait(ta_ready(t), pht);
+        tc_fence_after();
+        if (i < 12 && lane == 0) TC_STAMP(44 + i);
+        const uint32_t b_hi = (((smem_base + s * STAGE_BYTES + TC_A_BYTES) >> 4) & 0x3FFFu) | B_LOW, b_lo = b_hi + (B_BYTES >> 4);
+        const uint32_t a_hi = tab + t * 64, a_lo = a_hi + 32;
+        const uint32_t acc_hi = tb + (i % NMAIN) * BN;            // main accumulators rotate per k-block (see TcCfg)
+        const uint32_t first_hi = i >= NMAIN ? 1u : 0u, first_lo = i > 0 ? 1u : 0u;
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < TC_BK / 8; ++k)
-          tc_mma_tf32_w(acc_hi, a_hi + k * (A_KSTEP >> 4), A_HIW, b_hi + k * (B_KSTEP >> 4), B_HIW, idesc, k > 0 ? 1u : first_hi);
-      };
-      auto issue_lo = [&](int i) {
-        const int s = i % STAGES;
-        const uint32_t a_hi = (((smem_base + s * STAGE_BYTES) >> 4) & 0x3FFFu) | A_LOW, a_lo = a_hi + (TC_A_BYTES >> 4);
-        const uint32_t b_hi = a_hi - A_LOW + B_LOW + (2 * TC_A_BYTES >> 4), b_lo = b_hi + (B_BYTES >> 4);
-        const uint32_t first_lo = i > 0 ? 1u : 0u;
+          for (int k = 0; k < TC_BK / 8; ++k)
+            tc_mma_tf32_ts(acc_hi, a_hi + 8 * k, b_hi + k * (B_KSTEP >> 4), B_HIW, idesc, k > 0 ? 1u : first_hi);
 #pragma unroll
-        for (int k = 0; k < TC_BK / 8; ++k) {
-          tc_mma_tf32_w(acc_lo, a_lo + k * (A_KSTEP >> 4), A_HIW, b_hi + k * (B_KSTEP >> 4), B_HIW, idesc, k > 0 ? 1u : first_lo);
-          tc_mma_tf32_w(acc_lo, a_hi + k * (A_KSTEP >> 4), A_HIW, b_lo + k * (B_KSTEP >> 4), B_HIW, idesc, 1u);
-        }
-      };
-      if (RAWHI) {
-        // software pipeline: hi*hi(i) is issued as soon as block i lands, lo(i-1) right behind it — the tensor pipe
-        // works on block i's main term while the converters are still producing block i's lo parts
-        for (int i = 0; i <= nloc; ++i) {
-          if (i < nloc) {
-            const int s = i % STAGES, ph = (i / STAGES) & 1;
-            mbar_wait(full_bar(s), ph);
-            tc_fence_after();
-            if (i < 12 && lane == 0) TC_STAMP(44 + i);
-            if (elect_one()) issue_hh(i);
-            __syncwarp();
+          for (int k = 0; k < TC_BK / 8; ++k) {
+            tc_mma_tf32_ts(acc_lo, a_lo + 8 * k, b_hi + k * (B_KSTEP >> 4), B_HIW, idesc, k > 0 ? 1u : first_lo);
+            tc_mma_tf32_ts(acc_lo, a_hi + 8 * k, b_lo + k * (B_KSTEP >> 4), B_HIW, idesc, 1u);
           }
-          if (i > 0) {
-            const int j = i - 1, s = j % STAGES, ph = (j / STAGES) & 1;
-            mbar_wait(ready_bar(s), ph);
-            tc_fence_after();
-            if (elect_one()) {
-              issue_lo(j);
-              tc_commit(empty_bar(s));                     // smem stage reusable once these MMAs retire
-              if (j == nloc - 1) tc_commit(acc_bar);       // accumulators complete
-            }
-            __syncwarp();
-          }
+          tc_commit(empty_bar(s));                     // smem stage reusable once these MMAs retire
+          tc_commit(ta_empty(t));                      // so is the TMEM A slot
+          if (i == nloc - 1) tc_commit(acc_bar);       // accumulators complete
         }
-      } else {
-        for (int i = 0; i < nloc; ++i) {
-          const int s = i % STAGES, ph = (i / STAGES) & 1;
-          mbar_wait(ready_bar(s), ph);
-          tc_fence_after();
-          if (i < 12 && lane == 0) TC_STAMP(44 + i);
-          if (elect_one()) {
-            issue_hh(i);
-            issue_lo(i);
-            tc_commit(empty_bar(s));
-            if (i == nloc - 1) tc_commit(acc_bar);
-          }
-          __syncwarp();
-        }
+        __syncwarp();
       }
     } else {
-      // ===================== converters: lo parts (and, without RAWHI, the rounded hi parts) in shared memory =====================
-      const int ct = tid - 64;
-      for (int i = 0; i < nloc; ++i) {
-        const int s = i % STAGES, ph = (i / STAGES) & 1;
+      // ===================== converters: smem A tile -> (hi, lo) rows in TMEM; B lo in smem when not pre-split =====================
+      // two groups of 4 warps take alternate k-blocks; thread = one tile row = one TMEM lane
+      const int g = (warp - 2) >> 2, q = warp & 3, row = q * 32 + lane, cgt = ((warp - 2) & 3) * 32 + lane;
+      const uint32_t trow = ta_base + ((uint32_t)(q * 32) << 16);
+      for (int i = g; i < nloc; i += 2) {
+        const int s = i % STAGES, ph = (i / STAGES) & 1, t = i % TA, pht = (i / TA) & 1;
         mbar_wait(full_bar(s), ph);
-        if (ct == 0 && i < 12) TC_STAMP(20 + i);
+        if (tid == 64 && i < 12) TC_STAMP(20 + i);
         const uint32_t st = smem_base + s * STAGE_BYTES;
-        if (RAWHI) {
-          split_tile_lo<TC_A_BYTES / 16, TC_A_BYTES>(st, ct);
-          if (!BPRE) split_tile_lo<B_BYTES / 16, B_BYTES>(st + 2 * TC_A_BYTES, ct);
+        uint32_t raw[32], lo[32];
+        if (!AMN) {
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const float4 v = lds128(st + (uint32_t)row * 128u + (uint32_t)((c ^ (row & 7)) << 4));
+            raw[4 * c] = __float_as_uint(v.x); raw[4 * c + 1] = __float_as_uint(v.y);
+            raw[4 * c + 2] = __float_as_uint(v.z); raw[4 * c + 3] = __float_as_uint(v.w);
+          }
         } else {
-          split_tile<TC_A_BYTES / 16, TC_A_BYTES>(st, ct);
-          if (!BPRE) split_tile<B_BYTES / 16, B_BYTES>(st + 2 * TC_A_BYTES, ct);
+#pragma unroll
+          for (int k = 0; k < 32; ++k) raw[k] = __float_as_uint(lds32(st + (uint32_t)k * 512u + (uint32_t)row * 4u));
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
+        if (!BPRE) split_tile_lo<B_BYTES / 16, B_BYTES, 128>(st + TC_A_BYTES, cgt);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) lo[j] = lo_of_trunc(__uint_as_float(raw[j]));
+        mbar_wait(ta_empty(t), pht ^ 1);
+        tc_fence_after();
+        tmem_st32(trow + (uint32_t)(t * 64), raw);
+        tmem_st32(trow + (uint32_t)(t * 64 + 32), lo);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        if (!BPRE) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy smem writes -> visible to the tensor core
+        tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(ready_bar(s));
-        if (ct == 0 && i < 12) TC_STAMP(32 + i);
+        if (lane == 0) mbar_arrive(ta_ready(t));
+        if (tid == 64 && i < 12) TC_STAMP(32 + i);
       }
       // ===================== epilogue: TMEM -> registers -> smem transpose -> coalesced global =====================
       // 8 warps: warp w owns TMEM lane quarter w & 3 (hardware rule) and column half (w - 2) >> 2 of the tile
       mbar_wait(acc_bar, 0);
       tc_fence_after();
-      if (ct == 0) TC_STAMP(2);
-      const int q = warp & 3;                      // TMEM lane quarter this warp may access
-      const int hf = (warp - 2) >> 2;              // column half
+      if (tid == 64) TC_STAMP(2);
+      const int hf = g;                            // column half
       const uint32_t stg = smem_base + (warp - 2) * (32 * TC_EPI_LD * 4);   // pipeline stages are idle now (shared address)
       const int cq = lane & 7, rsub = lane >> 3;
       EpiArgs ea;
@@ -517,38 +505,38 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
         else if (p.res1 && !p.rowdiv && !p.mask && p.colscale_n == 0 && !p.relu && !p.bias) ekind = 3;
         else ekind = 6;
       }
-      const int nused = min(Cfg::NMAIN, nloc);      // main accumulators that received at least one k-block
-      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+      const int nused = min(NMAIN, nloc);      // main accumulators that received at least one k-block
+      const uint32_t arow = tmem_base + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
       for (int c0 = hf * (BN / 2); c0 < (hf + 1) * (BN / 2); c0 += 32) {
         if (n0 + c0 >= p.N) break;
         float sum[32];
         {
-          // two TMEM loads in flight per wait: (lo, main 0) then (main 1, main 2); summed in fp32 RN
+          // two TMEM loads in flight per wait; summed in fp32 RN
           uint32_t r0[32], r1[32];
-          tmem_ld32(trow + (uint32_t)(Cfg::NMAIN * BN + c0), r0);
-          tmem_ld32(trow + (uint32_t)c0, r1);
+          tmem_ld32(arow + (uint32_t)(NMAIN * BN + c0), r0);
+          tmem_ld32(arow + (uint32_t)c0, r1);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
           for (int j = 0; j < 32; ++j) sum[j] = __uint_as_float(r0[j]) + __uint_as_float(r1[j]);
           if (nused > 1) {
-            tmem_ld32(trow + (uint32_t)(BN + c0), r0);
-            if (nused > 2) tmem_ld32(trow + (uint32_t)(2 * BN + c0), r1);
+            tmem_ld32(arow + (uint32_t)(BN + c0), r0);
+            if (NMAIN > 2 && nused > 2) tmem_ld32(arow + (uint32_t)(2 * BN + c0), r1);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
             for (int j = 0; j < 32; ++j) sum[j] += __uint_as_float(r0[j]);
-            if (nused > 2) {
+            if (NMAIN > 2 && nused > 2) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) sum[j] += __uint_as_float(r1[j]);
             }
           }
         }
-        if (ct == 0 && c0 == 0) TC_STAMP(5);
+        if (tid == 64 && c0 == 0) TC_STAMP(5);
 #pragma unroll
         for (int k = 0; k < 8; ++k)
           sts128(stg + (lane * TC_EPI_LD + 4 * k) * 4, make_float4(sum[4 * k], sum[4 * k + 1], sum[4 * k + 2], sum[4 * k + 3]));
         __syncwarp();
-        if (ct == 0 && c0 == 0) TC_STAMP(6);
+        if (tid == 64 && c0 == 0) TC_STAMP(6);
         const int n = n0 + c0 + cq * 4;
         switch (ekind) {
           case 0: tc_epi_chunk<false, false, 0, EM_STORE>(p, ea, stg, rsub, cq, n, c0); break;
@@ -560,7 +548,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
           default: tc_epi_generic(p, ea, stg, rsub, cq, n, c0); break;
         }
         __syncwarp();
-        if (ct == 0 && c0 == 0) TC_STAMP(7);
+        if (tid == 64 && c0 == 0) TC_STAMP(7);
       }
     }
   }
@@ -606,7 +594,8 @@ struct TmapHash {
 };
 
 // 3-D fp32 tensor map {inner (contiguous), outer (stride ld), z (stride zs)} with a {box0, box1, 1} box, zero OOB fill;
-// atom32 = 0: SWIZZLE_128B (K-major operand tiles), 1: SWIZZLE_128B_ATOM_32B (MN-major tf32 operand tiles)
+// atom32 = 0: SWIZZLE_128B (K-major operand tiles), 1: SWIZZLE_128B_ATOM_32B (MN-major tf32 B tiles read by the tensor
+// core), 2: no swizzle (MN-major A tiles, read only by the converter warps)
 inline int make_tmap(CUtensorMap* out, const float* ptr, long long inner, long long outer, long long nz, long long ld, long long zs,
                      int box0, int box1, int atom32) {
   static thread_local std::unordered_map<TmapKey, CUtensorMap, TmapHash> cache;
@@ -620,7 +609,7 @@ inline int make_tmap(CUtensorMap* out, const float* ptr, long long inner, long l
   cuuint32_t box[3] = {(cuuint32_t)box0, (cuuint32_t)box1, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  atom32 == 2 ? CU_TENSOR_MAP_SWIZZLE_NONE : atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   SGRL_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed");
   if (cache.size() > 8192) cache.clear();
   cache.emplace(key, *out);
@@ -635,9 +624,9 @@ inline bool gemm_tc_eligible(const GemmP& p) {
   return true;
 }
 
-template <int BN, bool AMN, bool BMN, bool BPRE, bool RAWHI>
+template <int BN, bool AMN, bool BMN, bool BPRE>
 inline int gemm_tc_launch(const GemmP& p, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mbl, cudaStream_t st) {
-  auto kern = gemm_tc_kernel<BN, AMN, BMN, BPRE, RAWHI>;
+  auto kern = gemm_tc_kernel<BN, AMN, BMN, BPRE>;
   static bool attr_done = false;
   if (!attr_done) {
     SGRL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN>::SMEM));
@@ -645,22 +634,18 @@ inline int gemm_tc_launch(const GemmP& p, const CUtensorMap& ma, const CUtensorM
   }
   dim3 grid(ceil_div(p.M, TC_BM) * ceil_div(p.N, BN), p.splitk, p.nb);
   prof_begin(PC_GEMM_TC, 2.0 * p.M * p.N * (double)p.K * p.nb, st);
-  kern<<<grid, TC_THREADS, TcCfg<BN>::SMEM, st>>>(ma, mb, mbl, p);
+  launch_k(kern, grid, TC_THREADS, TcCfg<BN>::SMEM, st, ma, mb, mbl, p);
   prof_end(st);
   SGRL_LAUNCH_OK();
   return 0;
 }
 
-template <int BN, bool BPRE, bool RAWHI>
-inline int gemm_tc_dispatch2(const GemmP& p, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mbl, cudaStream_t st) {
-  if (!p.transA && !p.transB) return gemm_tc_launch<BN, false, false, BPRE, RAWHI>(p, ma, mb, mbl, st);
-  if (!p.transA && p.transB) return gemm_tc_launch<BN, false, true, BPRE, RAWHI>(p, ma, mb, mbl, st);
-  if (p.transA && p.transB) return gemm_tc_launch<BN, true, true, BPRE, RAWHI>(p, ma, mb, mbl, st);
-  return gemm_tc_launch<BN, true, false, BPRE, RAWHI>(p, ma, mb, mbl, st);
-}
 template <int BN, bool BPRE>
 inline int gemm_tc_dispatch(const GemmP& p, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mbl, cudaStream_t st) {
-  return p.rawhi ? gemm_tc_dispatch2<BN, BPRE, true>(p, ma, mb, mbl, st) : gemm_tc_dispatch2<BN, BPRE, false>(p, ma, mb, mbl, st);
+  if (!p.transA && !p.transB) return gemm_tc_launch<BN, false, false, BPRE>(p, ma, mb, mbl, st);
+  if (!p.transA && p.transB) return gemm_tc_launch<BN, false, true, BPRE>(p, ma, mb, mbl, st);
+  if (p.transA && p.transB) return gemm_tc_launch<BN, true, true, BPRE>(p, ma, mb, mbl, st);
+  return gemm_tc_launch<BN, true, false, BPRE>(p, ma, mb, mbl, st);
 }
 
 extern long long* g_gemm_trace;   // sgrl_gemm_trace(): device buffer of 64 int64 for TC_STAMP, or nullptr
@@ -670,8 +655,6 @@ inline int gemm_tc(const GemmP& p_in, cudaStream_t st) {
   p.dbg = g_gemm_trace;
   static const int sched_env = getenv("SGRL_TC_SCHED") ? atoi(getenv("SGRL_TC_SCHED")) : 0;
   p.sched = sched_env;
-  static const int rawhi_env = getenv("SGRL_TC_RAWHI") ? atoi(getenv("SGRL_TC_RAWHI")) : 1;
-  p.rawhi = rawhi_env;
   if (p.M <= 0 || p.N <= 0 || p.nb <= 0) return 0;
   SGRL_CHECK(gemm_tc_eligible(p), "gemm_tc: operands not TMA-compatible");
   SGRL_CHECK(p.splitk == 1 || (!p.relu && !p.rowdiv && !p.mask && !p.res1 && !p.res2 && p.colscale_n == 0), "gemm_tc: split-K only with a linear epilogue");
@@ -689,7 +672,7 @@ inline int gemm_tc(const GemmP& p_in, cudaStream_t st) {
   CUtensorMap ma, mb, mbl;
   // K-major operand: inner = K (contiguous), outer = rows; MN-major: inner = rows (contiguous), outer = K
   if (!p.transA) SGRL_TRY(make_tmap(&ma, p.A, p.K, p.M, nzA, p.lda, p.zsA, 32, TC_BM, 0));
-  else SGRL_TRY(make_tmap(&ma, p.A, p.M, p.K, nzA, p.lda, p.zsA, 32, 32, 1));
+  else SGRL_TRY(make_tmap(&ma, p.A, p.M, p.K, nzA, p.lda, p.zsA, TC_BM, 32, 2));
   if (!p.transB) SGRL_TRY(make_tmap(&mb, Bsrc, p.K, p.N, nzB, p.ldb, p.zsB, 32, BN, 0));
   else SGRL_TRY(make_tmap(&mb, Bsrc, p.N, p.K, nzB, p.ldb, p.zsB, 32, 32, 1));
   mbl = mb;

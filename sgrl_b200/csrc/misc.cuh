@@ -22,6 +22,7 @@ __global__ void __launch_bounds__(128) embed_fwd_kernel(
     const float* __restrict__ E0, const float* __restrict__ E1, const float* __restrict__ E2, long long zsP,
     float* __restrict__ V0, float* __restrict__ GD, float* __restrict__ SH, int ldsh,
     float* __restrict__ VG, float* __restrict__ H, int ldh, long long zsS, int T, int ng) {
+  SGRL_PDL_ENTER();
   __shared__ float xs[E_TOK][48];
   __shared__ int rk[E_TOK][3];
   const int c = threadIdx.x, z = blockIdx.y;
@@ -74,6 +75,7 @@ __global__ void __launch_bounds__(128) embed_fwd_kernel(
 __global__ void __launch_bounds__(128) pos_embed_bwd_kernel(
     const float* __restrict__ dH, int ldh, long long zsW, const int* __restrict__ rank3,
     float* __restrict__ dE0, float* __restrict__ dE1, float* __restrict__ dE2, long long zsG, int T) {
+  SGRL_PDL_ENTER();
   __shared__ float acc[MAX_NODE][128];
   const int c = threadIdx.x, z = blockIdx.y;
   dH += z * zsW; dE0 += z * zsG; dE1 += z * zsG; dE2 += z * zsG;
@@ -104,6 +106,7 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(
     const float* __restrict__ gamma, const float* __restrict__ beta, long long zsP,
     float* __restrict__ x, float* __restrict__ y, int ldy, float* __restrict__ y2, int ldy2,
     float* __restrict__ stats, long long zsS, int T, int vflags) {
+  SGRL_PDL_ENTER();
   const int lane = threadIdx.x & 31, z = blockIdx.y;
   a += z * zsS; if (b) b += z * zsS; if (x) x += z * zsS; y += z * zsS; if (y2) y2 += z * zsS; stats += z * zsS;
   gamma += z * zsP; beta += z * zsP;
@@ -133,6 +136,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(
     const float* __restrict__ x, int ldx, const float* __restrict__ stats, long long zsS,
     const float* __restrict__ gamma, long long zsP,
     float* __restrict__ dx, int lddx, long long zsW, float* __restrict__ dgamma, float* __restrict__ dbeta, long long zsG, int T, int vflags) {
+  SGRL_PDL_ENTER();
   __shared__ float red[2][8][128];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, z = blockIdx.y;
   dy1 += z * zsW; if (dy2) dy2 += z * zsW; dx += z * zsW;
@@ -177,6 +181,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(
 // =====================================================================================
 __global__ void __launch_bounds__(256) matapply_fwd_kernel(
     const float* __restrict__ Z, const float* __restrict__ M, float* __restrict__ R, long long zsS, int T) {
+  SGRL_PDL_ENTER();
   const int lane = threadIdx.x & 31, z = blockIdx.y;
   Z += z * zsS; M += z * zsS; R += z * zsS;
   for (int t = blockIdx.x * 8 + (threadIdx.x >> 5); t < T; t += gridDim.x * 8) {
@@ -199,6 +204,7 @@ __global__ void __launch_bounds__(256) matapply_fwd_kernel(
 __global__ void __launch_bounds__(256) matapply_bwd_kernel(
     const float* __restrict__ dR, const float* __restrict__ Z, const float* __restrict__ M, const float* __restrict__ Fn,
     long long zsS, float* __restrict__ dZ, float* __restrict__ dT, float* __restrict__ dF, long long zsW, int T) {
+  SGRL_PDL_ENTER();
   __shared__ float Ms[8][32][33];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, z = blockIdx.y;
   Z += z * zsS; M += z * zsS; Fn += z * zsS; dR += z * zsW; dZ += z * zsW; dT += z * zsW; dF += z * zsW;
@@ -242,6 +248,7 @@ __global__ void __launch_bounds__(256) matapply_bwd_kernel(
 __global__ void __launch_bounds__(256) actor_out_fwd_kernel(
     const float* __restrict__ R, const float* __restrict__ V0, const float* __restrict__ wd, long long zsP,
     float* __restrict__ W3, float* __restrict__ out, long long zsS, float max_action, int T) {
+  SGRL_PDL_ENTER();
   const int lane = threadIdx.x & 31, z = blockIdx.y;
   R += z * zsS; V0 += z * zsS; W3 += z * zsS; out += z * zsS; wd += z * zsP;
   const float w = wd[lane];
@@ -261,6 +268,7 @@ __global__ void __launch_bounds__(256) actor_out_bwd_kernel(
     const float* __restrict__ dOut, long long zsDo, const float* __restrict__ out, const float* __restrict__ R, const float* __restrict__ V0,
     long long zsS, const float* __restrict__ wd, long long zsP, float* __restrict__ dR, long long zsW,
     float* __restrict__ dwd, long long zsG, float max_action, int T) {
+  SGRL_PDL_ENTER();
   __shared__ float red[8][32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, z = blockIdx.y;
   dOut += z * zsDo; out += z * zsS; R += z * zsS; V0 += z * zsS; wd += z * zsP; dR += z * zsW; dwd += z * zsG;
@@ -300,6 +308,7 @@ __global__ void __launch_bounds__(256) actor_out_bwd_kernel(
 __global__ void __launch_bounds__(256) rowdiv_bwd_kernel(
     float* __restrict__ dy, int lddy, long long zsW, const float* __restrict__ y, int ldy, const float* __restrict__ Fn, long long zsS,
     float* __restrict__ dF, int N, float colscale, int cs_n, int T) {
+  SGRL_PDL_ENTER();
   const int lane = threadIdx.x & 31, z = blockIdx.y;
   dy += z * zsW; dF += z * zsW; y += z * zsS; Fn += z * zsS;
   for (int t = blockIdx.x * 8 + (threadIdx.x >> 5); t < T; t += gridDim.x * 8) {
@@ -318,6 +327,7 @@ __global__ void __launch_bounds__(256) rowdiv_bwd_kernel(
 // out[n] += alpha * sum_m X[m][n]
 __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ X, int ldx, long long zsX,
                                                      float* __restrict__ out, long long zsO, int M, int N, float alpha) {
+  SGRL_PDL_ENTER();
   __shared__ float red[8][32];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5, z = blockIdx.z;
   X += z * zsX; out += z * zsO;
@@ -338,6 +348,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ X
 // strided copy / add of a (T x N) block:  dst = (add ? dst : 0) + src
 __global__ void __launch_bounds__(256) block_copy_kernel(float* __restrict__ dst, int ldd, long long zsD,
                                                          const float* __restrict__ src, int lds, long long zsSrc, int M, int N, int add) {
+  SGRL_PDL_ENTER();
   const int z = blockIdx.y;
   dst += z * zsD; src += z * zsSrc;
   const long long total = (long long)M * N;

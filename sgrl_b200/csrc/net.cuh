@@ -98,20 +98,20 @@ inline GemmP wgrad(const NetCtx& c, const float* dY, int lddy, const float* X, i
 }
 inline int colsum(const NetCtx& c, const float* X, int ldx, long long g_off, int M, int N, float alpha = 1.f) {
   int gy = ceil_div(M, 64); if (gy > 32) gy = 32; if (gy < 1) gy = 1;
-  colsum_kernel<<<dim3(ceil_div(N, 32), gy, c.nb), 256, 0, c.stream>>>(X, ldx, c.zsW, c.Gr(g_off), c.zsG, M, N, alpha);
+  launch_k(colsum_kernel, dim3(ceil_div(N, 32), gy, c.nb), 256, 0, c.stream, X, ldx, c.zsW, c.Gr(g_off), c.zsG, M, N, alpha);
   SGRL_LAUNCH_OK();
   return 0;
 }
 inline int block_copy(const NetCtx& c, float* dst, int ldd, long long zsD, const float* src, int lds, long long zsSrc, int M, int N, int add) {
   int gx = ceil_div((long long)M * N, 256); if (gx > 4 * NUM_SMS) gx = 4 * NUM_SMS; if (gx < 1) gx = 1;
-  block_copy_kernel<<<dim3(gx, c.nb), 256, 0, c.stream>>>(dst, ldd, zsD, src, lds, zsSrc, M, N, add);
+  launch_k(block_copy_kernel, dim3(gx, c.nb), 256, 0, c.stream, dst, ldd, zsD, src, lds, zsSrc, M, N, add);
   SGRL_LAUNCH_OK();
   return 0;
 }
 inline int layernorm_fwd(const NetCtx& c, const float* a, int lda, const float* b, int ldb, long long g_off, long long b_off,
                          float* x, float* y, int ldy, float* stats) {
   const int vf = host_vec_ok(a, lda, c.zsS) | (host_vec_ok(b, ldb, c.zsS) << 1) | (host_vec_ok(y, ldy, c.zsS) << 2);
-  layernorm_fwd_kernel<<<dim3(grid_for_warps(c.T), c.nb), 256, 0, c.stream>>>(a, lda, b, ldb, c.P(g_off), c.P(b_off), c.zsP, x, y, ldy,
+  launch_k(layernorm_fwd_kernel, dim3(grid_for_warps(c.T), c.nb), 256, 0, c.stream, a, lda, b, ldb, c.P(g_off), c.P(b_off), c.zsP, x, y, ldy,
                                                                               nullptr, 0, stats, c.zsS, c.T, vf);
   SGRL_LAUNCH_OK();
   return 0;
@@ -120,13 +120,13 @@ inline int layernorm_bwd(const NetCtx& c, const float* dy1, int ld1, const float
                          const float* stats, long long g_off, long long b_off, float* dx, int lddx, bool wg) {
   int gx = grid_for_warps(c.T); if (gx > 2 * NUM_SMS) gx = 2 * NUM_SMS;
   const int vf = host_vec_ok(dy1, ld1, c.zsW) | (host_vec_ok(dy2, ld2, c.zsW) << 1) | (host_vec_ok(x, ldx, c.zsS) << 2) | (host_vec_ok(dx, lddx, c.zsW) << 3);
-  layernorm_bwd_kernel<<<dim3(gx, c.nb), 256, 0, c.stream>>>(dy1, ld1, dy2, ld2, x, ldx, stats, c.zsS, c.P(g_off), c.zsP, dx, lddx, c.zsW,
+  launch_k(layernorm_bwd_kernel, dim3(gx, c.nb), 256, 0, c.stream, dy1, ld1, dy2, ld2, x, ldx, stats, c.zsS, c.P(g_off), c.zsP, dx, lddx, c.zsW,
                                                              wg ? c.Gr(g_off) : nullptr, wg ? c.Gr(b_off) : nullptr, c.zsG, c.T, vf);
   SGRL_LAUNCH_OK();
   return 0;
 }
 inline int rowdiv_bwd(const NetCtx& c, float* dy, int lddy, const float* y, int ldy, const float* Fn, float* dF, int N, float cs, int cs_n) {
-  rowdiv_bwd_kernel<<<dim3(grid_for_warps(c.T), c.nb), 256, 0, c.stream>>>(dy, lddy, c.zsW, y, ldy, Fn, c.zsS, dF, N, cs, cs_n, c.T);
+  launch_k(rowdiv_bwd_kernel, dim3(grid_for_warps(c.T), c.nb), 256, 0, c.stream, dy, lddy, c.zsW, y, ldy, Fn, c.zsS, dF, N, cs, cs_n, c.T);
   SGRL_LAUNCH_OK();
   return 0;
 }
@@ -150,7 +150,7 @@ inline int net_forward(const NetCtx& c, const float* obs, long long zsObs, const
   SGRL_CHECK(c.kind == ACTOR || act != nullptr, "critic forward needs actions");
   {
     int gx = ceil_div(T, E_TOK); if (gx > 4 * NUM_SMS) gx = 4 * NUM_SMS;
-    embed_fwd_kernel<<<dim3(gx, c.nb), 128, 0, st>>>(obs, zsObs, c.kind == CRITIC ? act : nullptr, zsAct, c.rank3,
+    launch_k(embed_fwd_kernel, dim3(gx, c.nb), 128, 0, st, obs, zsObs, c.kind == CRITIC ? act : nullptr, zsAct, c.rank3,
         c.P(Y.gp[G_GENC_W]), c.P(Y.gp[G_ENC_W]), c.P(Y.gp[G_ENC_B]), c.P(Y.gp[G_POS0]), c.P(Y.gp[G_POS1]), c.P(Y.gp[G_POS2]), c.zsP,
         c.S(T_V0), c.S(T_GD), c.S(T_SH), KS, c.SL(0, S_VGIN), c.SL(0, S_UA) + 128, 256, zS, T, ng);
     SGRL_LAUNCH_OK();
@@ -198,7 +198,7 @@ inline int net_forward(const NetCtx& c, const float* obs, long long zsObs, const
     g = lin(c, c.SL(l, S_T31), 512, zS, lp[L_L4_W], lp[L_L4_B], c.SL(l, S_MM), 1024, zS, T, 1024, 256);
     g.rowdiv = c.SL(l, S_F2); g.zsRow = zS;
     SGRL_TRY(run_gemm(c, g));
-    matapply_fwd_kernel<<<dim3(grid_for_warps(T), c.nb), 256, 0, st>>>(c.SL(l, S_Z3), c.SL(l, S_MM), c.SL(l, S_R), zS, T);
+    launch_k(matapply_fwd_kernel, dim3(grid_for_warps(T), c.nb), 256, 0, st, c.SL(l, S_Z3), c.SL(l, S_MM), c.SL(l, S_R), zS, T);
     SGRL_LAUNCH_OK();
     g = lin(c, c.SL(l, S_R), 32, zS, lp[L_L5_W], -1, Vg_next, 128, zS, T3, 128, 32);
     g.res1 = Vg; g.zsR1 = zS; g.ldr1 = 128; g.res2 = c.SL(l, S_DV); g.zsR2 = zS; g.ldr2 = 128;
@@ -233,9 +233,9 @@ inline int net_forward(const NetCtx& c, const float* obs, long long zsObs, const
     g = lin(c, c.S(T_M1), 256, zS, Y.gp[G_H2M_W], Y.gp[G_H2M_B], c.S(T_MH), 1024, zS, T, 1024, 256);
     g.rowdiv = c.S(T_FH); g.zsRow = zS;
     SGRL_TRY(run_gemm(c, g));
-    matapply_fwd_kernel<<<dim3(grid_for_warps(T), c.nb), 256, 0, st>>>(c.S(T_ZH2), c.S(T_MH), c.S(T_RH), zS, T);
+    launch_k(matapply_fwd_kernel, dim3(grid_for_warps(T), c.nb), 256, 0, st, c.S(T_ZH2), c.S(T_MH), c.S(T_RH), zS, T);
     SGRL_LAUNCH_OK();
-    actor_out_fwd_kernel<<<dim3(grid_for_warps(T), c.nb), 256, 0, st>>>(c.S(T_RH), c.S(T_V0), c.P(Y.gp[G_DG_W]), c.zsP, c.S(T_W3), c.S(T_OUT), zS,
+    launch_k(actor_out_fwd_kernel, dim3(grid_for_warps(T), c.nb), 256, 0, st, c.S(T_RH), c.S(T_V0), c.P(Y.gp[G_DG_W]), c.zsP, c.S(T_W3), c.S(T_OUT), zS,
                                                                         c.max_action, T);
     SGRL_LAUNCH_OK();
   }
@@ -270,11 +270,10 @@ inline int net_backward(const NetCtx& c, const float* dOut, long long zsDo, int 
       SGRL_TRY(colsum(c, c.W(W_DQ), 1, Y.gp[G_DNG_B], T, 1));
     }
   } else {
-    actor_out_bwd_kernel<<<dim3(grid_for_warps(T) > 2 * NUM_SMS ? 2 * NUM_SMS : grid_for_warps(T), c.nb), 256, 0, st>>>(
-        dOut, zsDo, c.S(T_OUT), c.S(T_RH), c.S(T_V0), zS, c.P(Y.gp[G_DG_W]), c.zsP, c.W(W_DR), zW,
+    launch_k(actor_out_bwd_kernel, dim3(grid_for_warps(T) > 2 * NUM_SMS ? 2 * NUM_SMS : grid_for_warps(T), c.nb), 256, 0, st, dOut, zsDo, c.S(T_OUT), c.S(T_RH), c.S(T_V0), zS, c.P(Y.gp[G_DG_W]), c.zsP, c.W(W_DR), zW,
         wg ? c.Gr(Y.gp[G_DG_W]) : c.W(W_DQ) /*discarded*/, wg ? c.zsG : zW, c.max_action, T);
     SGRL_LAUNCH_OK();
-    matapply_bwd_kernel<<<dim3(grid_for_warps(T), c.nb), 256, 0, st>>>(c.W(W_DR), c.S(T_ZH2), c.S(T_MH), c.S(T_FH), zS,
+    launch_k(matapply_bwd_kernel, dim3(grid_for_warps(T), c.nb), 256, 0, st, c.W(W_DR), c.S(T_ZH2), c.S(T_MH), c.S(T_FH), zS,
                                                                        c.W(W_DZ3), c.W(W_DT4), dFh, zW, T);
     SGRL_LAUNCH_OK();
     if (wg) {
@@ -362,7 +361,7 @@ inline int net_backward(const NetCtx& c, const float* dOut, long long zsDo, int 
     g = dgrad(c, c.W(W_DVG), 128, lp[L_L5_W], 32, c.W(W_DR), 32, T3, 128, 32);
     SGRL_TRY(run_gemm(c, g));
     if (wg) SGRL_TRY(run_gemm(c, wgrad(c, c.W(W_DVG), 128, c.SL(l, S_R), 32, zS, lp[L_L5_W], 32, T3, 128, 32)));
-    matapply_bwd_kernel<<<dim3(grid_for_warps(T), c.nb), 256, 0, st>>>(c.W(W_DR), c.SL(l, S_Z3), c.SL(l, S_MM), c.SL(l, S_F2), zS,
+    launch_k(matapply_bwd_kernel, dim3(grid_for_warps(T), c.nb), 256, 0, st, c.W(W_DR), c.SL(l, S_Z3), c.SL(l, S_MM), c.SL(l, S_F2), zS,
                                                                        c.W(W_DZ3), c.W(W_DT4), c.W(W_DF2), zW, T);
     SGRL_LAUNCH_OK();
     if (wg) {
@@ -460,7 +459,7 @@ inline int net_backward(const NetCtx& c, const float* dOut, long long zsDo, int 
     SGRL_TRY(run_gemm(c, g));
     SGRL_TRY(colsum(c, c.W(W_DH), 128, Y.gp[G_ENC_B], T, 128, SQRT_D));
     int gx = ceil_div(T, 64); if (gx > NUM_SMS) gx = NUM_SMS; if (gx < 1) gx = 1;
-    pos_embed_bwd_kernel<<<dim3(gx, c.nb), 128, 0, st>>>(c.W(W_DH), 128, zW, c.rank3, c.Gr(Y.gp[G_POS0]), c.Gr(Y.gp[G_POS1]), c.Gr(Y.gp[G_POS2]), c.zsG, T);
+    launch_k(pos_embed_bwd_kernel, dim3(gx, c.nb), 128, 0, st, c.W(W_DH), 128, zW, c.rank3, c.Gr(Y.gp[G_POS0]), c.Gr(Y.gp[G_POS1]), c.Gr(Y.gp[G_POS2]), c.zsG, T);
     SGRL_LAUNCH_OK();
   }
   if (dact) {   // + sqrt(128) * dh0 . encoder.weight[:, 17:20]

@@ -9,6 +9,7 @@ thread_local char g_err[512] = "";
 long long g_launches = 0;
 Prof g_prof;
 long long* g_gemm_trace = nullptr;
+int g_pdl = -1;
 }
 using namespace sgrl;
 
@@ -183,7 +184,7 @@ int sgrl_gemm_presplit(const float* A, int lda, int trans_a, const float* B_hi, 
 int sgrl_td3_smooth_action(const float* pi_target, const float* noise, float* next_action, float noise_clip, float max_action,
                            int64_t n, sgrl_stream_t stream) {
   SGRL_CHECK(pi_target && noise && next_action, "null pointer");
-  td3_smooth_action_kernel<<<grid_for_flat(n * 4), 256, 0, ST(stream)>>>(pi_target, noise, next_action, noise_clip, max_action, n);
+  launch_k(td3_smooth_action_kernel, grid_for_flat(n * 4), 256, 0, ST(stream), pi_target, noise, next_action, noise_clip, max_action, n);
   SGRL_LAUNCH_OK();
   return 0;
 }
@@ -193,7 +194,7 @@ int sgrl_td3_critic_loss(const float* q1, const float* q2, const float* tq1, con
                          float reward_scale, int T, sgrl_stream_t stream) {
   SGRL_CHECK(q1 && q2 && tq1 && tq2 && reward && done && tok_graph && target && dq1 && dq2 && loss, "null pointer");
   int gx = ceil_div(T, 256); if (gx > NUM_SMS) gx = NUM_SMS;
-  td3_critic_loss_kernel<<<gx, 256, 0, ST(stream)>>>(q1, q2, tq1, tq2, reward, done, tok_graph, target, dq1, dq2, loss, discount, reward_scale, T);
+  launch_k(td3_critic_loss_kernel, gx, 256, 0, ST(stream), q1, q2, tq1, tq2, reward, done, tok_graph, target, dq1, dq2, loss, discount, reward_scale, T);
   SGRL_LAUNCH_OK();
   return 0;
 }
@@ -201,7 +202,7 @@ int sgrl_td3_critic_loss(const float* q1, const float* q2, const float* tq1, con
 int sgrl_td3_actor_loss(const float* q1, float* dq1, float* loss, int T, sgrl_stream_t stream) {
   SGRL_CHECK(q1 && dq1 && loss, "null pointer");
   int gx = ceil_div(T, 256); if (gx > NUM_SMS) gx = NUM_SMS;
-  td3_actor_loss_kernel<<<gx, 256, 0, ST(stream)>>>(q1, dq1, loss, T);
+  launch_k(td3_actor_loss_kernel, gx, 256, 0, ST(stream), q1, dq1, loss, T);
   SGRL_LAUNCH_OK();
   return 0;
 }
@@ -209,7 +210,7 @@ int sgrl_td3_actor_loss(const float* q1, float* dq1, float* loss, int T, sgrl_st
 int sgrl_sumsq(const float* g, int64_t n, float* out, sgrl_stream_t stream) {
   SGRL_CHECK(g && out, "null pointer");
   SGRL_CHECK(aligned16(g), "gradient arena must be 16-byte aligned");
-  sumsq_kernel<<<grid_for_flat(n), 256, 0, ST(stream)>>>(g, n, out);
+  launch_k(sumsq_kernel, grid_for_flat(n), 256, 0, ST(stream), g, n, out);
   SGRL_LAUNCH_OK();
   return 0;
 }
@@ -217,7 +218,7 @@ int sgrl_sumsq(const float* g, int64_t n, float* out, sgrl_stream_t stream) {
 int sgrl_split_tf32(const float* w, float* hi, float* lo, int64_t n, sgrl_stream_t stream) {
   SGRL_CHECK(w && hi && lo, "null pointer");
   SGRL_CHECK((n & 3) == 0 && aligned16(w) && aligned16(hi) && aligned16(lo), "arenas must be 16-byte aligned, n % 4 == 0");
-  split_tf32_kernel<<<grid_for_flat(n), 256, 0, ST(stream)>>>(w, hi, lo, n);
+  launch_k(split_tf32_kernel, grid_for_flat(n), 256, 0, ST(stream), w, hi, lo, n);
   SGRL_LAUNCH_OK();
   return 0;
 }
@@ -229,14 +230,14 @@ int sgrl_adam_clip(float* p, const float* g, float* m, float* v, int64_t n, cons
   SGRL_CHECK((p_hi == nullptr) == (p_lo == nullptr) && (!p_hi || (aligned16(p_hi) && aligned16(p_lo))), "p_hi/p_lo go together, 16-byte aligned");
   SGRL_CHECK((n & 3) == 0 && aligned16(p) && aligned16(g) && aligned16(m) && aligned16(v), "arenas must be 16-byte aligned, n % 4 == 0");
   AdamCfg c{lr, beta1, beta2, eps, max_norm, grad_scale};
-  adam_clip_kernel<<<grid_for_flat(n), 256, 0, ST(stream)>>>(p, g, m, v, n, sumsq, step, c, p_hi, p_lo);
+  launch_k(adam_clip_kernel, grid_for_flat(n), 256, 0, ST(stream), p, g, m, v, n, sumsq, step, c, p_hi, p_lo);
   SGRL_LAUNCH_OK();
   return 0;
 }
 
 int sgrl_bump_step(int32_t* step, sgrl_stream_t stream) {
   SGRL_CHECK(step, "null pointer");
-  bump_step_kernel<<<1, 1, 0, ST(stream)>>>(step);
+  launch_k(bump_step_kernel, 1, 1, 0, ST(stream), step);
   SGRL_LAUNCH_OK();
   return 0;
 }
@@ -247,7 +248,7 @@ int sgrl_polyak(float* target, const float* source, int64_t n, float tau, float*
   SGRL_CHECK((t_hi == nullptr) == (t_lo == nullptr) && (!t_hi || (aligned16(t_hi) && aligned16(t_lo) && (n_split & 3) == 0 && n_split <= n)),
              "t_hi/t_lo go together, 16-byte aligned, n_split % 4 == 0");
   SGRL_CHECK((n & 3) == 0 && aligned16(target) && aligned16(source), "arenas must be 16-byte aligned, n % 4 == 0");
-  polyak_kernel<<<grid_for_flat(n), 256, 0, ST(stream)>>>(target, source, n, tau, (float)(1.0 - (double)tau), t_hi, t_lo, n_split);
+  launch_k(polyak_kernel, grid_for_flat(n), 256, 0, ST(stream), target, source, n, tau, (float)(1.0 - (double)tau), t_hi, t_lo, n_split);
   SGRL_LAUNCH_OK();
   return 0;
 }

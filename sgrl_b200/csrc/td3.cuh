@@ -7,6 +7,7 @@ namespace sgrl {
 // next_action = clamp(pi_target(s') + clamp(noise, +-c), +-max_action)        agent.py:128-133
 __global__ void td3_smooth_action_kernel(const float* __restrict__ a, const float* __restrict__ noise, float* __restrict__ out,
                                          float noise_clip, float max_action, long long n) {
+  SGRL_PDL_ENTER();
   for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += gridDim.x * 256LL) {
     const float nz = fminf(fmaxf(noise[i], -noise_clip), noise_clip);
     out[i] = fminf(fmaxf(a[i] + nz, -max_action), max_action);
@@ -20,6 +21,7 @@ __global__ void __launch_bounds__(256) td3_critic_loss_kernel(
     const float* __restrict__ reward, const float* __restrict__ done, const int* __restrict__ tok_graph,
     float* __restrict__ target, float* __restrict__ dq1, float* __restrict__ dq2, float* __restrict__ loss,
     float discount, float reward_scale, int T) {
+  SGRL_PDL_ENTER();
   __shared__ float red[8];
   float acc = 0.f;
   const float invT = 1.f / (float)T;
@@ -44,6 +46,7 @@ __global__ void __launch_bounds__(256) td3_critic_loss_kernel(
 
 // actor loss = -mean(Q1):  dq = -1/T, loss += -sum(q)/T                                    agent.py:167
 __global__ void __launch_bounds__(256) td3_actor_loss_kernel(const float* __restrict__ q1, float* __restrict__ dq, float* __restrict__ loss, int T) {
+  SGRL_PDL_ENTER();
   __shared__ float red[8];
   float acc = 0.f;
   const float invT = 1.f / (float)T;
@@ -61,6 +64,7 @@ __global__ void __launch_bounds__(256) td3_actor_loss_kernel(const float* __rest
 
 // sum of squares of a flat gradient buffer -> *out (pre-zeroed)                            clip_grad_norm_, agent.py:152-155
 __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, long long n, float* __restrict__ out) {
+  SGRL_PDL_ENTER();
   __shared__ float red[8];
   float acc = 0.f;
   const long long n4 = n >> 2;
@@ -101,6 +105,7 @@ __device__ __forceinline__ void split_store4(float4 pv, float* hi, float* lo, lo
 }
 
 __global__ void __launch_bounds__(256) split_tf32_kernel(const float* __restrict__ w, float* __restrict__ hi, float* __restrict__ lo, long long n) {
+  SGRL_PDL_ENTER();
   const long long n4 = n >> 2;
   for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n4; i += gridDim.x * 256LL) split_store4(ldg4(w + i * 4), hi, lo, i);
 }
@@ -108,6 +113,7 @@ __global__ void __launch_bounds__(256) split_tf32_kernel(const float* __restrict
 __global__ void __launch_bounds__(256) adam_clip_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                                         float* __restrict__ v, long long n, const float* __restrict__ sumsq,
                                                         const int* __restrict__ step, AdamCfg c, float* __restrict__ hi, float* __restrict__ lo) {
+  SGRL_PDL_ENTER();
   __shared__ float sh[3];
   if (threadIdx.x == 0) {
     const float nrm = sqrtf(*sumsq) * c.grad_scale;
@@ -138,7 +144,8 @@ __global__ void __launch_bounds__(256) adam_clip_kernel(float* __restrict__ p, c
   }
 }
 
-__global__ void bump_step_kernel(int* step) { *step += 1; }
+__global__ void bump_step_kernel(int* step) {
+  SGRL_PDL_ENTER(); *step += 1; }
 
 // theta_t <- tau*theta + (1-tau)*theta_t                                                    functional.py:7-10
 // Rounded exactly like the reference's three fp32 tensor ops (mul, mul, add — no FMA contraction):
@@ -146,6 +153,7 @@ __global__ void bump_step_kernel(int* step) { *step += 1; }
 // hi/lo (nullable) cover the first n_split floats (the live prefix of the arena).
 __global__ void __launch_bounds__(256) polyak_kernel(float* __restrict__ tgt, const float* __restrict__ src, long long n,
                                                      float tau, float one_minus_tau, float* __restrict__ hi, float* __restrict__ lo, long long n_split) {
+  SGRL_PDL_ENTER();
   const long long n4 = n >> 2;
   for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n4; i += gridDim.x * 256LL) {
     float4 t = *reinterpret_cast<float4*>(tgt + i * 4);
