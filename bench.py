@@ -205,7 +205,7 @@ def run_ours(a):
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
-    l0 = _lib.lib.sgrl_launch_count()
+    l0 = _lib.lib.sgrl_launch_count() + agent.graph_replayed_launches
     barrier()
     for i in range(K):
         flush.zero_()
@@ -213,7 +213,7 @@ def run_ours(a):
         agent.update(devb[i % nbat], i, noise=noise[i % nbat])
         ev[i][1].record()
     barrier()
-    launches = (_lib.lib.sgrl_launch_count() - l0) / K
+    launches = (_lib.lib.sgrl_launch_count() + agent.graph_replayed_launches - l0) / K
     clk = clocks.stop() if rank == 0 else None
     total_ms = sum(s.elapsed_time(e) for s, e in ev)
     t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
@@ -254,12 +254,15 @@ def run_ours(a):
     # ---- roofline pass: device time per kernel class (CUDA events on the launching stream), 2 updates
     pk = peaks()
     barrier()
+    graphs_on = agent.use_graphs
+    agent.use_graphs = False          # the per-class timing pass brackets single launches with events: eager, one stream
     _lib.lib.sgrl_profile(1)
     for i in range(2):
         agent.update(devb[i % nbat], i, noise=noise[i % nbat])
     torch.cuda.synchronize()
     prof = _lib.profile_collect()
     _lib.lib.sgrl_profile(0)
+    agent.use_graphs = graphs_on
     step_ms = total_ms / K
     classes = {}
     for name, (ms, work, cnt) in prof.items():

@@ -51,7 +51,7 @@ int sgrl_arena_floats(int kind, int n_layers, int64_t* live_floats, int64_t* dea
 /* floats of forward stash per net instance for T tokens (keep=1: training, every layer kept;
  * keep=0: rollout, layers alias) and of backward workspace */
 int64_t sgrl_stash_floats(int kind, int n_layers, int64_t T, int keep);
-int64_t sgrl_ws_floats(int64_t T);
+int64_t sgrl_ws_floats(int n_layers, int64_t T);
 /* offset (floats) and floats-per-token of a named stash buffer (layer<0: global buffer); for tests */
 int sgrl_stash_info(int kind, int n_layers, int64_t T, int keep, const char* name, int layer,
                     int64_t* offset, int* per_token);

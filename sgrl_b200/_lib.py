@@ -56,7 +56,7 @@ _PROTOS = {
     "sgrl_param_info": (c_int, [c_int, c_int, c_int, C.c_char_p, c_int, C.POINTER(c_int), C.POINTER(c_int), C.POINTER(c_i64), C.POINTER(c_int)]),
     "sgrl_arena_floats": (c_int, [c_int, c_int, C.POINTER(c_i64), C.POINTER(c_i64)]),
     "sgrl_stash_floats": (c_i64, [c_int, c_int, c_i64, c_int]),
-    "sgrl_ws_floats": (c_i64, [c_i64]),
+    "sgrl_ws_floats": (c_i64, [c_int, c_i64]),
     "sgrl_stash_info": (c_int, [c_int, c_int, c_i64, c_int, C.c_char_p, c_int, C.POINTER(c_i64), C.POINTER(c_int)]),
     "sgrl_set_forward": (c_int, [C.POINTER(NetCall), c_f, c_i64, c_f, c_i64, c_f, c_i64, c_f]),
     "sgrl_set_backward": (c_int, [C.POINTER(NetCall), c_f, c_i64, c_int, c_f, c_i64, c_f]),

@@ -13,6 +13,8 @@ update (data parallel over replay samples / morphologies).
 from __future__ import annotations
 
 import ctypes as C
+import os
+import warnings
 from typing import Dict, Optional
 
 import numpy as np
@@ -89,6 +91,76 @@ def soft_update_network(source: SetNetModule, target: SetNetModule, tau: float):
     check(lib.sgrl_polyak(ptr(t), ptr(s), s.numel(), float(tau), ptr(hi), ptr(lo), target.live_arena.numel(), stream()), "sgrl_polyak")
 
 
+class _UpdatePlan:
+    """Static device state of Agent.update for one (morphology tables, batch size): input staging buffers, activation
+    stashes, backward workspace, small result buffers, the three forward streams and the two captured graphs."""
+
+    def __init__(self, agent: "Agent", tb, B: int, width: int):
+        dev = agent.actor.full_arena.device
+        T = tb.T
+        n = width // 41
+        f = lambda *shape: torch.empty(*shape, dtype=torch.float32, device=dev)
+        self.tb, self.B, self.agent = tb, B, agent
+        self.obs, self.nobs, self.act = f(B, width), f(B, width), f(B, 3 * n)
+        self.rew, self.done, self.noise = f(B), f(B), f(B, 3 * n)
+        self.a_t, self.next_action, self.pi = f(1, T, 3), f(T, 3), f(1, T, 3)
+        self.tq, self.q, self.q1 = f(2, T, 1), f(2, T, 1), f(1, T, 1)
+        self.dq, self.dq1, self.dact = f(2, T, 1), f(1, T, 1), f(1, T, 3)
+        self.target, self.scal = f(T), torch.zeros(2, dtype=torch.float32, device=dev)
+        ac, cr = agent.actor, agent.critic
+        self.stash_at = f(ac.stash_floats(T, False, 1))
+        self.stash_ct = f(cr.stash_floats(T, False, 2))
+        self.stash_c = f(cr.stash_floats(T, True, 2))
+        self.stash_a = f(ac.stash_floats(T, True, 1))
+        self.ws = f(max(cr.ws_floats(T, 2), ac.ws_floats(T, 1)))
+        self.s1, self.s2 = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+        self.ev_start, self.ev_a, self.ev_c = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
+        self.graphs = {}
+        self.graph_launches = {True: 0, False: 0}      # kernels of this library inside each captured graph
+        self.eager_runs = {True: 0, False: 0}
+
+    def load(self, batch: Dict, noise, policy_noise: float):
+        """Stage one replay batch (host numpy / pinned or device tensors) into the static input buffers."""
+        for dst, key in ((self.obs, "obs"), (self.act, "action"), (self.nobs, "next_obs"), (self.rew, "reward"), (self.done, "done")):
+            src = batch[key]
+            if not torch.is_tensor(src):
+                src = torch.as_tensor(np.asarray(src), dtype=torch.float32)
+            dst.copy_(src.reshape(dst.shape), non_blocking=True)
+        if noise is None:
+            self.noise.normal_(0.0, policy_noise)                                     # agent.py:128
+        else:
+            if not torch.is_tensor(noise):
+                noise = torch.as_tensor(np.asarray(noise), dtype=torch.float32)
+            self.noise.copy_(noise.reshape(self.noise.shape), non_blocking=True)
+
+    def replay(self, actor_step: bool):
+        g = self.graphs.get(actor_step)
+        if g is None:
+            # one eager run first (lazy one-time initialisation inside the library: function attributes, side streams,
+            # tensor-map cache), then capture the second
+            if self.eager_runs[actor_step] < 1:
+                self.eager_runs[actor_step] += 1
+                self.agent._update_impl(self, actor_step)
+                return
+            try:
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                l0 = lib.sgrl_launch_count()
+                with torch.cuda.graph(g):
+                    self.agent._update_impl(self, actor_step)
+                self.graph_launches[actor_step] = lib.sgrl_launch_count() - l0
+            except Exception as ex:   # keep running eagerly (still the CUDA path); say so once
+                warnings.warn(f"sgrl_b200: CUDA-graph capture of Agent.update failed ({ex}); running eagerly")
+                self.agent.use_graphs = False
+                torch.cuda.synchronize()
+                self.agent._update_impl(self, actor_step)
+                return
+            self.graphs[actor_step] = g
+            self.agent.graph_replayed_launches -= self.graph_launches[actor_step]   # the capture itself was counted by the library
+        g.replay()
+        self.agent.graph_replayed_launches += self.graph_launches[actor_step]
+
+
 class Agent(nn.Module):
     def __init__(self, args):
         super().__init__()
@@ -117,6 +189,10 @@ class Agent(nn.Module):
         self.target_smoothing_tau = args.agent.target_smoothing_tau
         self.reward_scale = args.agent.reward_scale
         self.lazy_stats = False      # True: reward statistics returned as 0-dim tensors (no host sync)
+        self.use_graphs = os.environ.get("SGRL_GRAPHS", "1") != "0"   # replay Agent.update as a captured CUDA graph
+        self._plans: Dict = {}
+        self._plan_sig = None
+        self.graph_replayed_launches = 0     # library kernels executed through graph replays (sgrl_launch_count() sees captures only)
         self._loss = None
 
     # ------------------------------------------------------------------ TD3 step
@@ -129,59 +205,100 @@ class Agent(nn.Module):
             import torch.distributed as dist
             dist.all_reduce(g, op=dist.ReduceOp.SUM)
 
+    def _plan(self, tb, B: int, width: int) -> "_UpdatePlan":
+        key = (id(tb), B)
+        plan = self._plans.get(key)
+        if plan is None or plan.tb is not tb:
+            if len(self._plans) >= 8:
+                self._plans.clear()
+            plan = _UpdatePlan(self, tb, B, width)
+            self._plans[key] = plan
+        return plan
+
     def update(self, data_batch: Dict, it: int, noise: Optional[torch.Tensor] = None):
         """One TD3 update (src/agent.py:117-183).  data_batch: obs (B,41N), action (B,3N),
         next_obs, reward (B,1), done (B,1) — torch tensors (any device) or numpy arrays.
-        `noise` (B,3N) optionally injects the target-policy noise (drawn on device otherwise)."""
+        `noise` (B,3N) optionally injects the target-policy noise (drawn on device otherwise).
+
+        The batch is copied into a static per-(morphology, B) plan (inputs, activation stashes, workspaces), then
+        the whole step runs as ONE captured CUDA graph (two graphs per plan: with and without the delayed actor
+        step) — three forward chains on parallel streams, weight-gradient GEMMs on side streams (csrc/net.cuh).
+        `self.use_graphs = False` runs the same sequence eagerly."""
         a = self.args
         dev = self.actor.full_arena.device
-        reward_in = data_batch["reward"]
-        t = {k: _to_dev(data_batch[k], dev) for k in ("obs", "action", "next_obs", "reward", "done")}
-        obs, act, nobs, rew, done = t["obs"], t["action"], t["next_obs"], t["reward"].reshape(-1), t["done"].reshape(-1)
-        B = obs.shape[0]
+        if dev.type != "cuda":
+            raise RuntimeError("sgrl_b200.Agent.update needs the modules on a CUDA device (no CPU fallback)")
+        obs_in = data_batch["obs"]
+        B, width = int(obs_in.shape[0]), int(obs_in.shape[1])
         tb = self.actor._tables(B)
-        T, st = tb.T, stream()
-        world = self._world()
-        if noise is None:
-            noise = torch.randn(B, act.shape[1], device=dev) * a.policy_noise                    # agent.py:128
+        mods = (self.actor, self.actor_target, self.critic, self.critic_target)
+        # the plans (and their captured graphs) hold raw pointers: drop them when a module was moved / re-flattened or
+        # its GEMM path changed; parameters edited from Python (load_state_dict, p.data.copy_) only stale the tf32 split
+        sig = tuple((m._arena.data_ptr(), int(m.use_tc)) for m in mods)
+        if sig != self._plan_sig:
+            self._plans.clear()
+            self._plan_sig = sig
+        for m in mods:
+            m._split_for(tb.T, True)
+        plan = self._plan(tb, B, width)
+        plan.load(data_batch, noise, float(a.policy_noise))
+        actor_step = it % a.policy_freq == 0
+        if self.use_graphs:
+            plan.replay(actor_step)
         else:
-            noise = _to_dev(noise, dev)
-        # ---- target:  y = r + (1-d) * gamma * min_i Q_i'(s', clip(pi'(s') + clip(eps)))       agent.py:127-139
-        a_t, _ = self.actor_target.forward_raw(tb, nobs, None, keep=False, trusted_split=True)
-        next_action = torch.empty(T, 3, device=dev)
-        check(lib.sgrl_td3_smooth_action(ptr(a_t), ptr(noise), ptr(next_action), float(a.noise_clip), float(a.max_action), T * 3, st))
-        tq, _ = self.critic_target.forward_raw(tb, nobs, next_action, keep=False, nb=2, trusted_split=True)
-        # ---- critic step                                                                       agent.py:142-156
-        q, stash = self.critic.forward_raw(tb, obs, act, keep=True, nb=2, trusted_split=True)
-        scal = torch.zeros(2, device=dev)            # [critic_loss, actor_loss]
-        target = torch.empty(T, device=dev)
-        dq = torch.empty(2, T, 1, device=dev)
-        check(lib.sgrl_td3_critic_loss(ptr(q[0]), ptr(q[1]), ptr(tq[0]), ptr(tq[1]), ptr(rew), ptr(done), ptr(tb.tok_graph), ptr(target),
-                                       ptr(dq[0]), ptr(dq[1]), ptr(scal), float(a.discount), float(self.reward_scale), T, st))
+            self._update_impl(plan, actor_step)
+        scal = plan.scal.clone()
+        loss_dict = {"loss/critic_loss": scal[0]}
+        loss_dict.update(self._reward_stats(data_batch["reward"], plan.rew))
+        if actor_step:
+            loss_dict["loss/actor_loss"] = scal[1]
+        self.tot_update_count += 1
+        self._last_target = plan.target
+        return loss_dict
+
+    def _update_impl(self, p: "_UpdatePlan", actor_step: bool):
+        """Enqueue one update on the current stream (+ p.s1, p.s2 and the library's side streams).  Capture-safe:
+        no allocation, no host synchronisation."""
+        a = self.args
+        tb, T, st = p.tb, p.tb.T, stream()
+        world = self._world()
+        main = torch.cuda.current_stream()
+        p.scal.zero_()
+        p.ev_start.record(main)
+        # ---- chain A (stream s1): y = r + (1-d) * gamma * min_i Q_i'(s', clip(pi'(s') + clip(eps)))        agent.py:127-139
+        with torch.cuda.stream(p.s1):
+            p.s1.wait_event(p.ev_start)
+            self.actor_target.forward_raw(tb, p.nobs, None, keep=False, trusted_split=True, out=p.a_t, stash=p.stash_at)
+            check(lib.sgrl_td3_smooth_action(ptr(p.a_t), ptr(p.noise), ptr(p.next_action), float(a.noise_clip), float(a.max_action), T * 3,
+                                             stream()))
+            self.critic_target.forward_raw(tb, p.nobs, p.next_action, keep=False, nb=2, trusted_split=True, out=p.tq, stash=p.stash_ct)
+            p.ev_a.record(p.s1)
+        # ---- chain C (stream s2, delayed actor step only): pi(s) — independent of the critic step           agent.py:167
+        if actor_step:
+            with torch.cuda.stream(p.s2):
+                p.s2.wait_event(p.ev_start)
+                self.actor.forward_raw(tb, p.obs, None, keep=True, trusted_split=True, out=p.pi, stash=p.stash_a)
+                p.ev_c.record(p.s2)
+        # ---- chain B (main): critic step                                                                    agent.py:142-156
+        self.critic.forward_raw(tb, p.obs, p.act, keep=True, nb=2, trusted_split=True, out=p.q, stash=p.stash_c)
+        main.wait_event(p.ev_a)
+        check(lib.sgrl_td3_critic_loss(ptr(p.q[0]), ptr(p.q[1]), ptr(p.tq[0]), ptr(p.tq[1]), ptr(p.rew), ptr(p.done), ptr(tb.tok_graph),
+                                       ptr(p.target), ptr(p.dq[0]), ptr(p.dq[1]), ptr(p.scal), float(a.discount), float(self.reward_scale), T, st))
         self.critic_optimizer.zero_grad()
-        self.critic.backward_raw(tb, stash, dq, 2, self.critic.grad_arena(), False, trusted_split=True)
-        del stash
+        self.critic.backward_raw(tb, p.stash_c, p.dq, 2, self.critic.grad_arena(), False, trusted_split=True, ws=p.ws)
         self._allreduce(self.critic.grad_arena(), world)
         self.critic_optimizer.step(max_norm=float(a.grad_clipping_value), world_size=world)
-        loss_dict = {"loss/critic_loss": scal[0]}
-        loss_dict.update(self._reward_stats(reward_in, rew))
-        # ---- delayed actor step + Polyak                                                       agent.py:165-180
-        if it % a.policy_freq == 0:
-            pi, stash_a = self.actor.forward_raw(tb, obs, None, keep=True, trusted_split=True)
-            q1, stash_c = self.critic.forward_raw(tb, obs, pi[0], keep=True, nb=1, trusted_split=True)
-            dq1 = torch.empty(1, T, 1, device=dev)
-            check(lib.sgrl_td3_actor_loss(ptr(q1), ptr(dq1), ptr(scal[1:]), T, st))
-            dact = self.critic.backward_raw(tb, stash_c, dq1, 1, None, True, trusted_split=True)     # only d/d(action) is needed
+        # ---- delayed actor step + Polyak                                                                    agent.py:165-180
+        if actor_step:
+            main.wait_event(p.ev_c)
+            self.critic.forward_raw(tb, p.obs, p.pi[0], keep=True, nb=1, trusted_split=True, out=p.q1, stash=p.stash_c)
+            check(lib.sgrl_td3_actor_loss(ptr(p.q1), ptr(p.dq1), ptr(p.scal[1:]), T, st))
+            self.critic.backward_raw(tb, p.stash_c, p.dq1, 1, None, True, trusted_split=True, ws=p.ws, dact=p.dact)   # only d/d(action)
             self.actor_optimizer.zero_grad()
-            self.actor.backward_raw(tb, stash_a, dact, 1, self.actor.grad_arena(), False, trusted_split=True)
-            del stash_a, stash_c
+            self.actor.backward_raw(tb, p.stash_a, p.dact, 1, self.actor.grad_arena(), False, trusted_split=True, ws=p.ws)
             self._allreduce(self.actor.grad_arena(), world)
             self.actor_optimizer.step(max_norm=float(a.grad_clipping_value), world_size=world)
             self.try_update_target_network()
-            loss_dict["loss/actor_loss"] = scal[1]
-        self.tot_update_count += 1
-        self._last_target = target
-        return loss_dict
 
     train_step = update   # BASELINE.json calls the TD3 step "train()"; the reference name is update (agent.py:117)
 

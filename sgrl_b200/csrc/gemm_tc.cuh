@@ -51,6 +51,7 @@ template <int BN> struct TcCfg {
   // profiles/r01b_mma_probe.txt).  TA_STAGES slots of 64 columns hold [hi 32 | lo 32] of one k-block.
   static constexpr int TA_STAGES = (512 - ACC_COLS) / 64;           // 2 | 4
   static constexpr int TMEM_COLS = 512;
+  static constexpr int UNROLL = BN == 128 ? 4 : 12;                 // lcm(STAGES, TA_STAGES, NMAIN)
   static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
@@ -371,9 +372,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
   if (nloc > 0) {
     if (warp == 0) {
       // ===================== TMA producer (warp-uniform loop, one elected lane issues) =====================
+      int s = 0; uint32_t ph = 0;
       for (int i = 0; i < nloc; ++i) {
-        const int s = i % STAGES, ph = (i / STAGES) & 1, k0 = (kb0 + i) * TC_BK;
-        mbar_wait(empty_bar(s), ph ^ 1);
+        const int k0 = (kb0 + i) * TC_BK;
+        mbar_wait(empty_bar(s), ph ^ 1u);
         if (elect_one()) {
           mbar_arrive_expect_tx(full_bar(s), TC_A_BYTES + (BPRE ? 2 : 1) * B_BYTES);
           const uint32_t a_dst = smem_base + s * STAGE_BYTES, b_dst = a_dst + TC_A_BYTES;
@@ -393,6 +395,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
           if (i < 12) TC_STAMP(8 + i);
         }
         __syncwarp();
+        if (++s == STAGES) { s = 0; ph ^= 1u; }
       }
     } else if (warp == 1) {
       // ===================== MMA issuer =====================
@@ -409,38 +412,65 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
       constexpr uint32_t B_HIW = (B_SBO >> 4) | (1u << 14) | (B_LAY << 29), B_LOW = (B_LBO >> 4) << 16;
       const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
       const uint32_t acc_lo = tb + NMAIN * BN, tab = tb + Cfg::ACC_COLS;
-      for (int i = 0; i < nloc; ++i) {
-        const int s = i % STAGES, ph = (i / STAGES) & 1, t = i % TA, pht = (i / TA) & 1;
-        mbar_wait(full_bar(s), ph);
-        mbar_wait(ta_ready(t), pht);
-        tc_fence_after();
-        if (i < 12 && lane == 0) TC_STAMP(44 + i);
-        const uint32_t b_hi = (((smem_base + s * STAGE_BYTES + TC_A_BYTES) >> 4) & 0x3FFFu) | B_LOW, b_lo = b_hi + (B_BYTES >> 4);
-        const uint32_t a_hi = tab + t * 64, a_lo = a_hi + 32;
-        const uint32_t acc_hi = tb + (i % NMAIN) * BN;            // main accumulators rotate per k-block (see TcCfg)
-        const uint32_t first_hi = i >= NMAIN ? 1u : 0u, first_lo = i > 0 ? 1u : 0u;
-        if (elect_one()) {
+      const uint32_t bdesc0 = (((smem_base + TC_A_BYTES) >> 4) & 0x3FFFu) | B_LOW;
+      // Measured (tools/mma_probe.cu, profiles/r01b_mma_probe.txt): the tensor pipe drains during ANY gap in the issue
+      // stream (queue of ~1-2 MMAs), so every instruction between two MMAs is exposed.  The loop is therefore unrolled
+      // over UNR = lcm(STAGES, TA_STAGES, NMAIN) k-blocks (ring slots, TMEM slots, accumulators and phase parities fold
+      // to constants) and the barrier waits of block i+1 sit between the 8th and 9th MMA of block i.
+      constexpr int UNR = Cfg::UNROLL;
+      static_assert(UNR % STAGES == 0 && UNR % TA == 0 && UNR % NMAIN == 0, "unroll must cover whole ring turns");
+      mbar_wait(full_bar(0), 0);
+      mbar_wait(ta_ready(0), 0);
+      tc_fence_after();
+      for (int it = 0, i0 = 0; i0 < nloc; ++it, i0 += UNR) {
 #pragma unroll
-          for (int k = 0; k < TC_BK / 8; ++k)
-            tc_mma_tf32_ts(acc_hi, a_hi + 8 * k, b_hi + k * (B_KSTEP >> 4), B_HIW, idesc, k > 0 ? 1u : first_hi);
+        for (int u = 0; u < UNR; ++u) {
+          const int i = i0 + u;
+          if (i < nloc) {                                                  // warp-uniform
+            const int s = u % STAGES, t = u % TA;
+            const uint32_t b_hi = bdesc0 + (uint32_t)(s * (STAGE_BYTES >> 4)), b_lo = b_hi + (B_BYTES >> 4);
+            const uint32_t a_hi = tab + t * 64, a_lo = a_hi + 32;
+            const uint32_t acc_hi = tb + (u % NMAIN) * BN;                 // main accumulators rotate per k-block (see TcCfg)
+            const uint32_t first_hi = (it > 0 || u >= NMAIN) ? 1u : 0u, first_lo = (it > 0 || u > 0) ? 1u : 0u;
+            if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < TC_BK / 8; ++k) {
-            tc_mma_tf32_ts(acc_lo, a_lo + 8 * k, b_hi + k * (B_KSTEP >> 4), B_HIW, idesc, k > 0 ? 1u : first_lo);
-            tc_mma_tf32_ts(acc_lo, a_hi + 8 * k, b_lo + k * (B_KSTEP >> 4), B_HIW, idesc, 1u);
+              for (int k = 0; k < TC_BK / 8; ++k)
+                tc_mma_tf32_ts(acc_hi, a_hi + 8 * k, b_hi + k * (B_KSTEP >> 4), B_HIW, idesc, k > 0 ? 1u : first_hi);
+#pragma unroll
+              for (int k = 0; k < 2; ++k) {
+                tc_mma_tf32_ts(acc_lo, a_lo + 8 * k, b_hi + k * (B_KSTEP >> 4), B_HIW, idesc, k > 0 ? 1u : first_lo);
+                tc_mma_tf32_ts(acc_lo, a_hi + 8 * k, b_lo + k * (B_KSTEP >> 4), B_HIW, idesc, 1u);
+              }
+            }
+            __syncwarp();
+            if (i + 1 < nloc) {                                            // operands of the next block (hidden behind queued MMAs)
+              const int un = (u + 1) % UNR, itn = it + (u + 1 == UNR ? 1 : 0);
+              mbar_wait(full_bar(un % STAGES), (uint32_t)((UNR / STAGES) * itn + un / STAGES) & 1u);
+              mbar_wait(ta_ready(un % TA), (uint32_t)((UNR / TA) * itn + un / TA) & 1u);
+              tc_fence_after();
+            }
+            if (elect_one()) {
+#pragma unroll
+              for (int k = 2; k < TC_BK / 8; ++k) {
+                tc_mma_tf32_ts(acc_lo, a_lo + 8 * k, b_hi + k * (B_KSTEP >> 4), B_HIW, idesc, 1u);
+                tc_mma_tf32_ts(acc_lo, a_hi + 8 * k, b_lo + k * (B_KSTEP >> 4), B_HIW, idesc, 1u);
+              }
+              tc_commit(empty_bar(s));                     // smem stage reusable once these MMAs retire
+              tc_commit(ta_empty(t));                      // so is the TMEM A slot
+              if (i == nloc - 1) tc_commit(acc_bar);       // accumulators complete
+            }
+            __syncwarp();
           }
-          tc_commit(empty_bar(s));                     // smem stage reusable once these MMAs retire
-          tc_commit(ta_empty(t));                      // so is the TMEM A slot
-          if (i == nloc - 1) tc_commit(acc_bar);       // accumulators complete
         }
-        __syncwarp();
       }
     } else {
       // ===================== converters: smem A tile -> (hi, lo) rows in TMEM; B lo in smem when not pre-split =====================
       // two groups of 4 warps take alternate k-blocks; thread = one tile row = one TMEM lane
       const int g = (warp - 2) >> 2, q = warp & 3, row = q * 32 + lane, cgt = ((warp - 2) & 3) * 32 + lane;
       const uint32_t trow = ta_base + ((uint32_t)(q * 32) << 16);
+      static_assert(STAGES % 2 == 0 && TA % 2 == 0, "two converter groups take alternate ring slots");
+      int s = g, t = g; uint32_t ph = 0, pht = 0;
       for (int i = g; i < nloc; i += 2) {
-        const int s = i % STAGES, ph = (i / STAGES) & 1, t = i % TA, pht = (i / TA) & 1;
         mbar_wait(full_bar(s), ph);
         if (tid == 64 && i < 12) TC_STAMP(20 + i);
         const uint32_t st = smem_base + s * STAGE_BYTES;
@@ -459,7 +489,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
         if (!BPRE) split_tile_lo<B_BYTES / 16, B_BYTES, 128>(st + TC_A_BYTES, cgt);
 #pragma unroll
         for (int j = 0; j < 32; ++j) lo[j] = lo_of_trunc(__uint_as_float(raw[j]));
-        mbar_wait(ta_empty(t), pht ^ 1);
+        mbar_wait(ta_empty(t), pht ^ 1u);
         tc_fence_after();
         tmem_st32(trow + (uint32_t)(t * 64), raw);
         tmem_st32(trow + (uint32_t)(t * 64 + 32), lo);
@@ -469,6 +499,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
         __syncwarp();
         if (lane == 0) mbar_arrive(ta_ready(t));
         if (tid == 64 && i < 12) TC_STAMP(32 + i);
+        s += 2; if (s >= STAGES) { s -= STAGES; ph ^= 1u; }
+        t += 2; if (t >= TA) { t -= TA; pht ^= 1u; }
       }
       // ===================== epilogue: TMEM -> registers -> smem transpose -> coalesced global =====================
       // 8 warps: warp w owns TMEM lane quarter w & 3 (hardware rule) and column half (w - 2) >> 2 of the tile
@@ -661,11 +693,40 @@ inline int gemm_tc(const GemmP& p_in, cudaStream_t st) {
   SGRL_CHECK((p.Blo == nullptr) == (p.Bhi == nullptr), "gemm_tc: Bhi and Blo go together");
   SGRL_CHECK(p.Blo == nullptr || (host_vec_ok(p.Blo, p.ldb, p.zsB) && host_vec_ok(p.Bhi, p.ldb, p.zsB)), "gemm_tc: pre-split B parts not TMA-compatible");
   const float* Bsrc = p.Blo ? p.Bhi : p.B;
-  // tile width: 128 unless that leaves most SMs idle
-  const long long ctas128 = (long long)ceil_div(p.M, TC_BM) * ceil_div(p.N, 128) * p.nb * p.splitk;
-  const int BN = (p.N > 64 && ctas128 >= 100) ? 128 : 64;
+  // Tile width and split-K from a small cost model in SM cycles: ceil(CTAs / wave) x (fixed + k-blocks x block time).
+  // Block times are the measured mainloop periods (tools/gemm_trace.py), the fixed part covers prologue, pipeline
+  // fill and epilogue.  The step runs several kernels concurrently (three forward chains, dW GEMMs on side streams),
+  // so what matters is SM-time (CTAs x duration) more than the duration of one kernel alone: the "wave" is therefore
+  // a third of the machine, not 148 (swept on B200: tools/sweep.sh, 6.27 ms/update at 48 vs 7.0 ms at 148).  A caller passes splitk > 1 to say "the epilogue is linear and C is pre-zeroed/accumulated":
+  // only then may K be split (atomics); the factor itself is chosen here.
   const int nkb = ceil_div(p.K, TC_BK);
-  if (p.splitk > nkb) p.splitk = nkb;
+  int BN = 64, sk = 1;
+  {
+    struct Tune { double blk64, blk128, fix64, fix128, split_fix; int wave; };
+    static const Tune tn = [] {
+      auto env = [](const char* k, double d) { const char* e = getenv(k); return e ? atof(e) : d; };
+      Tune t;
+      t.blk64 = env("SGRL_TC_BLK64", 860.0); t.blk128 = env("SGRL_TC_BLK128", 960.0);
+      t.fix64 = env("SGRL_TC_FIX64", 3000.0); t.fix128 = env("SGRL_TC_FIX128", 4000.0);
+      t.split_fix = env("SGRL_TC_SPLITFIX", 1500.0); t.wave = (int)env("SGRL_TC_WAVE", 48.0);
+      return t;
+    }();
+    const bool may_split = p.splitk > 1;
+    double best = 1e30;
+    for (int bn = 64; bn <= 128; bn += 64) {
+      if (bn == 128 && p.N <= 64) break;
+      const long long base = (long long)ceil_div(p.M, TC_BM) * ceil_div(p.N, bn) * p.nb;
+      const double blk = bn == 128 ? tn.blk128 : tn.blk64, fixed = bn == 128 ? tn.fix128 : tn.fix64;
+      const int sk_max = may_split ? (nkb / 4 < 1 ? 1 : (nkb / 4 > 64 ? 64 : nkb / 4)) : 1;
+      for (int k = 1; k <= sk_max; ++k) {
+        const long long ctas = base * k;
+        const double waves = (double)((ctas + tn.wave - 1) / tn.wave);
+        const double cost = waves * (fixed + (k > 1 ? tn.split_fix : 0.0) + ceil_div(nkb, k) * blk);
+        if (cost < best * 0.98) { best = cost; BN = bn; sk = k; }
+      }
+    }
+  }
+  p.splitk = sk;
   p.vecE = host_vec_ok(p.C, p.ldc, p.zsC) && (!p.mask || host_vec_ok(p.mask, p.ldmask, p.zsMask)) &&
            (!p.res1 || host_vec_ok(p.res1, p.ldr1, p.zsR1)) && (!p.res2 || host_vec_ok(p.res2, p.ldr2, p.zsR2));
   const long long nzA = p.zsA ? p.nb : 1, nzB = p.zsB ? p.nb : 1;

@@ -345,16 +345,19 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ X
   }
 }
 
-// strided copy / add of a (T x N) block:  dst = (add ? dst : 0) + src
+// strided copy / add of a (T x N) block:  dst = (add ? dst : 0) + src (+ src2)
 __global__ void __launch_bounds__(256) block_copy_kernel(float* __restrict__ dst, int ldd, long long zsD,
-                                                         const float* __restrict__ src, int lds, long long zsSrc, int M, int N, int add) {
+                                                         const float* __restrict__ src, int lds, long long zsSrc,
+                                                         const float* __restrict__ src2, int lds2, long long zsSrc2, int M, int N, int add) {
   SGRL_PDL_ENTER();
   const int z = blockIdx.y;
   dst += z * zsD; src += z * zsSrc;
+  if (src2) src2 += z * zsSrc2;
   const long long total = (long long)M * N;
   for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += gridDim.x * 256LL) {
     const int m = (int)(i / N), n = (int)(i % N);
-    const float v = src[(long long)m * lds + n];
+    float v = src[(long long)m * lds + n];
+    if (src2) v += src2[(long long)m * lds2 + n];
     float* d = dst + (long long)m * ldd + n;
     *d = add ? *d + v : v;
   }

@@ -18,22 +18,50 @@
 namespace sgrl {
 
 // ---- backward workspace (floats per token, per net instance) --------------------------
+// One FRAME of buffers per backward stage (frame l = encoder layer l, frame n_layers = the heads + final norm), no
+// buffer is reused inside a frame: the weight-gradient GEMMs run on side streams (see Side below) and may read a dY
+// buffer long after the data-gradient chain has moved on.  Gradients carried between stages (dVg, dh) are written
+// out of place into the consuming stage's frame.
 enum WS {
-  W_DVG, W_DH, W_DUA, W_DUB, W_DQKV, W_DVGP, W_DO, W_DOG, W_DX, W_DDV, W_DZ1, W_DZ2, W_DZ3, W_DG,
-  W_DF1, W_DF2, W_DA, W_DT31, W_DT4, W_DR, W_DFF, W_DUH, W_DSH, W_DQ, WS_COUNT
+  W_DVG, W_DH, W_DH1, W_DUA, W_DUB, W_DQKV, W_DVGP, W_DO, W_DOG, W_DX, W_DDV, W_DZ1, W_DZ2, W_DZ3, W_DG,
+  W_DF1, W_DF2, W_DA, W_DA2, W_DA3, W_DT31, W_DT4, W_DR, W_DFF, W_DUH, W_DSH, W_DQ, WS_COUNT
 };
 inline const int* ws_sizes() {
-  static const int s[WS_COUNT] = {384, 128, 256, 256, 768, 756, 256, 768, 128, 384, 96, 96, 96, 1024,
-                                  1, 1, 256, 512, 1024, 96, 128, 256, 148, 3};
+  static const int s[WS_COUNT] = {384, 128, 128, 256, 256, 768, 756, 256, 768, 128, 384, 96, 96, 96, 1024,
+                                  1, 1, 256, 256, 128, 512, 1024, 96, 128, 256, 148, 3};
   return s;
 }
-struct WsLayout { long long o[WS_COUNT]; long long total; };
-inline WsLayout make_ws(long long T) {
+struct WsLayout { long long o[MAX_LAYERS + 1][WS_COUNT]; long long total; };
+inline WsLayout make_ws(int n_layers, long long T) {
   WsLayout w; long long off = 0;
-  for (int i = 0; i < WS_COUNT; ++i) { w.o[i] = off; off = align_up(off + (long long)ws_sizes()[i] * T, 64); }
+  for (int f = 0; f <= n_layers; ++f)
+    for (int i = 0; i < WS_COUNT; ++i) { w.o[f][i] = off; off = align_up(off + (long long)ws_sizes()[i] * T, 64); }
   w.total = off;
   return w;
 }
+
+// ---- side streams: weight-gradient work (dW GEMMs, bias column sums) forks off the data-gradient chain ----------
+// fork = record an event on the main stream, make a side stream wait for it, launch there; join = main waits for
+// every side stream.  Under CUDA-graph capture this becomes plain fork/join edges of the graph.  SGRL_SIDE=0 disables.
+struct Side {
+  static constexpr int N = 3;
+  cudaStream_t s[N]; cudaEvent_t fork_ev; cudaEvent_t join_ev[N];
+  bool made = false; int enabled = -1; int rr = 0; bool used[N];
+  int init() {
+    if (enabled < 0) { const char* e = getenv("SGRL_SIDE"); enabled = e ? atoi(e) : 1; }
+    if (!made && enabled) {
+      for (int i = 0; i < N; ++i) {
+        SGRL_CUDA(cudaStreamCreateWithFlags(&s[i], cudaStreamNonBlocking));
+        SGRL_CUDA(cudaEventCreateWithFlags(&join_ev[i], cudaEventDisableTiming));
+        used[i] = false;
+      }
+      SGRL_CUDA(cudaEventCreateWithFlags(&fork_ev, cudaEventDisableTiming));
+      made = true;
+    }
+    return 0;
+  }
+};
+extern Side g_side;
 
 struct NetCtx {
   int kind, L, nb, T;
@@ -52,14 +80,38 @@ struct NetCtx {
   float* Gr(long long off) const { return grads + off; }
   float* S(int id) const { return stash + st.gs[id]; }
   float* SL(int l, int id) const { return stash + st.ls[l][id]; }
-  float* W(int id) const { return ws + wl.o[id]; }
+  float* W(int f, int id) const { return ws + wl.o[f][id]; }
   int ng() const { return kind == ACTOR ? 17 : 20; }
   int ks() const { return D + ng(); }
 };
 
-inline int run_gemm(const NetCtx& c, const GemmP& g) {
-  if (c.use_tc && gemm_tc_eligible(g)) return gemm_tc(g, c.stream);
-  return gemm_simt(g, c.stream);
+inline int run_gemm(const NetCtx& c, const GemmP& g, cudaStream_t st = nullptr) {
+  if (!st) st = c.stream;
+  if (c.use_tc && gemm_tc_eligible(g)) return gemm_tc(g, st);
+  return gemm_simt(g, st);
+}
+// stream for the next piece of weight-gradient work: a side stream that has been made to wait for everything
+// enqueued on the main stream so far (or the main stream itself when side streams are off / profiling is on)
+inline int side_fork(const NetCtx& c, cudaStream_t* out) {
+  Side& sd = g_side;
+  if (!sd.enabled || g_prof.on) { *out = c.stream; return 0; }
+  const int i = sd.rr; sd.rr = (sd.rr + 1) % Side::N;
+  SGRL_CUDA(cudaEventRecord(sd.fork_ev, c.stream));
+  SGRL_CUDA(cudaStreamWaitEvent(sd.s[i], sd.fork_ev, 0));
+  sd.used[i] = true;
+  *out = sd.s[i];
+  return 0;
+}
+inline int side_join(const NetCtx& c) {
+  Side& sd = g_side;
+  if (!sd.enabled) return 0;
+  for (int i = 0; i < Side::N; ++i) {
+    if (!sd.used[i]) continue;
+    SGRL_CUDA(cudaEventRecord(sd.join_ev[i], sd.s[i]));
+    SGRL_CUDA(cudaStreamWaitEvent(c.stream, sd.join_ev[i], 0));
+    sd.used[i] = false;
+  }
+  return 0;
 }
 
 // Y[M,N] = X[M,K] W^T (+b): X is stash-like, W/b parameters
@@ -96,15 +148,16 @@ inline GemmP wgrad(const NetCtx& c, const float* dY, int lddy, const float* X, i
   g.splitk = pick_splitk(Nw, Kw, M, c.nb);
   return g;
 }
-inline int colsum(const NetCtx& c, const float* X, int ldx, long long g_off, int M, int N, float alpha = 1.f) {
+inline int colsum(const NetCtx& c, const float* X, int ldx, long long g_off, int M, int N, float alpha, cudaStream_t st) {
   int gy = ceil_div(M, 64); if (gy > 32) gy = 32; if (gy < 1) gy = 1;
-  launch_k(colsum_kernel, dim3(ceil_div(N, 32), gy, c.nb), 256, 0, c.stream, X, ldx, c.zsW, c.Gr(g_off), c.zsG, M, N, alpha);
+  launch_k(colsum_kernel, dim3(ceil_div(N, 32), gy, c.nb), 256, 0, st, X, ldx, c.zsW, c.Gr(g_off), c.zsG, M, N, alpha);
   SGRL_LAUNCH_OK();
   return 0;
 }
-inline int block_copy(const NetCtx& c, float* dst, int ldd, long long zsD, const float* src, int lds, long long zsSrc, int M, int N, int add) {
+inline int block_copy(const NetCtx& c, float* dst, int ldd, long long zsD, const float* src, int lds, long long zsSrc, int M, int N, int add,
+                      const float* src2 = nullptr, int lds2 = 0, long long zsSrc2 = 0) {
   int gx = ceil_div((long long)M * N, 256); if (gx > 4 * NUM_SMS) gx = 4 * NUM_SMS; if (gx < 1) gx = 1;
-  launch_k(block_copy_kernel, dim3(gx, c.nb), 256, 0, c.stream, dst, ldd, zsD, src, lds, zsSrc, M, N, add);
+  launch_k(block_copy_kernel, dim3(gx, c.nb), 256, 0, c.stream, dst, ldd, zsD, src, lds, zsSrc, src2, lds2, zsSrc2, M, N, add);
   SGRL_LAUNCH_OK();
   return 0;
 }
@@ -130,8 +183,8 @@ inline int rowdiv_bwd(const NetCtx& c, float* dy, int lddy, const float* y, int 
   SGRL_LAUNCH_OK();
   return 0;
 }
-inline int zero_ws(const NetCtx& c, int id) {
-  for (int z = 0; z < c.nb; ++z) SGRL_CUDA(cudaMemsetAsync(c.W(id) + z * c.zsW, 0, sizeof(float) * ws_sizes()[id] * (size_t)c.T, c.stream));
+inline int zero_ws(const NetCtx& c, int f, int id) {
+  for (int z = 0; z < c.nb; ++z) SGRL_CUDA(cudaMemsetAsync(c.W(f, id) + z * c.zsW, 0, sizeof(float) * ws_sizes()[id] * (size_t)c.T, c.stream));
   return 0;
 }
 
@@ -249,6 +302,8 @@ inline int net_forward(const NetCtx& c, const float* obs, long long zsObs, const
 // instance stride zsDo.  need_wgrad=0 skips parameter gradients (actor step through
 // critic1: only d/d(action) is needed, agent.py:167).  dact (critic only, nullable)
 // receives d/d(action) (T x 3), overwritten.
+// The data-gradient chain runs on c.stream; every dW GEMM / bias column sum forks to a side
+// stream (side_fork) right after the dY it consumes has been produced.
 // ======================================================================================
 inline int net_backward(const NetCtx& c, const float* dOut, long long zsDo, int need_wgrad, float* dact, long long zsDact) {
   const int T = c.T, T3 = 3 * c.T, ng = c.ng(), KS = c.ks();
@@ -257,217 +312,186 @@ inline int net_backward(const NetCtx& c, const float* dOut, long long zsDo, int 
   const long long zS = c.zsS, zW = c.zsW;
   const bool wg = need_wgrad != 0;
   SGRL_CHECK(!wg || c.grads != nullptr, "backward with need_wgrad requires a gradient arena");
+  SGRL_TRY(g_side.init());
   GemmP g;
-  SGRL_TRY(zero_ws(c, W_DF1));   // used as dF of the head block first
-  float* dFh = c.W(W_DF1);
+  int f = c.L, fin = c.L;                               // frame written by this stage / frame holding the incoming dVg, dh
+  auto W = [&](int id) { return c.W(f, id); };
+  auto Wn = [&](int id) { return c.W(fin, id); };
+  // dW[Nw,Kw] += dY^T X (+ db[Nw] += alpha * colsum(dY)) on a side stream
+  auto side_w = [&](const float* dY, int lddy, const float* X, int ldx, long long zsX, long long dw_off, int ldw, int M, int Nw, int Kw,
+                    long long db_off = -1, float alpha = 1.f) -> int {
+    if (!wg) return 0;
+    cudaStream_t ss;
+    SGRL_TRY(side_fork(c, &ss));
+    GemmP w = wgrad(c, dY, lddy, X, ldx, zsX, dw_off, ldw, M, Nw, Kw);
+    w.alpha = alpha;
+    SGRL_TRY(run_gemm(c, w, ss));
+    if (db_off >= 0) SGRL_TRY(colsum(c, dY, lddy, db_off, M, Nw, alpha, ss));
+    return 0;
+  };
+
+  // ---------------------------------------------------------------- heads + final norm (frame L)
+  SGRL_TRY(zero_ws(c, f, W_DF1));   // dF of the head block
+  float* dFh = W(W_DF1);
   if (c.kind == CRITIC) {
-    SGRL_TRY(block_copy(c, c.W(W_DQ), 1, zW, dOut, 1, zsDo, T, 1, 0));
-    SGRL_TRY(rowdiv_bwd(c, c.W(W_DQ), 1, c.S(T_OUT), 1, c.S(T_FH), dFh, 1, 1.f, 0));
-    g = dgrad(c, c.W(W_DQ), 1, Y.gp[G_DNG_W], 256, c.W(W_DUH), 256, T, 1, 256);
+    SGRL_TRY(block_copy(c, W(W_DQ), 1, zW, dOut, 1, zsDo, T, 1, 0));
+    SGRL_TRY(rowdiv_bwd(c, W(W_DQ), 1, c.S(T_OUT), 1, c.S(T_FH), dFh, 1, 1.f, 0));
+    SGRL_TRY(side_w(W(W_DQ), 1, c.S(T_UH), 256, zS, Y.gp[G_DNG_W], 256, T, 1, 256, Y.gp[G_DNG_B]));
+    g = dgrad(c, W(W_DQ), 1, Y.gp[G_DNG_W], 256, W(W_DUH), 256, T, 1, 256);
     SGRL_TRY(run_gemm(c, g));
-    if (wg) {
-      SGRL_TRY(run_gemm(c, wgrad(c, c.W(W_DQ), 1, c.S(T_UH), 256, zS, Y.gp[G_DNG_W], 256, T, 1, 256)));
-      SGRL_TRY(colsum(c, c.W(W_DQ), 1, Y.gp[G_DNG_B], T, 1));
-    }
   } else {
-    launch_k(actor_out_bwd_kernel, dim3(grid_for_warps(T) > 2 * NUM_SMS ? 2 * NUM_SMS : grid_for_warps(T), c.nb), 256, 0, st, dOut, zsDo, c.S(T_OUT), c.S(T_RH), c.S(T_V0), zS, c.P(Y.gp[G_DG_W]), c.zsP, c.W(W_DR), zW,
-        wg ? c.Gr(Y.gp[G_DG_W]) : c.W(W_DQ) /*discarded*/, wg ? c.zsG : zW, c.max_action, T);
+    launch_k(actor_out_bwd_kernel, dim3(grid_for_warps(T) > 2 * NUM_SMS ? 2 * NUM_SMS : grid_for_warps(T), c.nb), 256, 0, st, dOut, zsDo, c.S(T_OUT),
+             c.S(T_RH), c.S(T_V0), zS, c.P(Y.gp[G_DG_W]), c.zsP, W(W_DR), zW, wg ? c.Gr(Y.gp[G_DG_W]) : W(W_DQ) /*discarded*/, wg ? c.zsG : zW,
+             c.max_action, T);
     SGRL_LAUNCH_OK();
-    launch_k(matapply_bwd_kernel, dim3(grid_for_warps(T), c.nb), 256, 0, st, c.W(W_DR), c.S(T_ZH2), c.S(T_MH), c.S(T_FH), zS,
-                                                                       c.W(W_DZ3), c.W(W_DT4), dFh, zW, T);
+    launch_k(matapply_bwd_kernel, dim3(grid_for_warps(T), c.nb), 256, 0, st, W(W_DR), c.S(T_ZH2), c.S(T_MH), c.S(T_FH), zS, W(W_DZ3), W(W_DT4), dFh,
+             zW, T);
     SGRL_LAUNCH_OK();
-    if (wg) {
-      SGRL_TRY(run_gemm(c, wgrad(c, c.W(W_DT4), 1024, c.S(T_M1), 256, zS, Y.gp[G_H2M_W], 256, T, 1024, 256)));
-      SGRL_TRY(colsum(c, c.W(W_DT4), 1024, Y.gp[G_H2M_B], T, 1024));
-    }
-    g = dgrad(c, c.W(W_DT4), 1024, Y.gp[G_H2M_W], 256, c.W(W_DA), 256, T, 1024, 256);
+    SGRL_TRY(side_w(W(W_DT4), 1024, c.S(T_M1), 256, zS, Y.gp[G_H2M_W], 256, T, 1024, 256, Y.gp[G_H2M_B]));
+    g = dgrad(c, W(W_DT4), 1024, Y.gp[G_H2M_W], 256, W(W_DA), 256, T, 1024, 256);
     g.mask = c.S(T_M1); g.zsMask = zS; g.ldmask = 256;
     SGRL_TRY(run_gemm(c, g));
-    if (wg) {
-      SGRL_TRY(run_gemm(c, wgrad(c, c.W(W_DA), 256, c.S(T_UH), 256, zS, Y.gp[G_H1M_W], 256, T, 256, 256)));
-      SGRL_TRY(colsum(c, c.W(W_DA), 256, Y.gp[G_H1M_B], T, 256));
-    }
-    g = dgrad(c, c.W(W_DA), 256, Y.gp[G_H1M_W], 256, c.W(W_DUH), 256, T, 256, 256);
+    SGRL_TRY(side_w(W(W_DA), 256, c.S(T_UH), 256, zS, Y.gp[G_H1M_W], 256, T, 256, 256, Y.gp[G_H1M_B]));
+    g = dgrad(c, W(W_DA), 256, Y.gp[G_H1M_W], 256, W(W_DUH), 256, T, 256, 256);
     SGRL_TRY(run_gemm(c, g));
   }
   // u[:, :128] = linear2_g(relu(linear1_g(vec G)))
-  if (wg) {
-    SGRL_TRY(run_gemm(c, wgrad(c, c.W(W_DUH), 256, c.S(T_AH), 128, zS, Y.gp[G_H2G_W], 128, T, 128, 128)));
-    SGRL_TRY(colsum(c, c.W(W_DUH), 256, Y.gp[G_H2G_B], T, 128));
-  }
-  g = dgrad(c, c.W(W_DUH), 256, Y.gp[G_H2G_W], 128, c.W(W_DA), 128, T, 128, 128);
+  SGRL_TRY(side_w(W(W_DUH), 256, c.S(T_AH), 128, zS, Y.gp[G_H2G_W], 128, T, 128, 128, Y.gp[G_H2G_B]));
+  g = dgrad(c, W(W_DUH), 256, Y.gp[G_H2G_W], 128, W(W_DA2), 128, T, 128, 128);
   g.mask = c.S(T_AH); g.zsMask = zS; g.ldmask = 128;
   SGRL_TRY(run_gemm(c, g));
-  if (wg) {
-    SGRL_TRY(run_gemm(c, wgrad(c, c.W(W_DA), 128, c.S(T_GH), 1024, zS, Y.gp[G_H1G_W], 1024, T, 128, 1024)));
-    SGRL_TRY(colsum(c, c.W(W_DA), 128, Y.gp[G_H1G_B], T, 128));
-  }
-  g = dgrad(c, c.W(W_DA), 128, Y.gp[G_H1G_W], 1024, c.W(W_DG), 1024, T, 128, 1024);
+  SGRL_TRY(side_w(W(W_DA2), 128, c.S(T_GH), 1024, zS, Y.gp[G_H1G_W], 1024, T, 128, 1024, Y.gp[G_H1G_B]));
+  g = dgrad(c, W(W_DA2), 128, Y.gp[G_H1G_W], 1024, W(W_DG), 1024, T, 128, 1024);
   SGRL_TRY(run_gemm(c, g));
-  SGRL_TRY(inv_feature_bwd(c.W(W_DG), dFh, c.S(T_ZH), c.S(T_FH), c.W(W_DZ1), zS, zW, T, c.nb, st));
+  SGRL_TRY(inv_feature_bwd(W(W_DG), dFh, c.S(T_ZH), c.S(T_FH), W(W_DZ1), zS, zW, T, c.nb, st));
   // dVgF = dZh[:, :30] gg_proj[:, 8:] (+ dZh2[:, :30] g_proj[:, 8:])
-  g = dgrad(c, c.W(W_DZ1), 32, Y.gp[G_GG_W] + GN, D + GN, c.W(W_DVG), 128, T3, NPJ, 128);
+  g = dgrad(c, W(W_DZ1), 32, Y.gp[G_GG_W] + GN, D + GN, W(W_DVG), 128, T3, NPJ, 128);
   SGRL_TRY(run_gemm(c, g));
   if (c.kind == ACTOR) {
-    g = dgrad(c, c.W(W_DZ3), 32, Y.gp[G_GPH_W] + GN, D + GN, c.W(W_DVG), 128, T3, NPJ, 128); g.accumulate = 1;
+    g = dgrad(c, W(W_DZ3), 32, Y.gp[G_GPH_W] + GN, D + GN, W(W_DVG), 128, T3, NPJ, 128); g.accumulate = 1;
     SGRL_TRY(run_gemm(c, g));
   }
-  if (wg) {
-    SGRL_TRY(run_gemm(c, wgrad(c, c.W(W_DZ1), 32, c.S(T_V0), 8, zS, Y.gp[G_GG_W], D + GN, T3, NPJ, GN)));
-    SGRL_TRY(run_gemm(c, wgrad(c, c.W(W_DZ1), 32, c.S(T_VGF), 128, zS, Y.gp[G_GG_W] + GN, D + GN, T3, NPJ, 128)));
-    if (c.kind == ACTOR) {
-      SGRL_TRY(run_gemm(c, wgrad(c, c.W(W_DZ3), 32, c.S(T_V0), 8, zS, Y.gp[G_GPH_W], D + GN, T3, NPJ, GN)));
-      SGRL_TRY(run_gemm(c, wgrad(c, c.W(W_DZ3), 32, c.S(T_VGF), 128, zS, Y.gp[G_GPH_W] + GN, D + GN, T3, NPJ, 128)));
-    }
+  SGRL_TRY(side_w(W(W_DZ1), 32, c.S(T_V0), 8, zS, Y.gp[G_GG_W], D + GN, T3, NPJ, GN));
+  SGRL_TRY(side_w(W(W_DZ1), 32, c.S(T_VGF), 128, zS, Y.gp[G_GG_W] + GN, D + GN, T3, NPJ, 128));
+  if (c.kind == ACTOR) {
+    SGRL_TRY(side_w(W(W_DZ3), 32, c.S(T_V0), 8, zS, Y.gp[G_GPH_W], D + GN, T3, NPJ, GN));
+    SGRL_TRY(side_w(W(W_DZ3), 32, c.S(T_VGF), 128, zS, Y.gp[G_GPH_W] + GN, D + GN, T3, NPJ, 128));
   }
   // u[:, 128:] = linear2_ng(relu(linear1_ng([s0 | h])))
-  if (wg) {
-    SGRL_TRY(run_gemm(c, wgrad(c, c.W(W_DUH) + 128, 256, c.S(T_BH), 128, zS, Y.gp[G_H2NG_W], 128, T, 128, 128)));
-    SGRL_TRY(colsum(c, c.W(W_DUH) + 128, 256, Y.gp[G_H2NG_B], T, 128));
-  }
-  g = dgrad(c, c.W(W_DUH) + 128, 256, Y.gp[G_H2NG_W], 128, c.W(W_DA), 128, T, 128, 128);
+  SGRL_TRY(side_w(W(W_DUH) + 128, 256, c.S(T_BH), 128, zS, Y.gp[G_H2NG_W], 128, T, 128, 128, Y.gp[G_H2NG_B]));
+  g = dgrad(c, W(W_DUH) + 128, 256, Y.gp[G_H2NG_W], 128, W(W_DA3), 128, T, 128, 128);
   g.mask = c.S(T_BH); g.zsMask = zS; g.ldmask = 128;
   SGRL_TRY(run_gemm(c, g));
-  if (wg) {
-    SGRL_TRY(run_gemm(c, wgrad(c, c.W(W_DA), 128, c.S(T_SH), KS, zS, Y.gp[G_H1NG_W], KS, T, 128, KS)));
-    SGRL_TRY(colsum(c, c.W(W_DA), 128, Y.gp[G_H1NG_B], T, 128));
-  }
-  g = dgrad(c, c.W(W_DA), 128, Y.gp[G_H1NG_W], KS, c.W(W_DSH), KS, T, 128, KS);
+  SGRL_TRY(side_w(W(W_DA3), 128, c.S(T_SH), KS, zS, Y.gp[G_H1NG_W], KS, T, 128, KS, Y.gp[G_H1NG_B]));
+  g = dgrad(c, W(W_DA3), 128, Y.gp[G_H1NG_W], KS, W(W_DSH), KS, T, 128, KS);
   SGRL_TRY(run_gemm(c, g));
-  if (dact) SGRL_TRY(block_copy(c, dact, 3, zsDact, c.W(W_DSH) + 17, KS, zW, T, 3, 0));
+  if (dact) SGRL_TRY(block_copy(c, dact, 3, zsDact, W(W_DSH) + 17, KS, zW, T, 3, 0));
   // final LayerNorm
-  SGRL_TRY(layernorm_bwd(c, c.W(W_DSH) + ng, KS, nullptr, 0, c.S(T_HL), 128, c.S(T_STF), Y.gp[G_NORM_W], Y.gp[G_NORM_B], c.W(W_DH), 128, wg));
+  SGRL_TRY(layernorm_bwd(c, W(W_DSH) + ng, KS, nullptr, 0, c.S(T_HL), 128, c.S(T_STF), Y.gp[G_NORM_W], Y.gp[G_NORM_B], W(W_DH), 128, wg));
 
+  // ---------------------------------------------------------------- encoder layers (frame l reads frame l+1)
   for (int l = c.L - 1; l >= 0; --l) {
+    fin = l + 1; f = l;
     const long long* lp = Y.lp[l];
     float* Vg = c.SL(l, S_VGIN);
     float* ua = c.SL(l, S_UA);
     float* ub = c.SL(l, S_UB);
     float* T31 = c.SL(l, S_T31);
-    SGRL_TRY(zero_ws(c, W_DF1));
-    SGRL_TRY(zero_ws(c, W_DF2));
+    SGRL_TRY(zero_ws(c, f, W_DF1));
+    SGRL_TRY(zero_ws(c, f, W_DF2));
     // LN2 and f = linear2(relu(linear1(u')))/F2
-    SGRL_TRY(layernorm_bwd(c, c.W(W_DH), 128, nullptr, 0, c.SL(l, S_X2), 128, c.SL(l, S_ST2), lp[L_N2_W], lp[L_N2_B], c.W(W_DX), 128, wg));
-    SGRL_TRY(block_copy(c, c.W(W_DFF), 128, zW, c.W(W_DX), 128, zW, T, 128, 0));
-    SGRL_TRY(rowdiv_bwd(c, c.W(W_DFF), 128, c.SL(l, S_FF), 128, c.SL(l, S_F2), c.W(W_DF2), 128, 1.f, 0));
-    if (wg) {
-      SGRL_TRY(run_gemm(c, wgrad(c, c.W(W_DFF), 128, T31 + 256, 512, zS, lp[L_L2_W], 256, T, 128, 256)));
-      SGRL_TRY(colsum(c, c.W(W_DFF), 128, lp[L_L2_B], T, 128));
-    }
-    g = dgrad(c, c.W(W_DFF), 128, lp[L_L2_W], 256, c.W(W_DT31) + 256, 512, T, 128, 256);
+    SGRL_TRY(layernorm_bwd(c, Wn(W_DH), 128, nullptr, 0, c.SL(l, S_X2), 128, c.SL(l, S_ST2), lp[L_N2_W], lp[L_N2_B], W(W_DX), 128, wg));
+    SGRL_TRY(block_copy(c, W(W_DFF), 128, zW, W(W_DX), 128, zW, T, 128, 0));
+    SGRL_TRY(rowdiv_bwd(c, W(W_DFF), 128, c.SL(l, S_FF), 128, c.SL(l, S_F2), W(W_DF2), 128, 1.f, 0));
+    SGRL_TRY(side_w(W(W_DFF), 128, T31 + 256, 512, zS, lp[L_L2_W], 256, T, 128, 256, lp[L_L2_B]));
+    g = dgrad(c, W(W_DFF), 128, lp[L_L2_W], 256, W(W_DT31) + 256, 512, T, 128, 256);
     g.mask = T31 + 256; g.zsMask = zS; g.ldmask = 512;
     SGRL_TRY(run_gemm(c, g));
     // Vg' = Vg + dV + linear5([g_proj3(dV)|gd] . M)
-    g = dgrad(c, c.W(W_DVG), 128, lp[L_L5_W], 32, c.W(W_DR), 32, T3, 128, 32);
+    g = dgrad(c, Wn(W_DVG), 128, lp[L_L5_W], 32, W(W_DR), 32, T3, 128, 32);
     SGRL_TRY(run_gemm(c, g));
-    if (wg) SGRL_TRY(run_gemm(c, wgrad(c, c.W(W_DVG), 128, c.SL(l, S_R), 32, zS, lp[L_L5_W], 32, T3, 128, 32)));
-    launch_k(matapply_bwd_kernel, dim3(grid_for_warps(T), c.nb), 256, 0, st, c.W(W_DR), c.SL(l, S_Z3), c.SL(l, S_MM), c.SL(l, S_F2), zS,
-                                                                       c.W(W_DZ3), c.W(W_DT4), c.W(W_DF2), zW, T);
+    SGRL_TRY(side_w(Wn(W_DVG), 128, c.SL(l, S_R), 32, zS, lp[L_L5_W], 32, T3, 128, 32));
+    launch_k(matapply_bwd_kernel, dim3(grid_for_warps(T), c.nb), 256, 0, st, W(W_DR), c.SL(l, S_Z3), c.SL(l, S_MM), c.SL(l, S_F2), zS, W(W_DZ3),
+             W(W_DT4), W(W_DF2), zW, T);
     SGRL_LAUNCH_OK();
-    if (wg) {
-      SGRL_TRY(run_gemm(c, wgrad(c, c.W(W_DT4), 1024, T31, 512, zS, lp[L_L4_W], 256, T, 1024, 256)));
-      SGRL_TRY(colsum(c, c.W(W_DT4), 1024, lp[L_L4_B], T, 1024));
-    }
-    g = dgrad(c, c.W(W_DT4), 1024, lp[L_L4_W], 256, c.W(W_DT31), 512, T, 1024, 256);
+    SGRL_TRY(side_w(W(W_DT4), 1024, T31, 512, zS, lp[L_L4_W], 256, T, 1024, 256, lp[L_L4_B]));
+    g = dgrad(c, W(W_DT4), 1024, lp[L_L4_W], 256, W(W_DT31), 512, T, 1024, 256);
     g.mask = T31; g.zsMask = zS; g.ldmask = 512;
     SGRL_TRY(run_gemm(c, g));
     // [linear3 | linear1](u')
-    if (wg) {
-      SGRL_TRY(run_gemm(c, wgrad(c, c.W(W_DT31), 512, ub, 256, zS, lp[L_L3_W], 256, T, 512, 256)));
-      SGRL_TRY(colsum(c, c.W(W_DT31), 512, lp[L_L3_B], T, 512));
-    }
-    g = dgrad(c, c.W(W_DT31), 512, lp[L_L3_W], 256, c.W(W_DUB), 256, T, 512, 256);
+    SGRL_TRY(side_w(W(W_DT31), 512, ub, 256, zS, lp[L_L3_W], 256, T, 512, 256, lp[L_L3_B]));
+    g = dgrad(c, W(W_DT31), 512, lp[L_L3_W], 256, W(W_DUB), 256, T, 512, 256);
     SGRL_TRY(run_gemm(c, g));
     // u'[:, :128] = linear_g2(relu(linear_g1(vec G2)))
-    if (wg) {
-      SGRL_TRY(run_gemm(c, wgrad(c, c.W(W_DUB), 256, c.SL(l, S_A2), 256, zS, lp[L_FG2_W], 256, T, 128, 256)));
-      SGRL_TRY(colsum(c, c.W(W_DUB), 256, lp[L_FG2_B], T, 128));
-    }
-    g = dgrad(c, c.W(W_DUB), 256, lp[L_FG2_W], 256, c.W(W_DA), 256, T, 128, 256);
+    SGRL_TRY(side_w(W(W_DUB), 256, c.SL(l, S_A2), 256, zS, lp[L_FG2_W], 256, T, 128, 256, lp[L_FG2_B]));
+    g = dgrad(c, W(W_DUB), 256, lp[L_FG2_W], 256, W(W_DA), 256, T, 128, 256);
     g.mask = c.SL(l, S_A2); g.zsMask = zS; g.ldmask = 256;
     SGRL_TRY(run_gemm(c, g));
-    if (wg) {
-      SGRL_TRY(run_gemm(c, wgrad(c, c.W(W_DA), 256, c.SL(l, S_G2), 1024, zS, lp[L_FG1_W], 1024, T, 256, 1024)));
-      SGRL_TRY(colsum(c, c.W(W_DA), 256, lp[L_FG1_B], T, 256));
-    }
-    g = dgrad(c, c.W(W_DA), 256, lp[L_FG1_W], 1024, c.W(W_DG), 1024, T, 256, 1024);
+    SGRL_TRY(side_w(W(W_DA), 256, c.SL(l, S_G2), 1024, zS, lp[L_FG1_W], 1024, T, 256, 1024, lp[L_FG1_B]));
+    g = dgrad(c, W(W_DA), 256, lp[L_FG1_W], 1024, W(W_DG), 1024, T, 256, 1024);
     SGRL_TRY(run_gemm(c, g));
-    SGRL_TRY(inv_feature_bwd(c.W(W_DG), c.W(W_DF2), c.SL(l, S_Z2), c.SL(l, S_F2), c.W(W_DZ2), zS, zW, T, c.nb, st));
+    SGRL_TRY(inv_feature_bwd(W(W_DG), W(W_DF2), c.SL(l, S_Z2), c.SL(l, S_F2), W(W_DZ2), zS, zW, T, c.nb, st));
     // d(dV) = dVg' + dZ2[:, :30] g_proj2 + dZ3[:, :30] g_proj3
-    g = dgrad(c, c.W(W_DZ2), 32, lp[L_GP2], 128, c.W(W_DDV), 128, T3, NPJ, 128);
-    g.res1 = c.W(W_DVG); g.zsR1 = zW; g.ldr1 = 128;
+    g = dgrad(c, W(W_DZ2), 32, lp[L_GP2], 128, W(W_DDV), 128, T3, NPJ, 128);
+    g.res1 = Wn(W_DVG); g.zsR1 = zW; g.ldr1 = 128;
     SGRL_TRY(run_gemm(c, g));
-    g = dgrad(c, c.W(W_DZ3), 32, lp[L_GP3], 128, c.W(W_DDV), 128, T3, NPJ, 128); g.accumulate = 1;
+    g = dgrad(c, W(W_DZ3), 32, lp[L_GP3], 128, W(W_DDV), 128, T3, NPJ, 128); g.accumulate = 1;
     SGRL_TRY(run_gemm(c, g));
-    if (wg) {
-      SGRL_TRY(run_gemm(c, wgrad(c, c.W(W_DZ2), 32, c.SL(l, S_DV), 128, zS, lp[L_GP2], 128, T3, NPJ, 128)));
-      SGRL_TRY(run_gemm(c, wgrad(c, c.W(W_DZ3), 32, c.SL(l, S_DV), 128, zS, lp[L_GP3], 128, T3, NPJ, 128)));
-    }
+    SGRL_TRY(side_w(W(W_DZ2), 32, c.SL(l, S_DV), 128, zS, lp[L_GP2], 128, T3, NPJ, 128));
+    SGRL_TRY(side_w(W(W_DZ3), 32, c.SL(l, S_DV), 128, zS, lp[L_GP3], 128, T3, NPJ, 128));
     // dV = g_out(og)
-    if (wg) SGRL_TRY(run_gemm(c, wgrad(c, c.W(W_DDV), 128, c.SL(l, S_OG), 256, zS, lp[L_GO_W], 256, T3, 128, 256)));
-    g = dgrad(c, c.W(W_DDV), 128, lp[L_GO_W], 256, c.W(W_DOG), 256, T3, 128, 256);
+    SGRL_TRY(side_w(W(W_DDV), 128, c.SL(l, S_OG), 256, zS, lp[L_GO_W], 256, T3, 128, 256));
+    g = dgrad(c, W(W_DDV), 128, lp[L_GO_W], 256, W(W_DOG), 256, T3, 128, 256);
     SGRL_TRY(run_gemm(c, g));
     // LN1: dy = dx2 (residual of LN2) + du'[:, 128:]
-    SGRL_TRY(layernorm_bwd(c, c.W(W_DX), 128, c.W(W_DUB) + 128, 256, c.SL(l, S_X1), 128, c.SL(l, S_ST1), lp[L_N1_W], lp[L_N1_B], c.W(W_DH), 128, wg));
+    SGRL_TRY(layernorm_bwd(c, W(W_DX), 128, W(W_DUB) + 128, 256, c.SL(l, S_X1), 128, c.SL(l, S_ST1), lp[L_N1_W], lp[L_N1_B], W(W_DH1), 128, wg));
     // dh = ng_out(o)
-    if (wg) {
-      SGRL_TRY(run_gemm(c, wgrad(c, c.W(W_DH), 128, c.SL(l, S_O), 256, zS, lp[L_NGO_W], 256, T, 128, 256)));
-      SGRL_TRY(colsum(c, c.W(W_DH), 128, lp[L_NGO_B], T, 128));
-    }
-    g = dgrad(c, c.W(W_DH), 128, lp[L_NGO_W], 256, c.W(W_DO), 256, T, 128, 256);
+    SGRL_TRY(side_w(W(W_DH1), 128, c.SL(l, S_O), 256, zS, lp[L_NGO_W], 256, T, 128, 256, lp[L_NGO_B]));
+    g = dgrad(c, W(W_DH1), 128, lp[L_NGO_W], 256, W(W_DO), 256, T, 128, 256);
     SGRL_TRY(run_gemm(c, g));
-    SGRL_TRY(attention_bwd(c.SL(l, S_QKV), c.SL(l, S_VGP), c.S(T_GD), c.SL(l, S_P), zS, c.W(W_DO), c.W(W_DOG), c.W(W_DQKV), c.W(W_DVGP), zW,
+    SGRL_TRY(attention_bwd(c.SL(l, S_QKV), c.SL(l, S_VGP), c.S(T_GD), c.SL(l, S_P), zS, W(W_DO), W(W_DOG), W(W_DQKV), W(W_DVGP), zW,
                            (l == 0 && wg) ? c.Gr(Y.gp[G_REL_W]) : nullptr, c.zsG, c.gr, c.nb, st));
-    // vg = vg_proj(Vg): dVg(in) = dVg' + dvg vg_proj
-    if (wg) SGRL_TRY(run_gemm(c, wgrad(c, c.W(W_DVGP), 252, Vg, 128, zS, lp[L_VG_W], 128, T3, 252, 128)));
-    g = dgrad(c, c.W(W_DVGP), 252, lp[L_VG_W], 128, c.W(W_DVG), 128, T3, 252, 128); g.accumulate = 1;
+    // vg = vg_proj(Vg): dVg(in) = dVg' + dvg vg_proj   (out of place: this frame's dVg)
+    SGRL_TRY(side_w(W(W_DVGP), 252, Vg, 128, zS, lp[L_VG_W], 128, T3, 252, 128));
+    g = dgrad(c, W(W_DVGP), 252, lp[L_VG_W], 128, W(W_DVG), 128, T3, 252, 128);
+    g.res1 = Wn(W_DVG); g.zsR1 = zW; g.ldr1 = 128;
     SGRL_TRY(run_gemm(c, g));
     // q|k|v = (W u + b)/F1 (q also * scale)
-    SGRL_TRY(rowdiv_bwd(c, c.W(W_DQKV), 768, c.SL(l, S_QKV), 768, c.SL(l, S_F1), c.W(W_DF1), 768, QSCALE, 256));
-    if (wg) {
-      SGRL_TRY(run_gemm(c, wgrad(c, c.W(W_DQKV), 768, ua, 256, zS, lp[L_Q_W], 256, T, 768, 256)));
-      SGRL_TRY(colsum(c, c.W(W_DQKV), 768, lp[L_Q_B], T, 768));
-    }
-    g = dgrad(c, c.W(W_DQKV), 768, lp[L_Q_W], 256, c.W(W_DUA), 256, T, 768, 256);
+    SGRL_TRY(rowdiv_bwd(c, W(W_DQKV), 768, c.SL(l, S_QKV), 768, c.SL(l, S_F1), W(W_DF1), 768, QSCALE, 256));
+    SGRL_TRY(side_w(W(W_DQKV), 768, ua, 256, zS, lp[L_Q_W], 256, T, 768, 256, lp[L_Q_B]));
+    g = dgrad(c, W(W_DQKV), 768, lp[L_Q_W], 256, W(W_DUA), 256, T, 768, 256);
     SGRL_TRY(run_gemm(c, g));
     // u[:, :128] = linear_g2(relu(linear_g1(vec G1)))
-    if (wg) {
-      SGRL_TRY(run_gemm(c, wgrad(c, c.W(W_DUA), 256, c.SL(l, S_A1), 256, zS, lp[L_G2_W], 256, T, 128, 256)));
-      SGRL_TRY(colsum(c, c.W(W_DUA), 256, lp[L_G2_B], T, 128));
-    }
-    g = dgrad(c, c.W(W_DUA), 256, lp[L_G2_W], 256, c.W(W_DA), 256, T, 128, 256);
+    SGRL_TRY(side_w(W(W_DUA), 256, c.SL(l, S_A1), 256, zS, lp[L_G2_W], 256, T, 128, 256, lp[L_G2_B]));
+    g = dgrad(c, W(W_DUA), 256, lp[L_G2_W], 256, W(W_DA2), 256, T, 128, 256);
     g.mask = c.SL(l, S_A1); g.zsMask = zS; g.ldmask = 256;
     SGRL_TRY(run_gemm(c, g));
-    if (wg) {
-      SGRL_TRY(run_gemm(c, wgrad(c, c.W(W_DA), 256, c.SL(l, S_G1), 1024, zS, lp[L_G1_W], 1024, T, 256, 1024)));
-      SGRL_TRY(colsum(c, c.W(W_DA), 256, lp[L_G1_B], T, 256));
-    }
-    g = dgrad(c, c.W(W_DA), 256, lp[L_G1_W], 1024, c.W(W_DG), 1024, T, 256, 1024);
+    SGRL_TRY(side_w(W(W_DA2), 256, c.SL(l, S_G1), 1024, zS, lp[L_G1_W], 1024, T, 256, 1024, lp[L_G1_B]));
+    g = dgrad(c, W(W_DA2), 256, lp[L_G1_W], 1024, W(W_DG), 1024, T, 256, 1024);
     SGRL_TRY(run_gemm(c, g));
-    SGRL_TRY(inv_feature_bwd(c.W(W_DG), c.W(W_DF1), c.SL(l, S_Z1), c.SL(l, S_F1), c.W(W_DZ1), zS, zW, T, c.nb, st));
-    if (wg) SGRL_TRY(run_gemm(c, wgrad(c, c.W(W_DZ1), 32, Vg, 128, zS, lp[L_GPROJ], 128, T3, NPJ, 128)));
-    g = dgrad(c, c.W(W_DZ1), 32, lp[L_GPROJ], 128, c.W(W_DVG), 128, T3, NPJ, 128); g.accumulate = 1;
+    SGRL_TRY(inv_feature_bwd(W(W_DG), W(W_DF1), c.SL(l, S_Z1), c.SL(l, S_F1), W(W_DZ1), zS, zW, T, c.nb, st));
+    SGRL_TRY(side_w(W(W_DZ1), 32, Vg, 128, zS, lp[L_GPROJ], 128, T3, NPJ, 128));
+    g = dgrad(c, W(W_DZ1), 32, lp[L_GPROJ], 128, W(W_DVG), 128, T3, NPJ, 128); g.accumulate = 1;
     SGRL_TRY(run_gemm(c, g));
     // dh(in) = dx1 + du[:, 128:]
-    SGRL_TRY(block_copy(c, c.W(W_DH), 128, zW, c.W(W_DUA) + 128, 256, zW, T, 128, 1));
+    SGRL_TRY(block_copy(c, W(W_DH), 128, zW, W(W_DH1), 128, zW, T, 128, 0, W(W_DUA) + 128, 256, zW));
   }
-  // embedding
+  // ---------------------------------------------------------------- embedding (reads frame 0)
+  f = 0; fin = 0;
   if (wg) {
-    g = wgrad(c, c.W(W_DVG), 128, c.S(T_V0), 8, zS, Y.gp[G_GENC_W], GN, T3, 128, GN); g.alpha = SQRT_D;
-    SGRL_TRY(run_gemm(c, g));
-    g = wgrad(c, c.W(W_DH), 128, c.S(T_SH), KS, zS, Y.gp[G_ENC_W], ng, T, 128, ng); g.alpha = SQRT_D;
-    SGRL_TRY(run_gemm(c, g));
-    SGRL_TRY(colsum(c, c.W(W_DH), 128, Y.gp[G_ENC_B], T, 128, SQRT_D));
+    SGRL_TRY(side_w(W(W_DVG), 128, c.S(T_V0), 8, zS, Y.gp[G_GENC_W], GN, T3, 128, GN, -1, SQRT_D));
+    SGRL_TRY(side_w(W(W_DH), 128, c.S(T_SH), KS, zS, Y.gp[G_ENC_W], ng, T, 128, ng, Y.gp[G_ENC_B], SQRT_D));
     int gx = ceil_div(T, 64); if (gx > NUM_SMS) gx = NUM_SMS; if (gx < 1) gx = 1;
-    launch_k(pos_embed_bwd_kernel, dim3(gx, c.nb), 128, 0, st, c.W(W_DH), 128, zW, c.rank3, c.Gr(Y.gp[G_POS0]), c.Gr(Y.gp[G_POS1]), c.Gr(Y.gp[G_POS2]), c.zsG, T);
+    launch_k(pos_embed_bwd_kernel, dim3(gx, c.nb), 128, 0, st, W(W_DH), 128, zW, c.rank3, c.Gr(Y.gp[G_POS0]), c.Gr(Y.gp[G_POS1]), c.Gr(Y.gp[G_POS2]), c.zsG, T);
     SGRL_LAUNCH_OK();
   }
   if (dact) {   // + sqrt(128) * dh0 . encoder.weight[:, 17:20]
     SGRL_CHECK(c.kind == CRITIC, "d/d(action) only exists for critics");
-    g = dgrad(c, c.W(W_DH), 128, Y.gp[G_ENC_W] + 17, ng, dact, 3, T, 128, 3);
+    g = dgrad(c, W(W_DH), 128, Y.gp[G_ENC_W] + 17, ng, dact, 3, T, 128, 3);
     g.zsC = zsDact; g.alpha = SQRT_D; g.accumulate = 1;
     SGRL_TRY(run_gemm(c, g));
   }
+  SGRL_TRY(side_join(c));
   return 0;
 }
 

@@ -10,6 +10,7 @@ long long g_launches = 0;
 Prof g_prof;
 long long* g_gemm_trace = nullptr;
 int g_pdl = -1;
+Side g_side;
 }
 using namespace sgrl;
 
@@ -67,7 +68,7 @@ int sgrl_arena_floats(int kind, int n_layers, int64_t* live_floats, int64_t* dea
 }
 
 int64_t sgrl_stash_floats(int kind, int n_layers, int64_t T, int keep) { return make_stash(kind, n_layers, T, keep).total; }
-int64_t sgrl_ws_floats(int64_t T) { return make_ws(T).total; }
+int64_t sgrl_ws_floats(int n_layers, int64_t T) { return make_ws(n_layers < 1 ? 1 : n_layers > MAX_LAYERS ? MAX_LAYERS : n_layers, T).total; }
 
 int sgrl_stash_info(int kind, int n_layers, int64_t T, int keep, const char* name, int layer, int64_t* offset, int* per_token) {
   StashLayout S = make_stash(kind, n_layers, T, keep);
@@ -98,7 +99,7 @@ static int make_ctx(const SgrlNetCall* k, cudaStream_t st, NetCtx& c) {
   c.st = make_stash(k->kind, k->n_layers, k->T, k->keep);
   SGRL_CHECK(k->stash_stride >= c.st.total, "stash_stride smaller than sgrl_stash_floats()");
   c.stash = k->stash; c.zsS = k->stash_stride;
-  c.wl = make_ws(k->T);
+  c.wl = make_ws(k->n_layers, k->T);
   c.ws = k->ws; c.zsW = k->ws_stride;
   c.gr.cu_limbs = k->cu_limbs; c.gr.rel_off = k->rel_off; c.gr.relation = k->relation; c.gr.G = k->G; c.gr.T = k->T;
   c.rank3 = k->rank3; c.max_action = k->max_action; c.use_tc = k->use_tc; c.stream = st;

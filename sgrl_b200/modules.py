@@ -269,16 +269,23 @@ class SetNetModule(nn.Module):
         k.max_action = self._max_action
         return k
 
+    def stash_floats(self, T: int, keep: bool, nb: int) -> int:
+        return nb * lib.sgrl_stash_floats(self._kind, self._n_layers, T, int(keep))
+
+    def ws_floats(self, T: int, nb: int) -> int:
+        return nb * lib.sgrl_ws_floats(self._n_layers, T)
+
     def forward_raw(self, tb: GraphTables, obs: torch.Tensor, act: Optional[torch.Tensor], keep: bool, nb: Optional[int] = None,
-                    out: Optional[torch.Tensor] = None, trusted_split: bool = False):
-        """Run nb nets on tokens obs (T,41) [act (T,3)].  Returns (out (nb,T,od), stash)."""
+                    out: Optional[torch.Tensor] = None, trusted_split: bool = False, stash: Optional[torch.Tensor] = None):
+        """Run nb nets on tokens obs (T,41) [act (T,3)].  Returns (out (nb,T,od), stash).  `out` / `stash` may be
+        caller-owned buffers (Agent.update's static plan); otherwise they are allocated here."""
         nb = self._nb if nb is None else nb
         od = 3 if self._kind == ACTOR else 1
         dev = self._arena.device
         if dev.type != "cuda":
             raise _lib.SgrlError("sgrl_b200 modules only run on CUDA devices (no CPU fallback)")
-        per = lib.sgrl_stash_floats(self._kind, self._n_layers, tb.T, int(keep))
-        stash = torch.empty(nb * per, dtype=torch.float32, device=dev)
+        if stash is None:
+            stash = torch.empty(self.stash_floats(tb.T, keep, nb), dtype=torch.float32, device=dev)
         if out is None:
             out = torch.empty(nb, tb.T, od, dtype=torch.float32, device=dev)
         k = self._call(tb, nb, int(keep), stash, split=self._split_for(tb.T, trusted_split))
@@ -286,11 +293,13 @@ class SetNetModule(nn.Module):
         return out, stash
 
     def backward_raw(self, tb: GraphTables, stash: torch.Tensor, dout: torch.Tensor, nb: int, grads: Optional[torch.Tensor],
-                     want_dact: bool, trusted_split: bool = False):
+                     want_dact: bool, trusted_split: bool = False, ws: Optional[torch.Tensor] = None, dact: Optional[torch.Tensor] = None):
         """dout (nb,T,od).  Accumulates parameter gradients into `grads` (None: data-only)."""
         dev = self._arena.device
-        ws = torch.empty(nb * lib.sgrl_ws_floats(tb.T), dtype=torch.float32, device=dev)
-        dact = torch.empty(nb, tb.T, 3, dtype=torch.float32, device=dev) if want_dact else None
+        if ws is None:
+            ws = torch.empty(self.ws_floats(tb.T, nb), dtype=torch.float32, device=dev)
+        if want_dact and dact is None:
+            dact = torch.empty(nb, tb.T, 3, dtype=torch.float32, device=dev)
         od = 3 if self._kind == ACTOR else 1
         k = self._call(tb, nb, 1, stash, grads=grads, ws=ws, split=self._split_for(tb.T, trusted_split))
         check(lib.sgrl_set_backward(C.byref(k), ptr(dout), tb.T * od, 1 if grads is not None else 0, ptr(dact), tb.T * 3, stream()),

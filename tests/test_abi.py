@@ -61,7 +61,7 @@ def test_error_reporting_without_gpu():
     assert _lib.lib.sgrl_param_count(7, 3) < 0
     assert b"bad kind" in _lib.lib.sgrl_last_error()
     assert _lib.lib.sgrl_stash_floats(0, 3, 900, 1) > _lib.lib.sgrl_stash_floats(0, 3, 900, 0) > 0
-    assert _lib.lib.sgrl_ws_floats(900) > 0
+    assert _lib.lib.sgrl_ws_floats(3, 900) > 0
 
 
 def test_modules_build_on_cpu_with_reference_state_dict_keys():

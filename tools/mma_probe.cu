@@ -162,12 +162,29 @@ __global__ void __launch_bounds__(320, 1) probe2(int nblocks, int flags, const f
       const uint64_t bh = b0 + (uint64_t)((stage * STAGE) >> 4), bl = bh + (uint64_t)((BN * 128) >> 4);
       const uint32_t ah = tb + 256 + t * 64, al = ah + 32;
       if (elect_one()) {
+        const uint32_t am = tb + (g % 3) * BN, alo = tb + 3 * BN, f0 = (g >= 3) ? 1u : 0u, l0 = (g > 0) ? 1u : 0u;
+        if ((flags & 192) == 0) {            // order 0: hh x4, then (lo,hi),(hi,lo) interleaved per k
 #pragma unroll
-        for (int k = 0; k < 4; ++k) mma_ts(tb + (g % 3) * BN, ah + 8 * k, bh + 2 * k, idesc, (g >= 3 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < 4; ++k) mma_ts(am, ah + 8 * k, bh + 2 * k, idesc, k > 0 ? 1u : f0);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          mma_ts(tb + 3 * BN, al + 8 * k, bh + 2 * k, idesc, (g > 0 || k > 0) ? 1u : 0u);
-          mma_ts(tb + 3 * BN, ah + 8 * k, bl + 2 * k, idesc, 1u);
+          for (int k = 0; k < 4; ++k) {
+            mma_ts(alo, al + 8 * k, bh + 2 * k, idesc, k > 0 ? 1u : l0);
+            mma_ts(alo, ah + 8 * k, bl + 2 * k, idesc, 1u);
+          }
+        } else if (flags & 64) {             // order 1: hh x4, (lo,hi) x4, (hi,lo) x4
+#pragma unroll
+          for (int k = 0; k < 4; ++k) mma_ts(am, ah + 8 * k, bh + 2 * k, idesc, k > 0 ? 1u : f0);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) mma_ts(alo, al + 8 * k, bh + 2 * k, idesc, k > 0 ? 1u : l0);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) mma_ts(alo, ah + 8 * k, bl + 2 * k, idesc, 1u);
+        } else {                             // order 2: per k: (hi,hi), (lo,hi), (hi,lo)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            mma_ts(am, ah + 8 * k, bh + 2 * k, idesc, k > 0 ? 1u : f0);
+            mma_ts(alo, al + 8 * k, bh + 2 * k, idesc, k > 0 ? 1u : l0);
+            mma_ts(alo, ah + 8 * k, bl + 2 * k, idesc, 1u);
+          }
         }
         if (flags & 2) {
           asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bsink)) : "memory");
@@ -257,7 +274,7 @@ int main() {
     run<64, 1, 1>(ng, grid, d); run<128, 1, 1>(ng, grid, d);
   }
   for (int grid : {1, 148})
-    for (int flags : {0, 1, 2, 3, 4, 16, 32, 8, 7, 15}) { run2<64>(ng, flags, grid, gsrc, d); }
-  for (int flags : {0, 3, 4, 8, 15}) run2<128>(ng, flags, 148, gsrc, d);
+    for (int flags : {0, 64, 128, 15, 15 + 64, 15 + 128}) { run2<64>(ng, flags, grid, gsrc, d); }
+  for (int flags : {0, 64, 128, 15, 15 + 64, 15 + 128}) run2<128>(ng, flags, 148, gsrc, d);
   return 0;
 }
