@@ -264,10 +264,11 @@ def run_ours(a):
     _lib.lib.sgrl_profile(0)
     agent.use_graphs = graphs_on
     step_ms = total_ms / K
+    ser_ms = max(sum(v[0] for v in prof.values()), 1e-9)     # the timing pass runs the launches one by one (no overlap)
     classes = {}
     for name, (ms, work, cnt) in prof.items():
         if cnt:
-            classes[name] = {"ms_per_step": ms / 2, "launches_per_step": cnt / 2, "share_of_step": (ms / 2) / step_ms}
+            classes[name] = {"ms_per_step": ms / 2, "launches_per_step": cnt / 2, "share_of_serialized": ms / ser_ms}
             if name.startswith("gemm"):
                 classes[name]["tflops"] = work / (ms * 1e-3) / 1e12
             else:
@@ -324,7 +325,11 @@ def run_ours(a):
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # captured graphs hold NCCL work; tearing the process group down underneath them can hang at exit (seen at N=2):
+        # synchronise, meet at a barrier, flush and leave without running destructors
+        barrier()
+        sys.stdout.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":

@@ -343,6 +343,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
   const int kb0 = blockIdx.y * per, kb1 = min(nkb, kb0 + per);
   const int nloc = kb1 - kb0;
   const int zA = p.zsA ? z : 0, zB = p.zsB ? z : 0;
+  // accumulators in rotation: at most ~12 k-blocks (48 truncating hi*hi accumulations) per accumulator — the level the
+  // K = 1024 projections run at with all NMAIN — so short-K tiles use (and later read back from TMEM) fewer of them
+  const int nrot = min(Cfg::NMAIN, (nloc + 11) / 12);
   long long* dbg = (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && z == 0) ? p.dbg : nullptr;
 #define TC_STAMP(slot) do { if (dbg) dbg[slot] = clock64(); } while (0)
   if (tid == 0) TC_STAMP(0);
@@ -430,8 +433,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
             const int s = u % STAGES, t = u % TA;
             const uint32_t b_hi = bdesc0 + (uint32_t)(s * (STAGE_BYTES >> 4)), b_lo = b_hi + (B_BYTES >> 4);
             const uint32_t a_hi = tab + t * 64, a_lo = a_hi + 32;
-            const uint32_t acc_hi = tb + (u % NMAIN) * BN;                 // main accumulators rotate per k-block (see TcCfg)
-            const uint32_t first_hi = (it > 0 || u >= NMAIN) ? 1u : 0u, first_lo = (it > 0 || u > 0) ? 1u : 0u;
+            const int ai = nrot == NMAIN ? (u % NMAIN) : (nrot == 1 ? 0 : (u & 1));   // UNR is even: (i0 + u) & 1 == u & 1
+            const uint32_t acc_hi = tb + ai * BN;                          // main accumulators rotate per k-block (see TcCfg)
+            const uint32_t first_hi = (it > 0 || u >= nrot) ? 1u : 0u, first_lo = (it > 0 || u > 0) ? 1u : 0u;
             if (elect_one()) {
 #pragma unroll
               for (int k = 0; k < TC_BK / 8; ++k)
@@ -537,7 +541,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
         else if (p.res1 && !p.rowdiv && !p.mask && p.colscale_n == 0 && !p.relu && !p.bias) ekind = 3;
         else ekind = 6;
       }
-      const int nused = min(NMAIN, nloc);      // main accumulators that received at least one k-block
+      const int nused = min(nrot, nloc);       // main accumulators that received at least one k-block
       const uint32_t arow = tmem_base + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
       for (int c0 = hf * (BN / 2); c0 < (hf + 1) * (BN / 2); c0 += 32) {

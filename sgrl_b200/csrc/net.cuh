@@ -43,22 +43,35 @@ inline WsLayout make_ws(int n_layers, long long T) {
 // ---- side streams: weight-gradient work (dW GEMMs, bias column sums) forks off the data-gradient chain ----------
 // fork = record an event on the main stream, make a side stream wait for it, launch there; join = main waits for
 // every side stream.  Under CUDA-graph capture this becomes plain fork/join edges of the graph.  SGRL_SIDE=0 disables.
-struct Side {
-  static constexpr int N = 3;
+struct SideSet {
+  static constexpr int N = 4;              // lane 0: independent branch of the dependency chain; lanes 1..3: dW / bias-gradient work
   cudaStream_t s[N]; cudaEvent_t fork_ev; cudaEvent_t join_ev[N];
-  bool made = false; int enabled = -1; int rr = 0; bool used[N];
+  bool used[N]; int rr; cudaStream_t owner;
+};
+struct Side {
+  static constexpr int NSETS = 6;          // one set per distinct main stream seen (main, the agent's two forward streams, a capture stream, ...)
+  SideSet set[NSETS];
+  bool made = false; int enabled = -1; int nowners = 0;
   int init() {
     if (enabled < 0) { const char* e = getenv("SGRL_SIDE"); enabled = e ? atoi(e) : 1; }
-    if (!made && enabled) {
-      for (int i = 0; i < N; ++i) {
-        SGRL_CUDA(cudaStreamCreateWithFlags(&s[i], cudaStreamNonBlocking));
-        SGRL_CUDA(cudaEventCreateWithFlags(&join_ev[i], cudaEventDisableTiming));
-        used[i] = false;
+    if (!made && enabled) {              // everything is created up front: nothing but event record/wait happens later (capture-safe)
+      for (int k = 0; k < NSETS; ++k) {
+        for (int i = 0; i < SideSet::N; ++i) {
+          SGRL_CUDA(cudaStreamCreateWithFlags(&set[k].s[i], cudaStreamNonBlocking));
+          SGRL_CUDA(cudaEventCreateWithFlags(&set[k].join_ev[i], cudaEventDisableTiming));
+          set[k].used[i] = false;
+        }
+        SGRL_CUDA(cudaEventCreateWithFlags(&set[k].fork_ev, cudaEventDisableTiming));
+        set[k].rr = 0; set[k].owner = nullptr;
       }
-      SGRL_CUDA(cudaEventCreateWithFlags(&fork_ev, cudaEventDisableTiming));
       made = true;
     }
     return 0;
+  }
+  SideSet& of(cudaStream_t main) {
+    for (int k = 0; k < nowners; ++k) if (set[k].owner == main) return set[k];
+    if (nowners < NSETS) { set[nowners].owner = main; return set[nowners++]; }
+    return set[(reinterpret_cast<uintptr_t>(main) >> 6) % NSETS];      // more mains than sets: share (only costs overlap)
   }
 };
 extern Side g_side;
@@ -92,24 +105,31 @@ inline int run_gemm(const NetCtx& c, const GemmP& g, cudaStream_t st = nullptr) 
 }
 // stream for the next piece of weight-gradient work: a side stream that has been made to wait for everything
 // enqueued on the main stream so far (or the main stream itself when side streams are off / profiling is on)
-inline int side_fork(const NetCtx& c, cudaStream_t* out) {
+// `from`: the stream whose work so far the forked stream must wait for (default: the main stream)
+inline int side_fork(const NetCtx& c, cudaStream_t* out, int lane = -1, cudaStream_t from = nullptr) {
   Side& sd = g_side;
   if (!sd.enabled || g_prof.on) { *out = c.stream; return 0; }
-  const int i = sd.rr; sd.rr = (sd.rr + 1) % Side::N;
-  SGRL_CUDA(cudaEventRecord(sd.fork_ev, c.stream));
-  SGRL_CUDA(cudaStreamWaitEvent(sd.s[i], sd.fork_ev, 0));
-  sd.used[i] = true;
-  *out = sd.s[i];
+  SideSet& ss = sd.of(c.stream);
+  int i = lane;
+  if (i < 0) { i = 1 + ss.rr; ss.rr = (ss.rr + 1) % (SideSet::N - 1); }
+  if (!from) from = c.stream;
+  if (from == ss.s[i]) { *out = from; return 0; }      // same queue: already ordered
+  SGRL_CUDA(cudaEventRecord(ss.fork_ev, from));
+  SGRL_CUDA(cudaStreamWaitEvent(ss.s[i], ss.fork_ev, 0));
+  ss.used[i] = true;
+  *out = ss.s[i];
   return 0;
 }
-inline int side_join(const NetCtx& c) {
+// lane < 0: every lane; else only that lane
+inline int side_join(const NetCtx& c, int lane = -1) {
   Side& sd = g_side;
-  if (!sd.enabled) return 0;
-  for (int i = 0; i < Side::N; ++i) {
-    if (!sd.used[i]) continue;
-    SGRL_CUDA(cudaEventRecord(sd.join_ev[i], sd.s[i]));
-    SGRL_CUDA(cudaStreamWaitEvent(c.stream, sd.join_ev[i], 0));
-    sd.used[i] = false;
+  if (!sd.enabled || g_prof.on) return 0;
+  SideSet& ss = sd.of(c.stream);
+  for (int i = 0; i < SideSet::N; ++i) {
+    if (!ss.used[i] || (lane >= 0 && i != lane)) continue;
+    SGRL_CUDA(cudaEventRecord(ss.join_ev[i], ss.s[i]));
+    SGRL_CUDA(cudaStreamWaitEvent(c.stream, ss.join_ev[i], 0));
+    ss.used[i] = false;
   }
   return 0;
 }
@@ -155,31 +175,36 @@ inline int colsum(const NetCtx& c, const float* X, int ldx, long long g_off, int
   return 0;
 }
 inline int block_copy(const NetCtx& c, float* dst, int ldd, long long zsD, const float* src, int lds, long long zsSrc, int M, int N, int add,
-                      const float* src2 = nullptr, int lds2 = 0, long long zsSrc2 = 0) {
+                      const float* src2 = nullptr, int lds2 = 0, long long zsSrc2 = 0, cudaStream_t st = nullptr) {
+  if (!st) st = c.stream;
   int gx = ceil_div((long long)M * N, 256); if (gx > 4 * NUM_SMS) gx = 4 * NUM_SMS; if (gx < 1) gx = 1;
-  launch_k(block_copy_kernel, dim3(gx, c.nb), 256, 0, c.stream, dst, ldd, zsD, src, lds, zsSrc, src2, lds2, zsSrc2, M, N, add);
+  launch_k(block_copy_kernel, dim3(gx, c.nb), 256, 0, st, dst, ldd, zsD, src, lds, zsSrc, src2, lds2, zsSrc2, M, N, add);
   SGRL_LAUNCH_OK();
   return 0;
 }
 inline int layernorm_fwd(const NetCtx& c, const float* a, int lda, const float* b, int ldb, long long g_off, long long b_off,
-                         float* x, float* y, int ldy, float* stats) {
+                         float* x, float* y, int ldy, float* stats, cudaStream_t st = nullptr) {
+  if (!st) st = c.stream;
   const int vf = host_vec_ok(a, lda, c.zsS) | (host_vec_ok(b, ldb, c.zsS) << 1) | (host_vec_ok(y, ldy, c.zsS) << 2);
-  launch_k(layernorm_fwd_kernel, dim3(grid_for_warps(c.T), c.nb), 256, 0, c.stream, a, lda, b, ldb, c.P(g_off), c.P(b_off), c.zsP, x, y, ldy,
+  launch_k(layernorm_fwd_kernel, dim3(grid_for_warps(c.T), c.nb), 256, 0, st, a, lda, b, ldb, c.P(g_off), c.P(b_off), c.zsP, x, y, ldy,
                                                                               nullptr, 0, stats, c.zsS, c.T, vf);
   SGRL_LAUNCH_OK();
   return 0;
 }
 inline int layernorm_bwd(const NetCtx& c, const float* dy1, int ld1, const float* dy2, int ld2, const float* x, int ldx,
-                         const float* stats, long long g_off, long long b_off, float* dx, int lddx, bool wg) {
+                         const float* stats, long long g_off, long long b_off, float* dx, int lddx, bool wg, cudaStream_t st = nullptr) {
+  if (!st) st = c.stream;
   int gx = grid_for_warps(c.T); if (gx > 2 * NUM_SMS) gx = 2 * NUM_SMS;
   const int vf = host_vec_ok(dy1, ld1, c.zsW) | (host_vec_ok(dy2, ld2, c.zsW) << 1) | (host_vec_ok(x, ldx, c.zsS) << 2) | (host_vec_ok(dx, lddx, c.zsW) << 3);
-  launch_k(layernorm_bwd_kernel, dim3(gx, c.nb), 256, 0, c.stream, dy1, ld1, dy2, ld2, x, ldx, stats, c.zsS, c.P(g_off), c.zsP, dx, lddx, c.zsW,
+  launch_k(layernorm_bwd_kernel, dim3(gx, c.nb), 256, 0, st, dy1, ld1, dy2, ld2, x, ldx, stats, c.zsS, c.P(g_off), c.zsP, dx, lddx, c.zsW,
                                                              wg ? c.Gr(g_off) : nullptr, wg ? c.Gr(b_off) : nullptr, c.zsG, c.T, vf);
   SGRL_LAUNCH_OK();
   return 0;
 }
-inline int rowdiv_bwd(const NetCtx& c, float* dy, int lddy, const float* y, int ldy, const float* Fn, float* dF, int N, float cs, int cs_n) {
-  launch_k(rowdiv_bwd_kernel, dim3(grid_for_warps(c.T), c.nb), 256, 0, c.stream, dy, lddy, c.zsW, y, ldy, Fn, c.zsS, dF, N, cs, cs_n, c.T);
+inline int rowdiv_bwd(const NetCtx& c, float* dy, int lddy, const float* y, int ldy, const float* Fn, float* dF, int N, float cs, int cs_n,
+                      cudaStream_t st = nullptr) {
+  if (!st) st = c.stream;
+  launch_k(rowdiv_bwd_kernel, dim3(grid_for_warps(c.T), c.nb), 256, 0, st, dy, lddy, c.zsW, y, ldy, Fn, c.zsS, dF, N, cs, cs_n, c.T);
   SGRL_LAUNCH_OK();
   return 0;
 }
@@ -201,6 +226,8 @@ inline int net_forward(const NetCtx& c, const float* obs, long long zsObs, const
   cudaStream_t st = c.stream;
   const long long zS = c.zsS;
   SGRL_CHECK(c.kind == ACTOR || act != nullptr, "critic forward needs actions");
+  SGRL_TRY(g_side.init());
+  cudaStream_t sb;                 // side stream of the independent branch of the moment (== st when side streams are off)
   {
     int gx = ceil_div(T, E_TOK); if (gx > 4 * NUM_SMS) gx = 4 * NUM_SMS;
     launch_k(embed_fwd_kernel, dim3(gx, c.nb), 128, 0, st, obs, zsObs, c.kind == CRITIC ? act : nullptr, zsAct, c.rank3,
@@ -220,21 +247,26 @@ inline int net_forward(const NetCtx& c, const float* obs, long long zsObs, const
     // -- attention block: invariant features of Vg -> u = [g-mlp | h]
     FeatFwdP f{}; f.Xg = Vg; f.zsXg = zS; f.gd = c.S(T_GD); f.zsGd = zS; f.P1 = c.P(lp[L_GPROJ]); f.zsP = c.zsP;
     f.Z = c.SL(l, S_Z1); f.G = c.SL(l, S_G1); f.Fn = c.SL(l, S_F1); f.zsAct = zS; f.T = T; f.nb = c.nb;
+    // branch: vg = vg_proj(Vg) only needs the layer input
+    SGRL_TRY(side_fork(c, &sb, 0));
+    GemmP g = lin(c, Vg, 128, zS, lp[L_VG_W], -1, c.SL(l, S_VGP), 252, zS, T3, 252, 128);
+    SGRL_TRY(run_gemm(c, g, sb));
     SGRL_TRY(inv_feature_fwd(f, st));
-    GemmP g = lin(c, c.SL(l, S_G1), 1024, zS, lp[L_G1_W], lp[L_G1_B], c.SL(l, S_A1), 256, zS, T, 256, 1024); g.relu = 1;
+    g = lin(c, c.SL(l, S_G1), 1024, zS, lp[L_G1_W], lp[L_G1_B], c.SL(l, S_A1), 256, zS, T, 256, 1024); g.relu = 1;
     SGRL_TRY(run_gemm(c, g));
     g = lin(c, c.SL(l, S_A1), 256, zS, lp[L_G2_W], lp[L_G2_B], ua, 256, zS, T, 128, 256);
     SGRL_TRY(run_gemm(c, g));
     g = lin(c, ua, 256, zS, lp[L_Q_W], lp[L_Q_B], c.SL(l, S_QKV), 768, zS, T, 768, 256);
     g.rowdiv = c.SL(l, S_F1); g.zsRow = zS; g.colscale = QSCALE; g.colscale_n = 256;
     SGRL_TRY(run_gemm(c, g));
-    g = lin(c, Vg, 128, zS, lp[L_VG_W], -1, c.SL(l, S_VGP), 252, zS, T3, 252, 128);
-    SGRL_TRY(run_gemm(c, g));
+    SGRL_TRY(side_join(c));
     SGRL_TRY(attention_fwd(c.SL(l, S_QKV), c.SL(l, S_VGP), c.S(T_GD), c.SL(l, S_O), c.SL(l, S_OG), c.SL(l, S_P), zS,
                            l == 0 ? c.P(Y.gp[G_REL_W]) : nullptr, l == 0 ? c.P(Y.gp[G_REL_B]) : nullptr, c.zsP, c.gr, c.nb, st));
+    // branch: scalar stream h = LN1(h + ng_out(o)) while the vector stream continues on the main stream
+    SGRL_TRY(side_fork(c, &sb, 0));
     g = lin(c, c.SL(l, S_O), 256, zS, lp[L_NGO_W], lp[L_NGO_B], c.SL(l, S_X1), 128, zS, T, 128, 256);
-    SGRL_TRY(run_gemm(c, g));
-    SGRL_TRY(layernorm_fwd(c, ua + 128, 256, c.SL(l, S_X1), 128, lp[L_N1_W], lp[L_N1_B], c.SL(l, S_X1), ub + 128, 256, c.SL(l, S_ST1)));
+    SGRL_TRY(run_gemm(c, g, sb));
+    SGRL_TRY(layernorm_fwd(c, ua + 128, 256, c.SL(l, S_X1), 128, lp[L_N1_W], lp[L_N1_B], c.SL(l, S_X1), ub + 128, 256, c.SL(l, S_ST1), sb));
     g = lin(c, c.SL(l, S_OG), 256, zS, lp[L_GO_W], -1, c.SL(l, S_DV), 128, zS, T3, 128, 256);
     SGRL_TRY(run_gemm(c, g));
     // -- feed-forward block: invariant features of dV
@@ -246,8 +278,15 @@ inline int net_forward(const NetCtx& c, const float* obs, long long zsObs, const
     SGRL_TRY(run_gemm(c, g));
     g = lin(c, c.SL(l, S_A2), 256, zS, lp[L_FG2_W], lp[L_FG2_B], ub, 256, zS, T, 128, 256);
     SGRL_TRY(run_gemm(c, g));
+    SGRL_TRY(side_join(c));
     g = lin(c, ub, 256, zS, lp[L_L3_W], lp[L_L3_B], c.SL(l, S_T31), 512, zS, T, 512, 256); g.relu = 1;   // [linear3 | linear1]
     SGRL_TRY(run_gemm(c, g));
+    // branch: h' = LN2(h + linear2(relu(linear1 u'))/F2) while M = linear4(..)/F2 -> matrix apply -> linear5 runs on the main stream
+    SGRL_TRY(side_fork(c, &sb, 0));
+    g = lin(c, c.SL(l, S_T31) + 256, 512, zS, lp[L_L2_W], lp[L_L2_B], c.SL(l, S_FF), 128, zS, T, 128, 256);
+    g.rowdiv = c.SL(l, S_F2); g.zsRow = zS;
+    SGRL_TRY(run_gemm(c, g, sb));
+    SGRL_TRY(layernorm_fwd(c, ub + 128, 256, c.SL(l, S_FF), 128, lp[L_N2_W], lp[L_N2_B], c.SL(l, S_X2), h_next, ld_hn, c.SL(l, S_ST2), sb));
     g = lin(c, c.SL(l, S_T31), 512, zS, lp[L_L4_W], lp[L_L4_B], c.SL(l, S_MM), 1024, zS, T, 1024, 256);
     g.rowdiv = c.SL(l, S_F2); g.zsRow = zS;
     SGRL_TRY(run_gemm(c, g));
@@ -256,10 +295,7 @@ inline int net_forward(const NetCtx& c, const float* obs, long long zsObs, const
     g = lin(c, c.SL(l, S_R), 32, zS, lp[L_L5_W], -1, Vg_next, 128, zS, T3, 128, 32);
     g.res1 = Vg; g.zsR1 = zS; g.ldr1 = 128; g.res2 = c.SL(l, S_DV); g.zsR2 = zS; g.ldr2 = 128;
     SGRL_TRY(run_gemm(c, g));
-    g = lin(c, c.SL(l, S_T31) + 256, 512, zS, lp[L_L2_W], lp[L_L2_B], c.SL(l, S_FF), 128, zS, T, 128, 256);
-    g.rowdiv = c.SL(l, S_F2); g.zsRow = zS;
-    SGRL_TRY(run_gemm(c, g));
-    SGRL_TRY(layernorm_fwd(c, ub + 128, 256, c.SL(l, S_FF), 128, lp[L_N2_W], lp[L_N2_B], c.SL(l, S_X2), h_next, ld_hn, c.SL(l, S_ST2)));
+    SGRL_TRY(side_join(c));
   }
   // final LayerNorm -> right part of SH = [s0 | h]
   SGRL_TRY(layernorm_fwd(c, c.S(T_HL), 128, nullptr, 0, Y.gp[G_NORM_W], Y.gp[G_NORM_B], nullptr, c.S(T_SH) + ng, KS, c.S(T_STF)));
@@ -319,10 +355,10 @@ inline int net_backward(const NetCtx& c, const float* dOut, long long zsDo, int 
   auto Wn = [&](int id) { return c.W(fin, id); };
   // dW[Nw,Kw] += dY^T X (+ db[Nw] += alpha * colsum(dY)) on a side stream
   auto side_w = [&](const float* dY, int lddy, const float* X, int ldx, long long zsX, long long dw_off, int ldw, int M, int Nw, int Kw,
-                    long long db_off = -1, float alpha = 1.f) -> int {
+                    long long db_off = -1, float alpha = 1.f, cudaStream_t from = nullptr) -> int {
     if (!wg) return 0;
     cudaStream_t ss;
-    SGRL_TRY(side_fork(c, &ss));
+    SGRL_TRY(side_fork(c, &ss, -1, from));
     GemmP w = wgrad(c, dY, lddy, X, ldx, zsX, dw_off, ldw, M, Nw, Kw);
     w.alpha = alpha;
     SGRL_TRY(run_gemm(c, w, ss));
@@ -399,15 +435,17 @@ inline int net_backward(const NetCtx& c, const float* dOut, long long zsDo, int 
     float* T31 = c.SL(l, S_T31);
     SGRL_TRY(zero_ws(c, f, W_DF1));
     SGRL_TRY(zero_ws(c, f, W_DF2));
-    // LN2 and f = linear2(relu(linear1(u')))/F2
-    SGRL_TRY(layernorm_bwd(c, Wn(W_DH), 128, nullptr, 0, c.SL(l, S_X2), 128, c.SL(l, S_ST2), lp[L_N2_W], lp[L_N2_B], W(W_DX), 128, wg));
-    SGRL_TRY(block_copy(c, W(W_DFF), 128, zW, W(W_DX), 128, zW, T, 128, 0));
-    SGRL_TRY(rowdiv_bwd(c, W(W_DFF), 128, c.SL(l, S_FF), 128, c.SL(l, S_F2), W(W_DF2), 128, 1.f, 0));
-    SGRL_TRY(side_w(W(W_DFF), 128, T31 + 256, 512, zS, lp[L_L2_W], 256, T, 128, 256, lp[L_L2_B]));
+    cudaStream_t sb;      // branch lane (== st when side streams are off: the program order below is a valid serial order)
+    // ---- branch (sb): LN2 and f = linear2(relu(linear1(u')))/F2
+    SGRL_TRY(side_fork(c, &sb, 0));
+    SGRL_TRY(layernorm_bwd(c, Wn(W_DH), 128, nullptr, 0, c.SL(l, S_X2), 128, c.SL(l, S_ST2), lp[L_N2_W], lp[L_N2_B], W(W_DX), 128, wg, sb));
+    SGRL_TRY(block_copy(c, W(W_DFF), 128, zW, W(W_DX), 128, zW, T, 128, 0, nullptr, 0, 0, sb));
+    SGRL_TRY(rowdiv_bwd(c, W(W_DFF), 128, c.SL(l, S_FF), 128, c.SL(l, S_F2), W(W_DF2), 128, 1.f, 0, sb));
+    SGRL_TRY(side_w(W(W_DFF), 128, T31 + 256, 512, zS, lp[L_L2_W], 256, T, 128, 256, lp[L_L2_B], 1.f, sb));
     g = dgrad(c, W(W_DFF), 128, lp[L_L2_W], 256, W(W_DT31) + 256, 512, T, 128, 256);
     g.mask = T31 + 256; g.zsMask = zS; g.ldmask = 512;
-    SGRL_TRY(run_gemm(c, g));
-    // Vg' = Vg + dV + linear5([g_proj3(dV)|gd] . M)
+    SGRL_TRY(run_gemm(c, g, sb));
+    // ---- main: Vg' = Vg + dV + linear5([g_proj3(dV)|gd] . M)
     g = dgrad(c, Wn(W_DVG), 128, lp[L_L5_W], 32, W(W_DR), 32, T3, 128, 32);
     SGRL_TRY(run_gemm(c, g));
     SGRL_TRY(side_w(Wn(W_DVG), 128, c.SL(l, S_R), 32, zS, lp[L_L5_W], 32, T3, 128, 32));
@@ -418,11 +456,18 @@ inline int net_backward(const NetCtx& c, const float* dOut, long long zsDo, int 
     g = dgrad(c, W(W_DT4), 1024, lp[L_L4_W], 256, W(W_DT31), 512, T, 1024, 256);
     g.mask = T31; g.zsMask = zS; g.ldmask = 512;
     SGRL_TRY(run_gemm(c, g));
+    SGRL_TRY(side_join(c, 0));
     // [linear3 | linear1](u')
     SGRL_TRY(side_w(W(W_DT31), 512, ub, 256, zS, lp[L_L3_W], 256, T, 512, 256, lp[L_L3_B]));
     g = dgrad(c, W(W_DT31), 512, lp[L_L3_W], 256, W(W_DUB), 256, T, 512, 256);
     SGRL_TRY(run_gemm(c, g));
-    // u'[:, :128] = linear_g2(relu(linear_g1(vec G2)))
+    // ---- branch (sb): LN1: dy = dx2 (residual of LN2) + du'[:, 128:];  dh = ng_out(o)
+    SGRL_TRY(side_fork(c, &sb, 0));
+    SGRL_TRY(layernorm_bwd(c, W(W_DX), 128, W(W_DUB) + 128, 256, c.SL(l, S_X1), 128, c.SL(l, S_ST1), lp[L_N1_W], lp[L_N1_B], W(W_DH1), 128, wg, sb));
+    SGRL_TRY(side_w(W(W_DH1), 128, c.SL(l, S_O), 256, zS, lp[L_NGO_W], 256, T, 128, 256, lp[L_NGO_B], 1.f, sb));
+    g = dgrad(c, W(W_DH1), 128, lp[L_NGO_W], 256, W(W_DO), 256, T, 128, 256);
+    SGRL_TRY(run_gemm(c, g, sb));
+    // ---- main: u'[:, :128] = linear_g2(relu(linear_g1(vec G2)))
     SGRL_TRY(side_w(W(W_DUB), 256, c.SL(l, S_A2), 256, zS, lp[L_FG2_W], 256, T, 128, 256, lp[L_FG2_B]));
     g = dgrad(c, W(W_DUB), 256, lp[L_FG2_W], 256, W(W_DA), 256, T, 128, 256);
     g.mask = c.SL(l, S_A2); g.zsMask = zS; g.ldmask = 256;
@@ -443,20 +488,16 @@ inline int net_backward(const NetCtx& c, const float* dOut, long long zsDo, int 
     SGRL_TRY(side_w(W(W_DDV), 128, c.SL(l, S_OG), 256, zS, lp[L_GO_W], 256, T3, 128, 256));
     g = dgrad(c, W(W_DDV), 128, lp[L_GO_W], 256, W(W_DOG), 256, T3, 128, 256);
     SGRL_TRY(run_gemm(c, g));
-    // LN1: dy = dx2 (residual of LN2) + du'[:, 128:]
-    SGRL_TRY(layernorm_bwd(c, W(W_DX), 128, W(W_DUB) + 128, 256, c.SL(l, S_X1), 128, c.SL(l, S_ST1), lp[L_N1_W], lp[L_N1_B], W(W_DH1), 128, wg));
-    // dh = ng_out(o)
-    SGRL_TRY(side_w(W(W_DH1), 128, c.SL(l, S_O), 256, zS, lp[L_NGO_W], 256, T, 128, 256, lp[L_NGO_B]));
-    g = dgrad(c, W(W_DH1), 128, lp[L_NGO_W], 256, W(W_DO), 256, T, 128, 256);
-    SGRL_TRY(run_gemm(c, g));
+    SGRL_TRY(side_join(c, 0));
     SGRL_TRY(attention_bwd(c.SL(l, S_QKV), c.SL(l, S_VGP), c.S(T_GD), c.SL(l, S_P), zS, W(W_DO), W(W_DOG), W(W_DQKV), W(W_DVGP), zW,
                            (l == 0 && wg) ? c.Gr(Y.gp[G_REL_W]) : nullptr, c.zsG, c.gr, c.nb, st));
-    // vg = vg_proj(Vg): dVg(in) = dVg' + dvg vg_proj   (out of place: this frame's dVg)
+    // ---- branch (sb): vg = vg_proj(Vg): dVg(in) = dVg' + dvg vg_proj   (out of place: this frame's dVg)
     SGRL_TRY(side_w(W(W_DVGP), 252, Vg, 128, zS, lp[L_VG_W], 128, T3, 252, 128));
+    SGRL_TRY(side_fork(c, &sb, 0));
     g = dgrad(c, W(W_DVGP), 252, lp[L_VG_W], 128, W(W_DVG), 128, T3, 252, 128);
     g.res1 = Wn(W_DVG); g.zsR1 = zW; g.ldr1 = 128;
-    SGRL_TRY(run_gemm(c, g));
-    // q|k|v = (W u + b)/F1 (q also * scale)
+    SGRL_TRY(run_gemm(c, g, sb));
+    // ---- main: q|k|v = (W u + b)/F1 (q also * scale)
     SGRL_TRY(rowdiv_bwd(c, W(W_DQKV), 768, c.SL(l, S_QKV), 768, c.SL(l, S_F1), W(W_DF1), 768, QSCALE, 256));
     SGRL_TRY(side_w(W(W_DQKV), 768, ua, 256, zS, lp[L_Q_W], 256, T, 768, 256, lp[L_Q_B]));
     g = dgrad(c, W(W_DQKV), 768, lp[L_Q_W], 256, W(W_DUA), 256, T, 768, 256);
@@ -471,6 +512,7 @@ inline int net_backward(const NetCtx& c, const float* dOut, long long zsDo, int 
     SGRL_TRY(run_gemm(c, g));
     SGRL_TRY(inv_feature_bwd(W(W_DG), W(W_DF1), c.SL(l, S_Z1), c.SL(l, S_F1), W(W_DZ1), zS, zW, T, c.nb, st));
     SGRL_TRY(side_w(W(W_DZ1), 32, Vg, 128, zS, lp[L_GPROJ], 128, T3, NPJ, 128));
+    SGRL_TRY(side_join(c, 0));
     g = dgrad(c, W(W_DZ1), 32, lp[L_GPROJ], 128, W(W_DVG), 128, T3, NPJ, 128); g.accumulate = 1;
     SGRL_TRY(run_gemm(c, g));
     // dh(in) = dx1 + du[:, 128:]
