@@ -135,11 +135,14 @@ int sgrl_split_tf32(const float* w, float* hi, float* lo, int64_t n, sgrl_stream
 int sgrl_td3_smooth_action(const float* pi_target, const float* noise, float* next_action, float noise_clip,
                            float max_action, int64_t n, sgrl_stream_t stream);
 /* target = r*scale + (1-done)*discount*min(tq1,tq2) broadcast over limbs; loss (1 float, accumulates)
- * = mse(q1,target)+mse(q2,target); dq1,dq2 = dloss/dq. tok_graph (T) maps token -> sample. */
+ * = mse(q1,target)+mse(q2,target); dq1,dq2 = dloss/dq. tok_graph (T) maps token -> sample.
+ * tok_weight (T, nullable): weight of each token in the loss for packed mixed-morphology batches
+ * (1/(#morphologies * tokens of the token's morphology): the mean over morphologies of the reference's
+ * per-morphology loss, src/trainer.py:245-250); NULL = 1/T (one morphology, exactly agent.py:146-148). */
 int sgrl_td3_critic_loss(const float* q1, const float* q2, const float* tq1, const float* tq2, const float* reward,
-                         const float* done, const int32_t* tok_graph, float* target, float* dq1, float* dq2,
-                         float* loss, float discount, float reward_scale, int T, sgrl_stream_t stream);
-int sgrl_td3_actor_loss(const float* q1, float* dq1, float* loss, int T, sgrl_stream_t stream);
+                         const float* done, const int32_t* tok_graph, const float* tok_weight, float* target, float* dq1,
+                         float* dq2, float* loss, float discount, float reward_scale, int T, sgrl_stream_t stream);
+int sgrl_td3_actor_loss(const float* q1, const float* tok_weight, float* dq1, float* loss, int T, sgrl_stream_t stream);
 
 /* ---- K6: optimizer (agent.py:150-156,170-178; common/functional.py:7-10) -------------------- */
 int sgrl_sumsq(const float* g, int64_t n, float* out /*accumulates*/, sgrl_stream_t stream);

@@ -95,14 +95,14 @@ class _UpdatePlan:
     """Static device state of Agent.update for one (morphology tables, batch size): input staging buffers, activation
     stashes, backward workspace, small result buffers, the three forward streams and the two captured graphs."""
 
-    def __init__(self, agent: "Agent", tb, B: int, width: int):
+    def __init__(self, agent: "Agent", tb):
         dev = agent.actor.full_arena.device
-        T = tb.T
-        n = width // 41
+        T, G = tb.T, tb.G
         f = lambda *shape: torch.empty(*shape, dtype=torch.float32, device=dev)
-        self.tb, self.B, self.agent = tb, B, agent
-        self.obs, self.nobs, self.act = f(B, width), f(B, width), f(B, 3 * n)
-        self.rew, self.done, self.noise = f(B), f(B), f(B, 3 * n)
+        self.tb, self.agent = tb, agent
+        # inputs as packed tokens: (T,41) observations / (T,3) actions are exactly the reference's (B, N*41) / (B, N*3) rows
+        self.obs, self.nobs, self.act = f(T, 41), f(T, 41), f(T, 3)
+        self.rew, self.done, self.noise = f(G), f(G), f(T, 3)
         self.a_t, self.next_action, self.pi = f(1, T, 3), f(T, 3), f(1, T, 3)
         self.tq, self.q, self.q1 = f(2, T, 1), f(2, T, 1), f(1, T, 1)
         self.dq, self.dq1, self.dact = f(2, T, 1), f(1, T, 1), f(1, T, 3)
@@ -119,19 +119,33 @@ class _UpdatePlan:
         self.graph_launches = {True: 0, False: 0}      # kernels of this library inside each captured graph
         self.eager_runs = {True: 0, False: 0}
 
-    def load(self, batch: Dict, noise, policy_noise: float):
-        """Stage one replay batch (host numpy / pinned or device tensors) into the static input buffers."""
-        for dst, key in ((self.obs, "obs"), (self.act, "action"), (self.nobs, "next_obs"), (self.rew, "reward"), (self.done, "done")):
-            src = batch[key]
-            if not torch.is_tensor(src):
-                src = torch.as_tensor(np.asarray(src), dtype=torch.float32)
-            dst.copy_(src.reshape(dst.shape), non_blocking=True)
-        if noise is None:
+    def load(self, batches, noises, policy_noise: float):
+        """Stage the replay batch of every morphology of the plan (host numpy / pinned or device tensors) into the static
+        input buffers.  batches[i]: dict obs (B_i, 41 N_i), action (B_i, 3 N_i), next_obs, reward (B_i,1), done (B_i,1)."""
+        parts = self.tb.parts
+        if len(batches) != len(parts):
+            raise ValueError(f"plan holds {len(parts)} morphologies, got {len(batches)} batches")
+        for i, ((t0, t1, g0, g1, n), batch) in enumerate(zip(parts, batches)):
+            B = g1 - g0
+            for dst, key, w in ((self.obs, "obs", 41), (self.act, "action", 3), (self.nobs, "next_obs", 41)):
+                src = batch[key]
+                if not torch.is_tensor(src):
+                    src = torch.as_tensor(np.asarray(src), dtype=torch.float32)
+                if tuple(src.shape) != (B, n * w):
+                    raise ValueError(f"{key}: expected {(B, n * w)} for this morphology, got {tuple(src.shape)}")
+                dst[t0:t1].view(B, n * w).copy_(src, non_blocking=True)
+            for dst, key in ((self.rew, "reward"), (self.done, "done")):
+                src = batch[key]
+                if not torch.is_tensor(src):
+                    src = torch.as_tensor(np.asarray(src), dtype=torch.float32)
+                dst[g0:g1].copy_(src.reshape(B), non_blocking=True)
+            nz = None if noises is None else noises[i]
+            if nz is not None:
+                if not torch.is_tensor(nz):
+                    nz = torch.as_tensor(np.asarray(nz), dtype=torch.float32)
+                self.noise[t0:t1].view(B, n * 3).copy_(nz.reshape(B, n * 3), non_blocking=True)
+        if noises is None:
             self.noise.normal_(0.0, policy_noise)                                     # agent.py:128
-        else:
-            if not torch.is_tensor(noise):
-                noise = torch.as_tensor(np.asarray(noise), dtype=torch.float32)
-            self.noise.copy_(noise.reshape(self.noise.shape), non_blocking=True)
 
     def replay(self, actor_step: bool):
         g = self.graphs.get(actor_step)
@@ -191,6 +205,7 @@ class Agent(nn.Module):
         self.lazy_stats = False      # True: reward statistics returned as 0-dim tensors (no host sync)
         self.use_graphs = os.environ.get("SGRL_GRAPHS", "1") != "0"   # replay Agent.update as a captured CUDA graph
         self._plans: Dict = {}
+        self._packed_tables: Dict = {}
         self._plan_sig = None
         self.graph_replayed_launches = 0     # library kernels executed through graph replays (sgrl_launch_count() sees captures only)
         self._loss = None
@@ -205,32 +220,49 @@ class Agent(nn.Module):
             import torch.distributed as dist
             dist.all_reduce(g, op=dist.ReduceOp.SUM)
 
-    def _plan(self, tb, B: int, width: int) -> "_UpdatePlan":
-        key = (id(tb), B)
+    def _plan(self, tb) -> "_UpdatePlan":
+        key = id(tb)
         plan = self._plans.get(key)
         if plan is None or plan.tb is not tb:
             if len(self._plans) >= 8:
                 self._plans.clear()
-            plan = _UpdatePlan(self, tb, B, width)
+            plan = _UpdatePlan(self, tb)
             self._plans[key] = plan
         return plan
 
     def update(self, data_batch: Dict, it: int, noise: Optional[torch.Tensor] = None):
-        """One TD3 update (src/agent.py:117-183).  data_batch: obs (B,41N), action (B,3N),
-        next_obs, reward (B,1), done (B,1) — torch tensors (any device) or numpy arrays.
-        `noise` (B,3N) optionally injects the target-policy noise (drawn on device otherwise).
+        """One TD3 update (src/agent.py:117-183) on the current morphology (change_morphology).  data_batch: obs (B,41N),
+        action (B,3N), next_obs, reward (B,1), done (B,1) — torch tensors (any device) or numpy arrays.  `noise` (B,3N)
+        optionally injects the target-policy noise (drawn on device otherwise).
 
         The batch is copied into a static per-(morphology, B) plan (inputs, activation stashes, workspaces), then
         the whole step runs as ONE captured CUDA graph (two graphs per plan: with and without the delayed actor
         step) — three forward chains on parallel streams, weight-gradient GEMMs on side streams (csrc/net.cuh).
         `self.use_graphs = False` runs the same sequence eagerly."""
+        B = int(data_batch["obs"].shape[0])
+        tb = self.actor._tables(B)
+        return self._run_update(tb, [data_batch], it, None if noise is None else [noise])
+
+    def update_packed(self, batches, it: int, noises=None):
+        """One TD3 update on a PACKED batch of several morphologies: batches = [(graph_dict, data_batch), ...].  The loss is
+        the mean over morphologies of the reference's per-morphology loss, so the gradient equals the average of the
+        gradients of the separate updates the reference performs one after the other (src/trainer.py:245-250) at the same
+        parameters; the limb-tokens of all morphologies go through every kernel together."""
+        from .modules import make_packed_tables
+        key = tuple((id(g.get("relation")), tuple(g["parents"]), int(b["obs"].shape[0])) for g, b in batches)
+        tb = self._packed_tables.get(key)
+        if tb is None:
+            if len(self._packed_tables) > 16:
+                self._packed_tables.clear()
+            tb = make_packed_tables([(g, int(b["obs"].shape[0])) for g, b in batches], self.actor.full_arena.device)
+            self._packed_tables[key] = tb
+        return self._run_update(tb, [b for _, b in batches], it, noises)
+
+    def _run_update(self, tb, batches, it: int, noises):
         a = self.args
         dev = self.actor.full_arena.device
         if dev.type != "cuda":
             raise RuntimeError("sgrl_b200.Agent.update needs the modules on a CUDA device (no CPU fallback)")
-        obs_in = data_batch["obs"]
-        B, width = int(obs_in.shape[0]), int(obs_in.shape[1])
-        tb = self.actor._tables(B)
         mods = (self.actor, self.actor_target, self.critic, self.critic_target)
         # the plans (and their captured graphs) hold raw pointers: drop them when a module was moved / re-flattened or
         # its GEMM path changed; parameters edited from Python (load_state_dict, p.data.copy_) only stale the tf32 split
@@ -240,8 +272,8 @@ class Agent(nn.Module):
             self._plan_sig = sig
         for m in mods:
             m._split_for(tb.T, True)
-        plan = self._plan(tb, B, width)
-        plan.load(data_batch, noise, float(a.policy_noise))
+        plan = self._plan(tb)
+        plan.load(batches, noises, float(a.policy_noise))
         actor_step = it % a.policy_freq == 0
         if self.use_graphs:
             plan.replay(actor_step)
@@ -249,7 +281,7 @@ class Agent(nn.Module):
             self._update_impl(plan, actor_step)
         scal = plan.scal.clone()
         loss_dict = {"loss/critic_loss": scal[0]}
-        loss_dict.update(self._reward_stats(data_batch["reward"], plan.rew))
+        loss_dict.update(self._reward_stats([b["reward"] for b in batches], plan.rew))
         if actor_step:
             loss_dict["loss/actor_loss"] = scal[1]
         self.tot_update_count += 1
@@ -283,7 +315,7 @@ class Agent(nn.Module):
         self.critic.forward_raw(tb, p.obs, p.act, keep=True, nb=2, trusted_split=True, out=p.q, stash=p.stash_c)
         main.wait_event(p.ev_a)
         check(lib.sgrl_td3_critic_loss(ptr(p.q[0]), ptr(p.q[1]), ptr(p.tq[0]), ptr(p.tq[1]), ptr(p.rew), ptr(p.done), ptr(tb.tok_graph),
-                                       ptr(p.target), ptr(p.dq[0]), ptr(p.dq[1]), ptr(p.scal), float(a.discount), float(self.reward_scale), T, st))
+                                       ptr(tb.tok_weight), ptr(p.target), ptr(p.dq[0]), ptr(p.dq[1]), ptr(p.scal), float(a.discount), float(self.reward_scale), T, st))
         self.critic_optimizer.zero_grad()
         self.critic.backward_raw(tb, p.stash_c, p.dq, 2, self.critic.grad_arena(), False, trusted_split=True, ws=p.ws)
         self._allreduce(self.critic.grad_arena(), world)
@@ -292,7 +324,7 @@ class Agent(nn.Module):
         if actor_step:
             main.wait_event(p.ev_c)
             self.critic.forward_raw(tb, p.obs, p.pi[0], keep=True, nb=1, trusted_split=True, out=p.q1, stash=p.stash_c)
-            check(lib.sgrl_td3_actor_loss(ptr(p.q1), ptr(p.dq1), ptr(p.scal[1:]), T, st))
+            check(lib.sgrl_td3_actor_loss(ptr(p.q1), ptr(tb.tok_weight), ptr(p.dq1), ptr(p.scal[1:]), T, st))
             self.critic.backward_raw(tb, p.stash_c, p.dq1, 1, None, True, trusted_split=True, ws=p.ws, dact=p.dact)   # only d/d(action)
             self.actor_optimizer.zero_grad()
             self.actor.backward_raw(tb, p.stash_a, p.dact, 1, self.actor.grad_arena(), False, trusted_split=True, ws=p.ws)
@@ -302,12 +334,12 @@ class Agent(nn.Module):
 
     train_step = update   # BASELINE.json calls the TD3 step "train()"; the reference name is update (agent.py:117)
 
-    def _reward_stats(self, reward_in, rew_dev):
+    def _reward_stats(self, rewards_in, rew_dev):
         """agent.py:158-162 returns Python floats (two device syncs in the reference).  When the batch
         arrived from host memory the statistics are computed there and nothing synchronises."""
         s = self.reward_scale
-        if isinstance(reward_in, np.ndarray) or (torch.is_tensor(reward_in) and not reward_in.is_cuda):
-            r = torch.as_tensor(reward_in, dtype=torch.float32).reshape(-1) * s
+        if all(isinstance(r, np.ndarray) or (torch.is_tensor(r) and not r.is_cuda) for r in rewards_in):
+            r = torch.cat([torch.as_tensor(x, dtype=torch.float32).reshape(-1) for x in rewards_in]) * s
             return {"misc/train_reward_mean": r.mean().item(), "misc/train_reward_var": r.var().item() if r.numel() > 1 else float("nan")}
         r = rew_dev * s
         if self.lazy_stats:

@@ -191,19 +191,19 @@ int sgrl_td3_smooth_action(const float* pi_target, const float* noise, float* ne
 }
 
 int sgrl_td3_critic_loss(const float* q1, const float* q2, const float* tq1, const float* tq2, const float* reward, const float* done,
-                         const int32_t* tok_graph, float* target, float* dq1, float* dq2, float* loss, float discount,
+                         const int32_t* tok_graph, const float* tok_weight, float* target, float* dq1, float* dq2, float* loss, float discount,
                          float reward_scale, int T, sgrl_stream_t stream) {
   SGRL_CHECK(q1 && q2 && tq1 && tq2 && reward && done && tok_graph && target && dq1 && dq2 && loss, "null pointer");
   int gx = ceil_div(T, 256); if (gx > NUM_SMS) gx = NUM_SMS;
-  launch_k(td3_critic_loss_kernel, gx, 256, 0, ST(stream), q1, q2, tq1, tq2, reward, done, tok_graph, target, dq1, dq2, loss, discount, reward_scale, T);
+  launch_k(td3_critic_loss_kernel, gx, 256, 0, ST(stream), q1, q2, tq1, tq2, reward, done, tok_graph, tok_weight, target, dq1, dq2, loss, discount, reward_scale, T);
   SGRL_LAUNCH_OK();
   return 0;
 }
 
-int sgrl_td3_actor_loss(const float* q1, float* dq1, float* loss, int T, sgrl_stream_t stream) {
+int sgrl_td3_actor_loss(const float* q1, const float* tok_weight, float* dq1, float* loss, int T, sgrl_stream_t stream) {
   SGRL_CHECK(q1 && dq1 && loss, "null pointer");
   int gx = ceil_div(T, 256); if (gx > NUM_SMS) gx = NUM_SMS;
-  launch_k(td3_actor_loss_kernel, gx, 256, 0, ST(stream), q1, dq1, loss, T);
+  launch_k(td3_actor_loss_kernel, gx, 256, 0, ST(stream), q1, tok_weight, dq1, loss, T);
   SGRL_LAUNCH_OK();
   return 0;
 }

@@ -19,6 +19,7 @@ __global__ void td3_smooth_action_kernel(const float* __restrict__ a, const floa
 __global__ void __launch_bounds__(256) td3_critic_loss_kernel(
     const float* __restrict__ q1, const float* __restrict__ q2, const float* __restrict__ tq1, const float* __restrict__ tq2,
     const float* __restrict__ reward, const float* __restrict__ done, const int* __restrict__ tok_graph,
+    const float* __restrict__ tok_w,
     float* __restrict__ target, float* __restrict__ dq1, float* __restrict__ dq2, float* __restrict__ loss,
     float discount, float reward_scale, int T) {
   SGRL_PDL_ENTER();
@@ -30,8 +31,11 @@ __global__ void __launch_bounds__(256) td3_critic_loss_kernel(
     const float y = reward[g] * reward_scale + (1.f - done[g]) * discount * fminf(tq1[t], tq2[t]);
     target[t] = y;
     const float e1 = q1[t] - y, e2 = q2[t] - y;
-    dq1[t] = 2.f * e1 * invT; dq2[t] = 2.f * e2 * invT;
-    acc += e1 * e1 + e2 * e2;
+    // tok_w (packed mixed-morphology batches): weight of token t in the loss = 1 / (#morphologies * tokens of its morphology),
+    // i.e. the mean over morphologies of the reference's per-morphology mse; single morphology: 1/T
+    const float w = tok_w ? tok_w[t] : invT;
+    dq1[t] = 2.f * e1 * w; dq2[t] = 2.f * e2 * w;
+    acc += (e1 * e1 + e2 * e2) * (tok_w ? w * (float)T : 1.f);
   }
   acc = warp_sum(acc);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
@@ -45,12 +49,16 @@ __global__ void __launch_bounds__(256) td3_critic_loss_kernel(
 }
 
 // actor loss = -mean(Q1):  dq = -1/T, loss += -sum(q)/T                                    agent.py:167
-__global__ void __launch_bounds__(256) td3_actor_loss_kernel(const float* __restrict__ q1, float* __restrict__ dq, float* __restrict__ loss, int T) {
+__global__ void __launch_bounds__(256) td3_actor_loss_kernel(const float* __restrict__ q1, const float* __restrict__ tok_w, float* __restrict__ dq,
+                                                             float* __restrict__ loss, int T) {
   SGRL_PDL_ENTER();
   __shared__ float red[8];
   float acc = 0.f;
   const float invT = 1.f / (float)T;
-  for (int t = blockIdx.x * 256 + threadIdx.x; t < T; t += gridDim.x * 256) { dq[t] = -invT; acc += q1[t]; }
+  for (int t = blockIdx.x * 256 + threadIdx.x; t < T; t += gridDim.x * 256) {
+    const float w = tok_w ? tok_w[t] : invT;
+    dq[t] = -w; acc += q1[t] * (tok_w ? w * (float)T : 1.f);
+  }
   acc = warp_sum(acc);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
   __syncthreads();

@@ -54,9 +54,11 @@ def _check_args(args):
 class GraphTables:
     """Device-side tables of one morphology (or of a packed mix of morphologies)."""
 
-    def __init__(self, cu_limbs, rank3, tok_graph, relation, rel_off, T, G):
+    def __init__(self, cu_limbs, rank3, tok_graph, relation, rel_off, T, G, tok_weight=None, parts=None):
         self.cu_limbs, self.rank3, self.tok_graph = cu_limbs, rank3, tok_graph
         self.relation, self.rel_off, self.T, self.G = relation, rel_off, T, G
+        self.tok_weight = tok_weight          # (T) loss weight per token, packed mixed-morphology batches only
+        self.parts = parts or [(0, T, 0, G, T // max(G, 1))]     # per morphology: (token0, token1, graph0, graph1, limbs)
 
 
 def make_tables(graph: Dict, batch: int, device) -> GraphTables:
@@ -76,6 +78,32 @@ def make_tables(graph: Dict, batch: int, device) -> GraphTables:
     rank3 = ranks.repeat(batch, 1).contiguous()
     tok_graph = torch.arange(batch, dtype=torch.int32, device=device).repeat_interleave(n).contiguous()
     return GraphTables(cu, rank3, tok_graph, rel, None, batch * n, batch)
+
+
+def make_packed_tables(parts, device) -> GraphTables:
+    """Tables for a PACKED batch of several morphologies: parts = [(graph_dict, batch_i), ...].  Tokens are ordered
+    morphology by morphology, sample-major, limb-minor; `cu_limbs` holds the ragged graph boundaries, `rel_off` each graph's
+    offset into the concatenated relation tables, `tok_weight` = 1 / (#morphologies * B_i * N_i): the loss of the packed
+    batch is the mean over morphologies of the reference's per-morphology loss (the reference steps the morphologies one
+    after the other, src/trainer.py:245-250)."""
+    cu, rank3, tokg, rel, reloff, w, spans = [0], [], [], [], [], [], []
+    t0 = g0 = ro = 0
+    m = len(parts)
+    for graph, batch in parts:
+        one = make_tables(graph, batch, "cpu")
+        n = len(graph["parents"])
+        cu.extend((one.cu_limbs[1:] + t0).tolist())
+        rank3.append(one.rank3)
+        tokg.append(one.tok_graph + g0)
+        rel.append(one.relation.reshape(-1))
+        reloff.extend([ro] * batch)
+        w.append(torch.full((batch * n,), 1.0 / (m * batch * n), dtype=torch.float32))
+        spans.append((t0, t0 + batch * n, g0, g0 + batch, n))
+        t0 += batch * n; g0 += batch; ro += n * n * 3
+    i32 = lambda x: torch.as_tensor(x, dtype=torch.int32).to(device).contiguous()
+    return GraphTables(i32(cu), torch.cat(rank3).to(device).contiguous(), torch.cat(tokg).to(torch.int32).to(device).contiguous(),
+                       torch.cat(rel).to(device).contiguous(), i32(reloff), t0, g0,
+                       tok_weight=torch.cat(w).to(device).contiguous() if m > 1 else None, parts=spans)
 
 
 class SetNetModule(nn.Module):
