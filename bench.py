@@ -41,6 +41,10 @@ def parse():
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--rollout-envs", type=int, default=16384)
     ap.add_argument("--use-tc", type=int, default=-1, help="1: tcgen05 3xTF32 projections, 0: fp32 SIMT, -1: library default")
+    ap.add_argument("--set", default="", help="morphology set (3d_hoppers, 3d_walkers, 3d_humanoids, 3d_cheetahs, 3d_cwhh): one step = one "
+                    "update of EVERY morphology of the set at --batch samples each (sharded round-robin over the ranks)")
+    ap.add_argument("--packed", action="store_true", help="with --set: all morphologies of the rank in ONE packed update (Agent.update_packed) "
+                    "instead of the reference's one-after-the-other schedule (src/trainer.py:245-250)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-rollout", action="store_true")
     return ap.parse_args()
@@ -183,6 +187,8 @@ def run_ours(a):
             dist.broadcast(m.full_arena, 0)
     g = G.build_graph(par, device=dev)
     agent.change_morphology(g)
+    if a.set:
+        return run_set(a, agent, dev, world, rank, local)
     nbat = 8
     host = [synth.make_batch(B, N, seed=100 + 17 * rank + i) for i in range(nbat)]
     host = [{k: v.pin_memory() for k, v in b.items()} for b in host]
@@ -330,6 +336,76 @@ def run_ours(a):
         barrier()
         sys.stdout.flush()
         os._exit(0)
+
+
+def run_set(a, agent, dev, world, rank, local):
+    """Multi-morphology step (BASELINE configs "Walker++ multi-morphology update", "cwhh ... sharded across 8 B200"): every
+    morphology of the set gets one TD3 update of --batch samples; the set is dealt round-robin over the ranks.  --packed runs a
+    rank's morphologies as one packed update; otherwise one update after the other like src/trainer.py:245-250."""
+    import torch
+    import torch.distributed as dist
+    from sgrl_b200 import graph as G, morphologies as M, synth
+    names = sorted(M.SETS[a.set])
+    mine = names[rank::world]
+    B = a.batch
+    K = a.steps + a.steps % 2
+    W = max(a.warmup, 4); W += W % 2
+    graphs = {n: G.build_graph(M.SETS[a.set][n], device=dev) for n in mine}
+    host = {n: {k: v.pin_memory() for k, v in synth.make_batch(B, len(M.SETS[a.set][n]), seed=300 + i).items()} for i, n in enumerate(mine)}
+    devb = {n: {k: v.to(dev) for k, v in host[n].items()} for n in mine}
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier(); torch.cuda.synchronize()
+
+    def step(i, batches):
+        if a.packed:
+            return agent.update_packed([(graphs[n], batches[n]) for n in mine], i)
+        ld = None
+        for n in mine:
+            agent.change_morphology(graphs[n])
+            ld = agent.update(batches[n], i)
+        return ld
+
+    agent.lazy_stats = True
+    for i in range(W):
+        step(i, devb)
+    barrier()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    for i in range(K):
+        flush.zero_()
+        ev[i][0].record(); step(i, devb); ev[i][1].record()
+    barrier()
+    t = torch.tensor([sum(s.elapsed_time(e) for s, e in ev)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = t.item()
+    agent.lazy_stats = False
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(K):
+        step(i, host)["loss/critic_loss"].item()
+    barrier()
+    t = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    nsamp = B * len(names)
+    toks = B * sum(len(M.SETS[a.set][n]) for n in names)
+    line = {"metric": "SET TD3 update samples/sec", "value": nsamp * K / (total_ms * 1e-3), "unit": "samples/s", "n_gpus": world, "steps": K,
+            "warmup": W, "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32 (3xTF32 tensor-core projections, fp32 accumulate)", "data": "synthetic",
+            "config": {"workload": f"{a.set}: {len(names)} morphologies x B={B}, one TD3 update each per step, "
+                                   + ("packed into one update per rank (Agent.update_packed)" if a.packed else "one after the other (src/trainer.py:245-250)"),
+                       "morphologies_per_rank": len(mine), "limb_tokens_per_step": toks, "l2": "256 MiB buffer written between timed steps"},
+            "e2e": {"value": nsamp * K / t.item(), "unit": "samples/s", "h2d_bytes_per_step": sum(v.numel() * 4 for n in mine for v in host[n].values()),
+                    "d2h_bytes_per_step": 4, "how": "update(_packed) with pinned host batches + critic_loss.item(), wall clock, max over ranks"},
+            "whole_step_tflops": FLOP_PER_TOKEN_UPDATE * toks / (total_ms / K * 1e-3) / 1e12}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        barrier(); sys.stdout.flush(); os._exit(0)
 
 
 if __name__ == "__main__":
