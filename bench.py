@@ -324,6 +324,61 @@ def run_ours(a):
                            "gemm_tflops": (rp["gemm_simt"][1] + rp["gemm_tcgen05"][1]) / max(rp["gemm_simt"][0] + rp["gemm_tcgen05"][0], 1e-9) / 1e9,
                            "hbm_peak_gbs": pk["hbm_gbs"]}
 
+    # ---- callers either side of the path, rank-local, wall clock through the public calls
+    if not a.no_rollout:
+        import random
+        from sgrl_b200.buffer import ReplayBuffer
+        cap = 32768
+        rb = ReplayBuffer(41 * N, 3 * N, max_buffer_size=cap, device=dev)
+        fill = synth.make_batch(cap, N, seed=5)
+        rb.add_batch(*(fill[k].to(dev) for k in ("obs", "action", "next_obs", "reward", "done")))
+        random.seed(rank)
+        agent.lazy_stats = True
+        for i in range(4):
+            agent.update_from_buffer(rb, B, i)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(K):
+            ld = agent.update_from_buffer(rb, B, i)
+        ld["loss/critic_loss"].item()
+        barrier()
+        dt_rb = time.perf_counter() - t0
+        evg = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        idx = torch.randint(0, cap, (4096,), device=dev)
+        outs = [torch.empty(4096, w, device=dev) for w in (41 * N, 3 * N, 41 * N, 1, 1)]
+        rb.gather_into(idx, *outs)
+        evg[0].record()
+        for _ in range(20):
+            rb.gather_into(idx, *outs)
+        evg[1].record(); torch.cuda.synchronize()
+        line["replay"] = {"value": world * B * K / dt_rb, "unit": "samples/s", "how": "Agent.update_from_buffer(device-resident ReplayBuffer, B, it): "
+                          "host draws B indices (random.sample), one gather kernel fills the update graph's inputs; wall clock",
+                          "h2d_bytes_per_step": 8 * B, "gather_gbs_B4096": 20 * 4096 * 8.0 * rb.row_floats / (evg[0].elapsed_time(evg[1]) * 1e-3) / 1e9}
+        agent.lazy_stats = False
+        # acting: B=1 select_action (the reference's per-env call) and the batched front-end over a mixed set of envs
+        one = synth.make_obs(1, N, seed=3)[0].numpy().astype("float64")
+        for _ in range(5):
+            agent.select_action(one)
+        t0 = time.perf_counter()
+        for _ in range(200):
+            agent.select_action(one)
+        us_one = (time.perf_counter() - t0) / 200 * 1e6
+        names = sorted(M.SETS["3d_humanoids"]) * 4
+        gl = {n: G.build_graph(M.SETS["3d_humanoids"][n], device=dev) for n in set(names)}
+        ol = [synth.make_obs(1, len(M.SETS["3d_humanoids"][n]), seed=i)[0].numpy() for i, n in enumerate(names)]
+        gs = [gl[n] for n in names]
+        for _ in range(5):
+            agent.select_actions(ol, gs)
+        t0 = time.perf_counter()
+        for _ in range(100):
+            agent.select_actions(ol, gs)
+        us_all = (time.perf_counter() - t0) / 100 * 1e6
+        agent.change_morphology(g)
+        line["acting"] = {"select_action_us": us_one, "select_actions_us": us_all, "envs": len(names),
+                          "us_per_env_batched": us_all / len(names),
+                          "how": "numpy obs in, numpy actions out (pinned H2D + replayed CUDA graph + D2H + sync); batched = one packed "
+                                 "forward over %d Humanoid++ envs of 6 morphologies (src/trainer.py:174-196 does them one by one)" % len(names)}
+
     # ---- reference algorithm on this box's host cores (rank 0, N=1 only; bounded sample)
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         cb = cpu_reference_rate(a.morph, B, budget_s=15.0)

@@ -65,7 +65,7 @@ typedef struct {
   int32_t G;           /* graphs (samples) in the batch */
   int32_t keep;        /* 1: keep every layer's activations for backward */
   int32_t use_tc;      /* 1: tcgen05 tensor-core projections (3xTF32), 0: fp32 SIMT */
-  int32_t reserved;
+  int32_t max_limbs;   /* largest graph of the batch (2..16), 0 = unknown: sizes the attention kernel's shared-memory staging */
   const float* params; /* live arena of the module (nb * live_floats) */
   float* grads;        /* gradient arena, same layout; may be NULL for forward / data-only backward */
   float* stash;        /* nb * stash_stride floats */
@@ -155,6 +155,19 @@ int sgrl_adam_clip(float* p, const float* g, float* m, float* v, int64_t n, cons
 int sgrl_bump_step(int32_t* step, sgrl_stream_t stream);
 int sgrl_polyak(float* target, const float* source, int64_t n, float tau,
                 float* t_hi /*nullable: refreshed tf32 split of target[0:n_split]*/, float* t_lo, int64_t n_split, sgrl_stream_t stream);
+
+/* ---- K7: device-resident replay storage (common/buffer.py:35-126) --------
+ * One transition = one packed row [obs (obs_dim) | action (act_dim) | next_obs (obs_dim) | reward | done] of
+ * row_floats = 2*obs_dim + act_dim + 2 floats; `rows` holds `capacity` of them in HBM.
+ * sgrl_replay_gather replaces ReplayBuffer.sample / get_batch's five fancy-index gathers + five H2D copies
+ * (buffer.py:103-145): idx (batch) int64 row numbers (device) -> obs (batch,obs_dim), action (batch,act_dim),
+ * next_obs, reward (batch), done (batch).  The outputs may be the static input buffers of a TD3 update.
+ * sgrl_replay_scatter writes n staged rows to rows[dst[i]] (add_transition for transitions already on the device,
+ * buffer.py:74-84). */
+int sgrl_replay_gather(const float* rows, int64_t row_floats, int64_t capacity, const int64_t* idx, int batch, int obs_dim, int act_dim,
+                       float* obs, float* action, float* next_obs, float* reward, float* done, sgrl_stream_t stream);
+int sgrl_replay_scatter(float* rows, int64_t row_floats, int64_t capacity, const int64_t* dst, const float* staged, int n,
+                        sgrl_stream_t stream);
 
 #ifdef __cplusplus
 }

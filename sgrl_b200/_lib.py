@@ -36,7 +36,7 @@ c_int = C.c_int
 class NetCall(C.Structure):
     _fields_ = [
         ("kind", C.c_int32), ("n_layers", C.c_int32), ("nb", C.c_int32), ("T", C.c_int32),
-        ("G", C.c_int32), ("keep", C.c_int32), ("use_tc", C.c_int32), ("reserved", C.c_int32),
+        ("G", C.c_int32), ("keep", C.c_int32), ("use_tc", C.c_int32), ("max_limbs", C.c_int32),
         ("params", c_f), ("grads", c_f), ("stash", c_f), ("stash_stride", c_i64),
         ("ws", c_f), ("ws_stride", c_i64),
         ("cu_limbs", c_f), ("rel_off", c_f), ("relation", c_f), ("rank3", c_f),
@@ -76,6 +76,8 @@ _PROTOS = {
     "sgrl_adam_clip": (c_int, [c_f, c_f, c_f, c_f, c_i64, c_f, c_f, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, c_f, c_f, c_f]),
     "sgrl_bump_step": (c_int, [c_f, c_f]),
     "sgrl_polyak": (c_int, [c_f, c_f, c_i64, C.c_float, c_f, c_f, c_i64, c_f]),
+    "sgrl_replay_gather": (c_int, [c_f, c_i64, c_i64, c_f, c_int, c_int, c_int, c_f, c_f, c_f, c_f, c_f, c_f]),
+    "sgrl_replay_scatter": (c_int, [c_f, c_i64, c_i64, c_f, c_f, c_int, c_f]),
 }
 EXPORTS = tuple(_PROTOS)
 

@@ -175,6 +175,68 @@ class _UpdatePlan:
         self.agent.graph_replayed_launches += self.graph_launches[actor_step]
 
 
+class _RolloutPlan:
+    """Static state of the actor's rollout forward for one packed table set: pinned host staging for observations and
+    actions, their device twins, the activation scratch, and the captured graph."""
+
+    def __init__(self, agent: "Agent", tb):
+        ac = agent.actor
+        dev = ac.full_arena.device
+        self.tb, self.agent = tb, agent
+        T = tb.T
+        self.h_obs = torch.zeros(T, 41, dtype=torch.float32, pin_memory=True)
+        self.h_out = torch.zeros(T, 3, dtype=torch.float32, pin_memory=True)
+        self.h_obs_np, self.h_out_np = self.h_obs.numpy().reshape(-1), self.h_out.numpy().reshape(-1)
+        self.obs = torch.zeros(T, 41, dtype=torch.float32, device=dev)
+        self.out = torch.zeros(1, T, 3, dtype=torch.float32, device=dev)
+        self.stash = torch.empty(ac.stash_floats(T, False, 1), dtype=torch.float32, device=dev)
+        self.graph, self.graph_launches, self.eager_runs = None, 0, 0
+
+    def _forward(self):
+        self.agent.actor.forward_raw(self.tb, self.obs, None, keep=False, nb=1, trusted_split=True, out=self.out, stash=self.stash)
+
+    def run(self, obs_list):
+        """obs_list: one array per part of the table set (env, or the (B,41N) batch of a single-morphology plan).
+        Returns per part a numpy view (valid until the next run) of its actions."""
+        ag, parts = self.agent, self.tb.parts
+        if len(obs_list) != len(parts):
+            raise ValueError(f"plan holds {len(parts)} parts, got {len(obs_list)} observations")
+        for (t0, t1, _, _, n), o in zip(parts, obs_list):
+            o = o.detach().cpu().numpy() if torch.is_tensor(o) else np.asarray(o)
+            if o.size != (t1 - t0) * 41:
+                raise RuntimeError(f"observation of {o.size} floats for a part of {t1 - t0} limbs x 41")
+            self.h_obs_np[t0 * 41:t1 * 41] = o.reshape(-1)           # numpy casts float64 observations (ModularEnv) to fp32 here
+        self.obs.copy_(self.h_obs, non_blocking=True)
+        ag.actor._split_for(self.tb.T, True)                          # refreshes the tf32 split only if the weights changed
+        if not ag.use_graphs:
+            self._forward()
+        elif self.graph is None and self.eager_runs < 1:
+            self.eager_runs += 1
+            self._forward()
+        else:
+            if self.graph is None:
+                try:
+                    torch.cuda.synchronize()
+                    g = torch.cuda.CUDAGraph()
+                    l0 = lib.sgrl_launch_count()
+                    with torch.cuda.graph(g):
+                        self._forward()
+                    self.graph_launches = lib.sgrl_launch_count() - l0
+                    ag.graph_replayed_launches -= self.graph_launches
+                    self.graph = g
+                except Exception as ex:
+                    warnings.warn(f"sgrl_b200: CUDA-graph capture of the rollout forward failed ({ex}); running eagerly")
+                    ag.use_graphs = False
+                    torch.cuda.synchronize()
+                    self._forward()
+            if self.graph is not None:
+                self.graph.replay()
+                ag.graph_replayed_launches += self.graph_launches
+        self.h_out.copy_(self.out[0], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return [self.h_out_np[t0 * 3:t1 * 3] for (t0, t1, _, _, _) in parts]
+
+
 class Agent(nn.Module):
     def __init__(self, args):
         super().__init__()
@@ -208,6 +270,9 @@ class Agent(nn.Module):
         self._packed_tables: Dict = {}
         self._plan_sig = None
         self.graph_replayed_launches = 0     # library kernels executed through graph replays (sgrl_launch_count() sees captures only)
+        self._rollout_plans: Dict = {}
+        self._rollout_tables: Dict = {}
+        self._rollout_sig = None
         self._loss = None
 
     # ------------------------------------------------------------------ TD3 step
@@ -258,7 +323,29 @@ class Agent(nn.Module):
             self._packed_tables[key] = tb
         return self._run_update(tb, [b for _, b in batches], it, noises)
 
-    def _run_update(self, tb, batches, it: int, noises):
+    def update_from_buffer(self, buffer, batch_size: int, it: int, noise: Optional[torch.Tensor] = None,
+                           sequential: bool = False, allow_duplicate: bool = False):
+        """``update(buffer.sample(batch_size), it)`` (src/trainer.py:289-293) without materialising the batch: the indices are
+        drawn like the reference draws them (buffer.py:87-101), and ONE gather kernel writes the sampled rows of the
+        device-resident ``sgrl_b200.buffer.ReplayBuffer`` straight into the static input buffers of the update's CUDA
+        graph.  Per step the host sends batch_size int64 indices and nothing else."""
+        idx = buffer.draw_indices(batch_size, sequential, allow_duplicate)
+        B, n = len(idx), self.actor.num_limbs
+        if buffer.obs_dim != 41 * n or buffer.action_dim != 3 * n:
+            raise ValueError(f"buffer rows ({buffer.obs_dim} obs, {buffer.action_dim} action floats) do not match the current "
+                             f"morphology ({n} limbs)")
+        tb = self.actor._tables(B)
+
+        def load(plan):
+            buffer.gather_into(idx, plan.obs, plan.act, plan.nobs, plan.rew, plan.done)
+            if noise is not None:
+                plan.noise.view(B, n * 3).copy_(torch.as_tensor(noise, dtype=torch.float32).reshape(B, n * 3), non_blocking=True)
+            else:
+                plan.noise.normal_(0.0, float(self.args.policy_noise))                # agent.py:128
+
+        return self._run_update(tb, None, it, None, loader=load)
+
+    def _run_update(self, tb, batches, it: int, noises, loader=None):
         a = self.args
         dev = self.actor.full_arena.device
         if dev.type != "cuda":
@@ -273,7 +360,10 @@ class Agent(nn.Module):
         for m in mods:
             m._split_for(tb.T, True)
         plan = self._plan(tb)
-        plan.load(batches, noises, float(a.policy_noise))
+        if loader is not None:
+            loader(plan)
+        else:
+            plan.load(batches, noises, float(a.policy_noise))
         actor_step = it % a.policy_freq == 0
         if self.use_graphs:
             plan.replay(actor_step)
@@ -281,7 +371,7 @@ class Agent(nn.Module):
             self._update_impl(plan, actor_step)
         scal = plan.scal.clone()
         loss_dict = {"loss/critic_loss": scal[0]}
-        loss_dict.update(self._reward_stats([b["reward"] for b in batches], plan.rew))
+        loss_dict.update(self._reward_stats([b["reward"] for b in batches] if batches is not None else [plan.rew], plan.rew))
         if actor_step:
             loss_dict["loss/actor_loss"] = scal[1]
         self.tot_update_count += 1
@@ -351,15 +441,56 @@ class Agent(nn.Module):
         soft_update_network(self.actor, self.actor_target, self.target_smoothing_tau)
 
     # ------------------------------------------------------------------ acting
+    def _rollout_plan(self, tb) -> "_RolloutPlan":
+        sig = (self.actor._arena.data_ptr(), int(self.actor.use_tc))
+        if sig != self._rollout_sig:
+            self._rollout_plans.clear()
+            self._rollout_sig = sig
+        plan = self._rollout_plans.get(id(tb))
+        if plan is None or plan.tb is not tb:
+            if len(self._rollout_plans) >= 64:
+                self._rollout_plans.clear()
+            plan = _RolloutPlan(self, tb)
+            self._rollout_plans[id(tb)] = plan
+        return plan
+
     @torch.no_grad()
     def select_action(self, obs, deterministic=False):
-        """src/agent.py:189-198: numpy (41N,) or (B,41N) -> numpy (B,3N)."""
+        """src/agent.py:189-198: numpy (41N,) or (B,41N) -> numpy (B,3N).  The forward of one (morphology, B) runs as a
+        replayed CUDA graph over pinned staging buffers (one H2D copy, ~70 kernels in one launch, one D2H copy)."""
         if len(obs.shape) == 1:
             obs = obs[None,]
-        if not isinstance(obs, torch.Tensor):
-            obs = torch.as_tensor(np.asarray(obs), dtype=torch.float32)
-        obs = obs.to(self.actor.full_arena.device, non_blocking=True)
-        return self.actor(obs).cpu().numpy()
+        dev = self.actor.full_arena.device
+        if dev.type != "cuda":
+            raise RuntimeError("sgrl_b200.Agent.select_action needs the modules on a CUDA device (no CPU fallback)")
+        B, n = int(obs.shape[0]), self.actor.num_limbs
+        if obs.shape[1] != 41 * n:
+            raise RuntimeError(f"shape '[{B}, {n}, -1]' is invalid for input of size {int(np.prod(obs.shape))}")
+        if torch.is_tensor(obs) and obs.is_cuda:
+            return self.actor(obs).cpu().numpy()
+        plan = self._rollout_plan(self.actor._tables(B))
+        return plan.run([obs])[0].reshape(B, 3 * n).copy()
+
+    @torch.no_grad()
+    def select_actions(self, obs_list, graphs, deterministic=False):
+        """Batched rollout front-end.  The reference acts env by env —
+        ``change_morphology(graph_i); select_action(obs_i)`` with B=1, src/trainer.py:174-196 and common/trainer.py:93-109 —
+        i.e. one ~1 700-op forward and two host<->device round trips per env and step.  Here the observations of ALL envs
+        (mixed morphologies) are packed into one ragged batch: obs_list[i] is env i's un-padded (41*N_i,) observation,
+        graphs[i] its graph dict; returns [ (1, 3*N_i) numpy action ] in env order.  One pinned H2D copy, one replayed
+        CUDA graph of the packed actor forward, one D2H copy.  Exploration noise / zero-padding stay with the caller."""
+        from .modules import make_packed_tables
+        if len(obs_list) != len(graphs) or not obs_list:
+            raise ValueError("select_actions needs one graph per observation")
+        key = tuple((id(g.get("relation")), tuple(g["parents"])) for g in graphs)
+        tb = self._rollout_tables.get(key)
+        if tb is None:
+            if len(self._rollout_tables) > 16:
+                self._rollout_tables.clear()
+            tb = make_packed_tables([(g, 1) for g in graphs], self.actor.full_arena.device)
+            self._rollout_tables[key] = tb
+        out = self._rollout_plan(tb).run(obs_list)
+        return [o.reshape(1, -1).copy() for o in out]
 
     def change_morphology(self, graph):
         self.actor.change_morphology(graph)

@@ -27,7 +27,9 @@ struct AttnGraphs {
   const float* relation;  // packed relation tables
   int G;
   int T;                  // total tokens (profiling/bookkeeping only)
+  int nmax;               // largest graph of the batch (limbs), 0 = unknown (MAXN): sizes the shared-memory staging, i.e. CTAs per SM
 };
+inline int attn_rows(const AttnGraphs& gr) { return (gr.nmax >= 2 && gr.nmax <= MAXN) ? gr.nmax : MAXN; }
 
 __device__ __forceinline__ void attn_stage_common(float* qs, float* vs, const float* __restrict__ QKV,
                                                   const float* __restrict__ VGP, const float* __restrict__ GD,
@@ -58,9 +60,10 @@ __global__ void __launch_bounds__(A_FWD_THREADS) attention_fwd_kernel(
     AttnGraphs gr) {
   SGRL_PDL_ENTER();
   extern __shared__ __align__(16) float smem[];
-  float* qs = smem;                     // [MAXN][A_RS]   q | k | v
-  float* vs = qs + MAXN * A_RS;         // [MAXN][A_RS]   vgx: [r][h][128]
-  float* S = vs + MAXN * A_RS;          // [2][16][16]
+  const int nr = (gr.nmax >= 2 && gr.nmax <= MAXN) ? gr.nmax : MAXN;
+  float* qs = smem;                     // [nr][A_RS]   q | k | v
+  float* vs = qs + nr * A_RS;           // [nr][A_RS]   vgx: [r][h][128]
+  float* S = vs + nr * A_RS;            // [2][16][16]
   const int tid = threadIdx.x, z = blockIdx.y;
   QKV += z * zsS; VGP += z * zsS; GD += z * zsS; O += z * zsS; OG += z * zsS; P += z * zsS;
   float wr[HEADS][3] = {{0, 0, 0}, {0, 0, 0}}, br[HEADS] = {0, 0};
@@ -137,8 +140,8 @@ __global__ void __launch_bounds__(A_FWD_THREADS) attention_fwd_kernel(
   }
 }
 
-constexpr size_t attn_fwd_smem() { return sizeof(float) * (2 * MAXN * A_RS + 512); }
-constexpr size_t attn_bwd_smem() { return sizeof(float) * (2 * MAXN * A_RS + MAXN * A_DS + 1024 + 16); }
+constexpr size_t attn_fwd_smem(int nr = MAXN) { return sizeof(float) * (2 * nr * A_RS + 512); }
+constexpr size_t attn_bwd_smem(int nr = MAXN) { return sizeof(float) * (2 * nr * A_RS + nr * A_DS + 1024 + 16); }
 
 // Backward.  Inputs dO (T,256), dOG (T,768) [workspace], saved P, QKV, VGP, GD [stash].
 // Outputs dQKV (T,768) — gradient w.r.t. the *stored* (post /F, post-scale) q|k|v — and
@@ -149,10 +152,11 @@ __global__ void __launch_bounds__(A_BWD_THREADS) attention_bwd_kernel(
     float* __restrict__ dWrel, long long zsG, AttnGraphs gr) {
   SGRL_PDL_ENTER();
   extern __shared__ __align__(16) float smem[];
+  const int nr = (gr.nmax >= 2 && gr.nmax <= MAXN) ? gr.nmax : MAXN;
   float* qs = smem;
-  float* vs = qs + MAXN * A_RS;
-  float* ds = vs + MAXN * A_RS;          // [MAXN][A_DS]  dO | dOG
-  float* Ps = ds + MAXN * A_DS;          // [2][16][16]
+  float* vs = qs + nr * A_RS;
+  float* ds = vs + nr * A_RS;            // [nr][A_DS]  dO | dOG
+  float* Ps = ds + nr * A_DS;            // [2][16][16]
   float* dS = Ps + 512;                  // [2][16][16]
   float* wacc = dS + 512;                // [6]
   const int tid = threadIdx.x, z = blockIdx.y;
@@ -279,10 +283,12 @@ inline int attention_fwd(const float* QKV, const float* VGP, const float* GD, fl
     SGRL_CUDA(cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_fwd_smem()));
     attr_done = true;
   }
-  const int gx = gr.G < 4 * NUM_SMS ? gr.G : 4 * NUM_SMS;
+  const int nr = attn_rows(gr);
+  const int per_sm = (int)((227 * 1024) / (attn_fwd_smem(nr) + 1024)) < 8 ? (int)((227 * 1024) / (attn_fwd_smem(nr) + 1024)) : 8;
+  const int gx = gr.G < per_sm * NUM_SMS ? gr.G : per_sm * NUM_SMS;
   // algorithmic bytes per token: read q|k|v 3072 + vg 3024 + gd 24, write o 1024 + og 3072 (+ P 128)
   prof_begin(PC_ATTENTION, (double)gr.T * nb * (3072.0 + 3024 + 24 + 1024 + 3072 + 128), st);
-  launch_k(attention_fwd_kernel, dim3(gx, nb), A_FWD_THREADS, attn_fwd_smem(), st, QKV, VGP, GD, O, OG, P, zsS, Wrel, brel, zsP, gr);
+  launch_k(attention_fwd_kernel, dim3(gx, nb), A_FWD_THREADS, attn_fwd_smem(nr), st, QKV, VGP, GD, O, OG, P, zsS, Wrel, brel, zsP, gr);
   prof_end(st);
   SGRL_LAUNCH_OK();
   return 0;
@@ -297,8 +303,10 @@ inline int attention_bwd(const float* QKV, const float* VGP, const float* GD, co
     SGRL_CUDA(cudaFuncSetAttribute(attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_bwd_smem()));
     attr_done = true;
   }
-  const int gx = gr.G < 2 * NUM_SMS ? gr.G : 2 * NUM_SMS;
-  launch_k(attention_bwd_kernel, dim3(gx, nb), A_BWD_THREADS, attn_bwd_smem(), st, QKV, VGP, GD, P, zsS, dO, dOG, dQKV, dVGP, zsW, dWrel, zsG, gr);
+  const int nr = attn_rows(gr);
+  const int per_sm = (int)((227 * 1024) / (attn_bwd_smem(nr) + 1024)) < 4 ? (int)((227 * 1024) / (attn_bwd_smem(nr) + 1024)) : 4;
+  const int gx = gr.G < per_sm * NUM_SMS ? gr.G : per_sm * NUM_SMS;
+  launch_k(attention_bwd_kernel, dim3(gx, nb), A_BWD_THREADS, attn_bwd_smem(nr), st, QKV, VGP, GD, P, zsS, dO, dOG, dQKV, dVGP, zsW, dWrel, zsG, gr);
   SGRL_LAUNCH_OK();
   return 0;
 }

@@ -18,7 +18,7 @@
 
 namespace sgrl {
 
-constexpr int F_TT = 32;        // tokens per tile
+constexpr int F_TT = 32;        // tokens per tile (16-token tiles at 4 CTAs/SM measured slower: 2 204 vs 2 783 GB/s at 147 K tokens)
 constexpr int F_THREADS = 256;
 
 template <int CE, int NPROJ>

@@ -2,6 +2,7 @@
 #include "../../include/sgrl_b200.h"
 
 #include "net.cuh"
+#include "replay.cuh"
 #include "td3.cuh"
 
 namespace sgrl {
@@ -101,7 +102,7 @@ static int make_ctx(const SgrlNetCall* k, cudaStream_t st, NetCtx& c) {
   c.stash = k->stash; c.zsS = k->stash_stride;
   c.wl = make_ws(k->n_layers, k->T);
   c.ws = k->ws; c.zsW = k->ws_stride;
-  c.gr.cu_limbs = k->cu_limbs; c.gr.rel_off = k->rel_off; c.gr.relation = k->relation; c.gr.G = k->G; c.gr.T = k->T;
+  c.gr.cu_limbs = k->cu_limbs; c.gr.rel_off = k->rel_off; c.gr.relation = k->relation; c.gr.G = k->G; c.gr.T = k->T; c.gr.nmax = k->max_limbs;
   c.rank3 = k->rank3; c.max_action = k->max_action; c.use_tc = k->use_tc; c.stream = st;
   return 0;
 }
@@ -143,7 +144,7 @@ int sgrl_attention_fwd(const float* qkv, const float* vgp, const float* gd, cons
                        sgrl_stream_t stream) {
   SGRL_CHECK(qkv && vgp && gd && cu_limbs && o && og && p, "null pointer");
   SGRL_CHECK((rel_w == nullptr) || (rel_b && relation), "bias needs rel_b and relation");
-  AttnGraphs gr{cu_limbs, rel_off, relation, G, 0};
+  AttnGraphs gr{cu_limbs, rel_off, relation, G, 0, 0};
   return attention_fwd(qkv, vgp, gd, o, og, p, 0, rel_w, rel_b, 0, gr, 1, ST(stream));
 }
 
@@ -151,7 +152,7 @@ int sgrl_attention_bwd(const float* qkv, const float* vgp, const float* gd, cons
                        const int32_t* cu_limbs, const int32_t* rel_off, const float* relation, int G, float* dqkv, float* dvgp,
                        float* drel_w, sgrl_stream_t stream) {
   SGRL_CHECK(qkv && vgp && gd && p && d_o && d_og && cu_limbs && dqkv && dvgp, "null pointer");
-  AttnGraphs gr{cu_limbs, rel_off, relation, G, 0};
+  AttnGraphs gr{cu_limbs, rel_off, relation, G, 0, 0};
   return attention_bwd(qkv, vgp, gd, p, 0, d_o, d_og, dqkv, dvgp, 0, drel_w, 0, gr, 1, ST(stream));
 }
 
@@ -252,6 +253,20 @@ int sgrl_polyak(float* target, const float* source, int64_t n, float tau, float*
   launch_k(polyak_kernel, grid_for_flat(n), 256, 0, ST(stream), target, source, n, tau, (float)(1.0 - (double)tau), t_hi, t_lo, n_split);
   SGRL_LAUNCH_OK();
   return 0;
+}
+
+int sgrl_replay_gather(const float* rows, int64_t row_floats, int64_t capacity, const int64_t* idx, int batch, int obs_dim, int act_dim,
+                       float* obs, float* action, float* next_obs, float* reward, float* done, sgrl_stream_t stream) {
+  SGRL_CHECK(rows && idx && obs && action && next_obs && reward && done, "null pointer");
+  SGRL_CHECK(obs_dim > 0 && act_dim > 0 && row_floats == 2LL * obs_dim + act_dim + 2 && capacity > 0 && batch >= 0, "bad replay row geometry");
+  ReplayOut o{obs, action, next_obs, reward, done};
+  return replay_gather(rows, row_floats, reinterpret_cast<const long long*>(idx), batch, obs_dim, act_dim, capacity, o, ST(stream));
+}
+
+int sgrl_replay_scatter(float* rows, int64_t row_floats, int64_t capacity, const int64_t* dst, const float* staged, int n, sgrl_stream_t stream) {
+  SGRL_CHECK(rows && dst && staged, "null pointer");
+  SGRL_CHECK(row_floats > 0 && capacity > 0 && n >= 0, "bad replay row geometry");
+  return replay_scatter(rows, row_floats, reinterpret_cast<const long long*>(dst), staged, n, capacity, ST(stream));
 }
 
 }  // extern "C"

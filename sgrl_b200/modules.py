@@ -59,6 +59,7 @@ class GraphTables:
         self.relation, self.rel_off, self.T, self.G = relation, rel_off, T, G
         self.tok_weight = tok_weight          # (T) loss weight per token, packed mixed-morphology batches only
         self.parts = parts or [(0, T, 0, G, T // max(G, 1))]     # per morphology: (token0, token1, graph0, graph1, limbs)
+        self.nmax = max(p[4] for p in self.parts)                 # largest graph: sizes the attention kernel's staging
 
 
 def make_tables(graph: Dict, batch: int, device) -> GraphTables:
@@ -284,7 +285,7 @@ class SetNetModule(nn.Module):
     def _call(self, tb: GraphTables, nb: int, keep: int, stash, grads=None, ws=None, split=(None, None)) -> NetCall:
         k = NetCall()
         k.kind, k.n_layers, k.nb, k.T, k.G = self._kind, self._n_layers, nb, tb.T, tb.G
-        k.keep, k.use_tc = keep, int(self.use_tc)
+        k.keep, k.use_tc, k.max_limbs = keep, int(self.use_tc), int(tb.nmax)
         k.params = ptr(self.live_arena)
         k.params_hi, k.params_lo = ptr(split[0]), ptr(split[1])
         k.grads = ptr(grads)
