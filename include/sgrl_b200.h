@@ -102,7 +102,9 @@ int sgrl_set_backward(const SgrlNetCall* call, const float* dout, int64_t dout_s
 /* ---- single kernels (unit tests, profiling) ---------------------------------------------- */
 /* K1: Z=[X P^T | gd], G=Z^T Z, F=||G||+1 (subequivariant_attentions.py:90-96; SEActor.py:93-100,
  * 256-262).  X (T,3,128); v0 (T,3,8) or NULL (head variant, C=136); P1,P2 (30,C) (P2/Z2 NULL for
- * one projection); outputs Z,Z2 (T,3,32), G (T,1024), F (T). */
+ * one projection); outputs Z,Z2 (T,3,32), F (T) and G (T,544): G is symmetric, so vec(G) is kept as its upper
+ * triangle (528 entries, row-major i<=j, zero-padded to 544 = 17 k-blocks) and contracted against triangle-folded
+ * weights W'[o][p(i,j)] = W[o][32i+j] + W[o][32j+i].  The backward takes dG in the same packed form. */
 int sgrl_inv_feature_fwd(const float* X, const float* v0, const float* gd, const float* P1, const float* P2,
                          float* Z, float* Z2, float* G, float* F, int T, sgrl_stream_t stream);
 int sgrl_inv_feature_bwd(const float* dG, const float* dF, const float* Z, const float* F, float* dZ, int T,

@@ -10,13 +10,28 @@
 // Optionally a second projection P' gives Z'_t = [X_t P'^T | gd_t] (the operand of the
 // per-token matrix apply, SEActor.py:108-110 / :273-274) from the same staged X tile.
 //
-// HBM-bound: reads 12*C+24 B, writes 4096+4+384 B per token.  One CTA stages P once and
+// G is symmetric: only its upper triangle (528 entries, row-major i<=j, zero-padded to GP_K = 544) is written, and the
+// consumers contract it against triangle-folded weights (layout.h, fold_sym_kernel below).
+// HBM-bound: reads 12*C+24 B, writes 2176+4+384 B per token.  One CTA stages P once and
 // walks 32-token tiles: coalesced float4 loads -> padded smem -> 3x4 register micro-tiles
 // for the projection -> per-warp Gram rows written as 512 B coalesced float4 stores.
 #pragma once
 #include "common.cuh"
+#include "layout.h"
 
 namespace sgrl {
+
+// p -> (i << 8 | j) of the packed upper triangle; 0xFFFF for the zero padding p >= GP
+struct TriLut { unsigned short v[GP_K]; };
+constexpr TriLut make_tri_lut() {
+  TriLut t{};
+  int p = 0;
+  for (int i = 0; i < CH; ++i)
+    for (int j = i; j < CH; ++j) t.v[p++] = (unsigned short)((i << 8) | j);
+  for (; p < GP_K; ++p) t.v[p] = 0xFFFFu;
+  return t;
+}
+__constant__ TriLut c_tri = make_tri_lut();
 
 constexpr int F_TT = 32;        // tokens per tile (16-token tiles at 4 CTAs/SM measured slower: 2 204 vs 2 783 GB/s at 147 K tokens)
 constexpr int F_THREADS = 256;
@@ -26,7 +41,7 @@ struct FeatSmem {
   static constexpr int C = 128 + CE;
   static constexpr int PJ = 32 * NPROJ;
   static constexpr int XS = 3 * C + 4;  // padded token stride (floats)
-  static constexpr size_t bytes = sizeof(float) * ((size_t)C * PJ + (size_t)F_TT * XS + (size_t)F_TT * 3 * PJ + F_TT * 8);
+  static constexpr size_t bytes = sizeof(float) * ((size_t)C * PJ + (size_t)F_TT * XS + (size_t)F_TT * 3 * PJ + F_TT * 8 + GP_K / 2);
 };
 
 // X = [V0 (T,3,8) if CE==8 | Xg (T,3,128)], P1/P2 (30,C) row-major, gd (T,3,2)
@@ -45,6 +60,7 @@ __global__ void __launch_bounds__(F_THREADS) inv_feature_fwd_kernel(
   float* Xs = Ps + C * PJ;                // [TT][XS]
   float* Zs = Xs + F_TT * XS;             // [TT][3][PJ]
   float* gds = Zs + F_TT * 3 * PJ;        // [TT][8] (6 used)
+  unsigned short* tri = reinterpret_cast<unsigned short*>(gds + F_TT * 8);   // [GP_K] (divergent lookups: not from constant memory)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, z = blockIdx.y;
   Xg += z * zsXg; gd += z * zsGd; P1 += z * zsP;
   if (CE) V0 += z * zsV0;
@@ -52,6 +68,7 @@ __global__ void __launch_bounds__(F_THREADS) inv_feature_fwd_kernel(
   Z += z * zsAct; G += z * zsAct; Fn += z * zsAct;
   if (NPROJ == 2) Z2 += z * zsAct;
 
+  for (int i = tid; i < GP_K; i += F_THREADS) tri[i] = c_tri.v[i];
   // stage P transposed: Ps[c][j] = P[j][c]; columns 30,31 (and 62,63) are zero
   for (int i = tid; i < C * PJ; i += F_THREADS) {
     const int j = i / C, c = i % C;        // coalesced along c in global
@@ -129,24 +146,25 @@ __global__ void __launch_bounds__(F_THREADS) inv_feature_fwd_kernel(
         stg4((which ? Z2 : Z) + ((long long)t0 * 3 + row) * 32 + q * 4, v);
       }
     }
-    // ---- Gram + Frobenius norm: one warp per token, 8 x (32 lanes x float4) = 1024 outputs
+    // ---- Gram (upper triangle) + Frobenius norm: one warp per token, 17 x 32 coalesced outputs
     for (int tk = warp; tk < F_TT; tk += F_THREADS / 32) {
       if (t0 + tk >= T) break;
       const float* zr = Zs + tk * 3 * PJ;
       float ss = 0.f;
-      float* g = G + (long long)(t0 + tk) * 1024;
+      float* g = G + (long long)(t0 + tk) * GP_K;
 #pragma unroll
-      for (int n = 0; n < 8; ++n) {
-        const int idx = n * 32 + lane, i = idx >> 3, jq = idx & 7;
-        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-        for (int r = 0; r < 3; ++r) {
-          const float zi = zr[r * PJ + i];
-          const float4 zj = *reinterpret_cast<const float4*>(zr + r * PJ + jq * 4);
-          o.x = fmaf(zi, zj.x, o.x); o.y = fmaf(zi, zj.y, o.y); o.z = fmaf(zi, zj.z, o.z); o.w = fmaf(zi, zj.w, o.w);
+      for (int n = 0; n < GP_K / 32; ++n) {
+        const int p = n * 32 + lane;
+        const unsigned code = tri[p];
+        float o = 0.f;
+        if (code != 0xFFFFu) {
+          const int i = code >> 8, j = code & 255;
+          o = zr[i] * zr[j];
+          o = fmaf(zr[PJ + i], zr[PJ + j], o);
+          o = fmaf(zr[2 * PJ + i], zr[2 * PJ + j], o);
+          ss = fmaf(i == j ? o : 2.f * o, o, ss);     // ||G||_F^2 over the full symmetric matrix
         }
-        stg4(g + idx * 4, o);
-        ss += o.x * o.x + o.y * o.y + o.z * o.z + o.w * o.w;
+        g[p] = o;
       }
       ss = warp_sum(ss);
       if (lane == 0) Fn[t0 + tk] = sqrtf(ss) + 1.0f;
@@ -172,8 +190,8 @@ inline int inv_feature_fwd_launch(const FeatFwdP& p, cudaStream_t st) {
   }
   const int ntiles = ceil_div(p.T, F_TT);
   const int gx = ntiles < 2 * NUM_SMS ? ntiles : 2 * NUM_SMS;
-  // algorithmic bytes per token: read X (12*C) + gd (24), write G (4096) + F (4) + Z (384 per projection)
-  prof_begin(PC_FEATURE, (double)p.T * p.nb * (12.0 * S::C + 24 + 4096 + 4 + 384.0 * NPROJ), st);
+  // algorithmic bytes per token: read X (12*C) + gd (24), write G (4*GP_K = 2176: packed triangle) + F (4) + Z (384 per projection)
+  prof_begin(PC_FEATURE, (double)p.T * p.nb * (12.0 * S::C + 24 + 4.0 * GP_K + 4 + 384.0 * NPROJ), st);
   launch_k(kern, dim3(gx, p.nb), F_THREADS, S::bytes, st, p.Xg, p.zsXg, p.V0, p.zsV0, p.gd, p.zsGd, p.P1, p.P2, p.zsP,
                                                    p.Z, p.Z2, p.G, p.Fn, p.zsAct, p.T);
   prof_end(st);
@@ -189,16 +207,16 @@ inline int inv_feature_fwd(const FeatFwdP& p, cudaStream_t st) {
 }
 
 // ---- backward ------------------------------------------------------------------------
-// Inputs: dG (T,1024) gradient w.r.t. vec(G) from the consumer GEMM, dF (T) accumulated
-// gradient w.r.t. F from every division by F, Z (T,3,32), F (T).
-//   dG_tot = dG + dF * G / (F-1)        (G recomputed from Z; F-1 = ||G||_F, 0 -> subgradient 0)
-//   dZ     = Z (dG_tot + dG_tot^T)      (T,3,32); columns 30,31 (inputs) are ignored downstream
-// If dZ_add != nullptr its contents are added (gradient reaching Z through another path).
+// Inputs: dGp (T,GP_K) gradient w.r.t. the packed triangle from the consumer GEMM (against the folded weights, so
+// dGp[p(i,j)] = dL/dG_ij + dL/dG_ji for i<j and dL/dG_ii on the diagonal), dF (T) accumulated gradient w.r.t. F from
+// every division by F, Z (T,3,32), F (T).
+//   S      = dG + dG^T + 2 dF G / (F-1)   (G recomputed from Z; F-1 = ||G||_F, 0 -> subgradient 0)
+//   dZ     = Z S                          (T,3,32); columns 30,31 (inputs) are ignored downstream
 __global__ void __launch_bounds__(256) inv_feature_bwd_kernel(
     const float* __restrict__ dG, const float* __restrict__ dF, const float* __restrict__ Z,
     const float* __restrict__ Fn, float* __restrict__ dZ, long long zsAct, long long zsWs, int T) {
   SGRL_PDL_ENTER();
-  __shared__ float S[8][32][33];
+  __shared__ float Sg[8][GP_K];
   __shared__ float Zw[8][3][32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, z = blockIdx.y;
   dG += z * zsWs; dF += z * zsWs; dZ += z * zsWs; Z += z * zsAct; Fn += z * zsAct;
@@ -206,22 +224,22 @@ __global__ void __launch_bounds__(256) inv_feature_bwd_kernel(
     __syncwarp();
 #pragma unroll
     for (int r = 0; r < 3; ++r) Zw[warp][r][lane] = Z[(long long)t * 96 + r * 32 + lane];
+    const float* dg = dG + (long long)t * GP_K;
+#pragma unroll
+    for (int n = 0; n < GP_K / 32; ++n) Sg[warp][n * 32 + lane] = __ldg(dg + n * 32 + lane);
     const float nrm = Fn[t] - 1.0f;
     const float coef = nrm > 0.f ? dF[t] / nrm : 0.f;
     __syncwarp();
     const float zj0 = Zw[warp][0][lane], zj1 = Zw[warp][1][lane], zj2 = Zw[warp][2][lane];
-    const float* dg = dG + (long long)t * 1024;
-#pragma unroll 4
-    for (int i = 0; i < 32; ++i) {
-      const float g = Zw[warp][0][i] * zj0 + Zw[warp][1][i] * zj1 + Zw[warp][2][i] * zj2;
-      S[warp][i][lane] = __ldg(dg + i * 32 + lane) + coef * g;
-    }
-    __syncwarp();
     float a0 = 0.f, a1 = 0.f, a2 = 0.f;
 #pragma unroll 4
     for (int i = 0; i < 32; ++i) {
-      const float s = S[warp][i][lane] + S[warp][lane][i];
-      a0 = fmaf(Zw[warp][0][i], s, a0); a1 = fmaf(Zw[warp][1][i], s, a1); a2 = fmaf(Zw[warp][2][i], s, a2);
+      const float zi0 = Zw[warp][0][i], zi1 = Zw[warp][1][i], zi2 = Zw[warp][2][i];
+      const float g = zi0 * zj0 + zi1 * zj1 + zi2 * zj2;
+      const int lo = min(i, lane), hi = max(i, lane);
+      const float d = Sg[warp][tri_index(lo, hi)];
+      const float s = (i == lane) ? 2.f * (d + coef * g) : d + 2.f * coef * g;
+      a0 = fmaf(zi0, s, a0); a1 = fmaf(zi1, s, a1); a2 = fmaf(zi2, s, a2);
     }
     float* o = dZ + (long long)t * 96;
     o[lane] = a0; o[32 + lane] = a1; o[64 + lane] = a2;
@@ -236,6 +254,67 @@ inline int inv_feature_bwd(const float* dG, const float* dF, const float* Z, con
   launch_k(inv_feature_bwd_kernel, dim3(gx, nb), 256, 0, st, dG, dF, Z, Fn, dZ, zsAct, zsWs, T);
   SGRL_LAUNCH_OK();
   return 0;
+}
+
+// ---- triangle fold of the vec(G) consumers (layout.h) -----------------------------------------------------------
+struct FoldDesc {
+  long long src[2 * MAX_LAYERS + 1];   // offset of the (rows,1024) weight inside the parameter / gradient arena
+  long long dst[2 * MAX_LAYERS + 1];   // offset of the (rows,GP_K) folded matrix inside a fold plane
+  int rows[2 * MAX_LAYERS + 1];
+  int n;
+};
+
+// W'[o][p(i,j)] = W[o][32i+j] + W[o][32j+i] (i<j) | W[o][33i]; planes: fp32, and (with_split) tf32 hi / lo for the tcgen05 path
+__global__ void __launch_bounds__(256) fold_sym_kernel(const float* __restrict__ params, long long zsP, float* __restrict__ wf, long long zsS,
+                                                       long long plane, int with_split, FoldDesc d) {
+  SGRL_PDL_ENTER();
+  __shared__ unsigned short tri[GP_K];
+  for (int i = threadIdx.x; i < GP_K; i += 256) tri[i] = c_tri.v[i];
+  __syncthreads();
+  const int m = blockIdx.y, z = blockIdx.z;
+  const float* W = params + z * zsP + d.src[m];
+  float* o0 = wf + z * zsS + d.dst[m];
+  const int total = d.rows[m] * GP_K;
+  for (int idx = blockIdx.x * 256 + threadIdx.x; idx < total; idx += gridDim.x * 256) {
+    const int o = idx / GP_K, p = idx - o * GP_K;
+    const unsigned code = tri[p];
+    float v = 0.f;
+    if (code != 0xFFFFu) {
+      const int i = code >> 8, j = code & 255;
+      const float* w = W + (long long)o * (CH * CH);
+      v = __ldg(w + i * CH + j);
+      if (i != j) v += __ldg(w + j * CH + i);
+    }
+    o0[idx] = v;
+    if (with_split) {
+      const unsigned hb = (__float_as_uint(v) + 0x1000u) & 0xFFFFE000u;
+      const float h = __uint_as_float(hb);
+      o0[plane + idx] = h;
+      o0[2 * plane + idx] = __uint_as_float((__float_as_uint(v - h) + 0x1000u) & 0xFFFFE000u);
+    }
+  }
+}
+
+// gradient of the fold: dW[o][32i+j] += dW'[o][p], dW[o][32j+i] += dW'[o][p]  (G symmetric: both get the same value)
+__global__ void __launch_bounds__(256) unfold_sym_kernel(const float* __restrict__ gf, long long zsW, float* __restrict__ grads, long long zsG, FoldDesc d) {
+  SGRL_PDL_ENTER();
+  __shared__ unsigned short tri[GP_K];
+  for (int i = threadIdx.x; i < GP_K; i += 256) tri[i] = c_tri.v[i];
+  __syncthreads();
+  const int m = blockIdx.y, z = blockIdx.z;
+  const float* src = gf + z * zsW + d.dst[m];
+  float* G = grads + z * zsG + d.src[m];
+  const int total = d.rows[m] * GP_K;
+  for (int idx = blockIdx.x * 256 + threadIdx.x; idx < total; idx += gridDim.x * 256) {
+    const int o = idx / GP_K, p = idx - o * GP_K;
+    const unsigned code = tri[p];
+    if (code == 0xFFFFu) continue;
+    const int i = code >> 8, j = code & 255;
+    const float v = src[idx];
+    float* g = G + (long long)o * (CH * CH);
+    g[i * CH + j] += v;
+    if (i != j) g[j * CH + i] += v;
+  }
 }
 
 }  // namespace sgrl

@@ -27,15 +27,16 @@ enum WS {
   W_DF1, W_DF2, W_DA, W_DA2, W_DA3, W_DT31, W_DT4, W_DR, W_DFF, W_DUH, W_DSH, W_DQ, WS_COUNT
 };
 inline const int* ws_sizes() {
-  static const int s[WS_COUNT] = {384, 128, 128, 256, 256, 768, 756, 256, 768, 128, 384, 96, 96, 96, 1024,
+  static const int s[WS_COUNT] = {384, 128, 128, 256, 256, 768, 756, 256, 768, 128, 384, 96, 96, 96, GP_K,
                                   1, 1, 256, 256, 128, 512, 1024, 96, 128, 256, 148, 3};
   return s;
 }
-struct WsLayout { long long o[MAX_LAYERS + 1][WS_COUNT]; long long total; };
+struct WsLayout { long long o[MAX_LAYERS + 1][WS_COUNT]; long long gf /* gradients of the folded vec(G) weights */; long long total; };
 inline WsLayout make_ws(int n_layers, long long T) {
   WsLayout w; long long off = 0;
   for (int f = 0; f <= n_layers; ++f)
     for (int i = 0; i < WS_COUNT; ++i) { w.o[f][i] = off; off = align_up(off + (long long)ws_sizes()[i] * T, 64); }
+  w.gf = off; off += fold_floats(n_layers);
   w.total = off;
   return w;
 }
@@ -168,6 +169,44 @@ inline GemmP wgrad(const NetCtx& c, const float* dY, int lddy, const float* X, i
   g.splitk = pick_splitk(Nw, Kw, M, c.nb);
   return g;
 }
+// ---- the three vec(G) consumers run against their triangle-folded copies (layout.h): K = GP_K instead of 1024 ----
+inline FoldDesc fold_desc(const NetCtx& c) {
+  FoldDesc d; d.n = 0;
+  for (int l = 0; l < c.L; ++l)
+    for (int w = 0; w < 2; ++w) { d.src[d.n] = c.lay.lp[l][w ? L_FG1_W : L_G1_W]; d.dst[d.n] = fold_offset(c.L, l, w); d.rows[d.n] = HID; ++d.n; }
+  d.src[d.n] = c.lay.gp[G_H1G_W]; d.dst[d.n] = fold_offset(c.L, c.L, 0); d.rows[d.n] = D; ++d.n;
+  return d;
+}
+inline void use_fold(const NetCtx& c, GemmP& g, long long fold_off) {
+  const float* w = c.stash + c.st.wf + fold_off;
+  g.B = w; g.zsB = c.zsS; g.ldb = GP_K;
+  g.Bhi = c.phi ? w + c.st.wf_plane : nullptr; g.Blo = c.phi ? w + 2 * c.st.wf_plane : nullptr;
+}
+// Y[M,N] = Gp[M,GP_K] W'^T + b
+inline GemmP lin_fold(const NetCtx& c, const float* Gp, long long fold_off, long long b_off, float* Y, int ldy, int M, int N) {
+  GemmP g = lin(c, Gp, GP_K, c.zsS, 0, b_off, Y, ldy, c.zsS, M, N, GP_K);
+  use_fold(c, g, fold_off);
+  return g;
+}
+// dGp[M,GP_K] = dY[M,Nw] W'
+inline GemmP dgrad_fold(const NetCtx& c, const float* dY, int lddy, long long fold_off, float* dGp, int M, int Nw) {
+  GemmP g = dgrad(c, dY, lddy, 0, GP_K, dGp, GP_K, M, Nw, GP_K);
+  use_fold(c, g, fold_off);
+  return g;
+}
+// dW'[Nw,GP_K] += dY^T Gp   (into the workspace; unfolded into the gradient arena at the end of the backward)
+inline GemmP wgrad_fold(const NetCtx& c, const float* dY, int lddy, const float* Gp, long long fold_off, int M, int Nw) {
+  GemmP g = wgrad(c, dY, lddy, Gp, GP_K, c.zsS, 0, GP_K, M, Nw, GP_K);
+  g.C = c.ws + c.wl.gf + fold_off; g.zsC = c.zsW;
+  return g;
+}
+inline int fold_weights(const NetCtx& c, cudaStream_t st) {
+  const FoldDesc d = fold_desc(c);
+  launch_k(fold_sym_kernel, dim3(32, d.n, c.nb), 256, 0, st, c.params, c.zsP, c.stash + c.st.wf, c.zsS, c.st.wf_plane, c.phi ? 1 : 0, d);
+  SGRL_LAUNCH_OK();
+  return 0;
+}
+
 inline int colsum(const NetCtx& c, const float* X, int ldx, long long g_off, int M, int N, float alpha, cudaStream_t st) {
   int gy = ceil_div(M, 64); if (gy > 32) gy = 32; if (gy < 1) gy = 1;
   launch_k(colsum_kernel, dim3(ceil_div(N, 32), gy, c.nb), 256, 0, st, X, ldx, c.zsW, c.Gr(g_off), c.zsG, M, N, alpha);
@@ -249,10 +288,12 @@ inline int net_forward(const NetCtx& c, const float* obs, long long zsObs, const
     f.Z = c.SL(l, S_Z1); f.G = c.SL(l, S_G1); f.Fn = c.SL(l, S_F1); f.zsAct = zS; f.T = T; f.nb = c.nb;
     // branch: vg = vg_proj(Vg) only needs the layer input
     SGRL_TRY(side_fork(c, &sb, 0));
+    if (l == 0) SGRL_TRY(fold_weights(c, sb));       // triangle-folded vec(G) consumers of every layer, off the main chain
     GemmP g = lin(c, Vg, 128, zS, lp[L_VG_W], -1, c.SL(l, S_VGP), 252, zS, T3, 252, 128);
     SGRL_TRY(run_gemm(c, g, sb));
     SGRL_TRY(inv_feature_fwd(f, st));
-    g = lin(c, c.SL(l, S_G1), 1024, zS, lp[L_G1_W], lp[L_G1_B], c.SL(l, S_A1), 256, zS, T, 256, 1024); g.relu = 1;
+    if (l == 0) SGRL_TRY(side_join(c, 0));
+    g = lin_fold(c, c.SL(l, S_G1), fold_offset(c.L, l, 0), lp[L_G1_B], c.SL(l, S_A1), 256, T, 256); g.relu = 1;
     SGRL_TRY(run_gemm(c, g));
     g = lin(c, c.SL(l, S_A1), 256, zS, lp[L_G2_W], lp[L_G2_B], ua, 256, zS, T, 128, 256);
     SGRL_TRY(run_gemm(c, g));
@@ -274,7 +315,7 @@ inline int net_forward(const NetCtx& c, const float* obs, long long zsObs, const
     f2.P1 = c.P(lp[L_GP2]); f2.P2 = c.P(lp[L_GP3]); f2.zsP = c.zsP;
     f2.Z = c.SL(l, S_Z2); f2.Z2 = c.SL(l, S_Z3); f2.G = c.SL(l, S_G2); f2.Fn = c.SL(l, S_F2); f2.zsAct = zS; f2.T = T; f2.nb = c.nb;
     SGRL_TRY(inv_feature_fwd(f2, st));
-    g = lin(c, c.SL(l, S_G2), 1024, zS, lp[L_FG1_W], lp[L_FG1_B], c.SL(l, S_A2), 256, zS, T, 256, 1024); g.relu = 1;
+    g = lin_fold(c, c.SL(l, S_G2), fold_offset(c.L, l, 1), lp[L_FG1_B], c.SL(l, S_A2), 256, T, 256); g.relu = 1;
     SGRL_TRY(run_gemm(c, g));
     g = lin(c, c.SL(l, S_A2), 256, zS, lp[L_FG2_W], lp[L_FG2_B], ub, 256, zS, T, 128, 256);
     SGRL_TRY(run_gemm(c, g));
@@ -304,7 +345,7 @@ inline int net_forward(const NetCtx& c, const float* obs, long long zsObs, const
   fh.P1 = c.P(Y.gp[G_GG_W]); fh.P2 = c.kind == ACTOR ? c.P(Y.gp[G_GPH_W]) : nullptr; fh.zsP = c.zsP;
   fh.Z = c.S(T_ZH); fh.Z2 = c.kind == ACTOR ? c.S(T_ZH2) : nullptr; fh.G = c.S(T_GH); fh.Fn = c.S(T_FH); fh.zsAct = zS; fh.T = T; fh.nb = c.nb;
   SGRL_TRY(inv_feature_fwd(fh, st));
-  GemmP g = lin(c, c.S(T_GH), 1024, zS, Y.gp[G_H1G_W], Y.gp[G_H1G_B], c.S(T_AH), 128, zS, T, 128, 1024); g.relu = 1;
+  GemmP g = lin_fold(c, c.S(T_GH), fold_offset(c.L, c.L, 0), Y.gp[G_H1G_B], c.S(T_AH), 128, T, 128); g.relu = 1;
   SGRL_TRY(run_gemm(c, g));
   g = lin(c, c.S(T_AH), 128, zS, Y.gp[G_H2G_W], Y.gp[G_H2G_B], c.S(T_UH), 256, zS, T, 128, 128);
   SGRL_TRY(run_gemm(c, g));
@@ -366,6 +407,19 @@ inline int net_backward(const NetCtx& c, const float* dOut, long long zsDo, int 
     return 0;
   };
 
+  // dW of a vec(G) consumer: dW'[Nw,GP_K] += dY^T Gp (+ bias column sum) on a side stream, unfolded at the end
+  auto side_w_fold = [&](const float* dY, int lddy, const float* Gp, long long fold_off, int M, int Nw, long long db_off) -> int {
+    if (!wg) return 0;
+    cudaStream_t ss;
+    SGRL_TRY(side_fork(c, &ss, -1, nullptr));
+    GemmP w = wgrad_fold(c, dY, lddy, Gp, fold_off, M, Nw);
+    SGRL_TRY(run_gemm(c, w, ss));
+    SGRL_TRY(colsum(c, dY, lddy, db_off, M, Nw, 1.f, ss));
+    return 0;
+  };
+  if (wg)
+    for (int z = 0; z < c.nb; ++z) SGRL_CUDA(cudaMemsetAsync(c.ws + c.wl.gf + z * c.zsW, 0, sizeof(float) * (size_t)fold_floats(c.L), st));
+
   // ---------------------------------------------------------------- heads + final norm (frame L)
   SGRL_TRY(zero_ws(c, f, W_DF1));   // dF of the head block
   float* dFh = W(W_DF1);
@@ -396,8 +450,8 @@ inline int net_backward(const NetCtx& c, const float* dOut, long long zsDo, int 
   g = dgrad(c, W(W_DUH), 256, Y.gp[G_H2G_W], 128, W(W_DA2), 128, T, 128, 128);
   g.mask = c.S(T_AH); g.zsMask = zS; g.ldmask = 128;
   SGRL_TRY(run_gemm(c, g));
-  SGRL_TRY(side_w(W(W_DA2), 128, c.S(T_GH), 1024, zS, Y.gp[G_H1G_W], 1024, T, 128, 1024, Y.gp[G_H1G_B]));
-  g = dgrad(c, W(W_DA2), 128, Y.gp[G_H1G_W], 1024, W(W_DG), 1024, T, 128, 1024);
+  SGRL_TRY(side_w_fold(W(W_DA2), 128, c.S(T_GH), fold_offset(c.L, c.L, 0), T, 128, Y.gp[G_H1G_B]));
+  g = dgrad_fold(c, W(W_DA2), 128, fold_offset(c.L, c.L, 0), W(W_DG), T, 128);
   SGRL_TRY(run_gemm(c, g));
   SGRL_TRY(inv_feature_bwd(W(W_DG), dFh, c.S(T_ZH), c.S(T_FH), W(W_DZ1), zS, zW, T, c.nb, st));
   // dVgF = dZh[:, :30] gg_proj[:, 8:] (+ dZh2[:, :30] g_proj[:, 8:])
@@ -472,8 +526,8 @@ inline int net_backward(const NetCtx& c, const float* dOut, long long zsDo, int 
     g = dgrad(c, W(W_DUB), 256, lp[L_FG2_W], 256, W(W_DA), 256, T, 128, 256);
     g.mask = c.SL(l, S_A2); g.zsMask = zS; g.ldmask = 256;
     SGRL_TRY(run_gemm(c, g));
-    SGRL_TRY(side_w(W(W_DA), 256, c.SL(l, S_G2), 1024, zS, lp[L_FG1_W], 1024, T, 256, 1024, lp[L_FG1_B]));
-    g = dgrad(c, W(W_DA), 256, lp[L_FG1_W], 1024, W(W_DG), 1024, T, 256, 1024);
+    SGRL_TRY(side_w_fold(W(W_DA), 256, c.SL(l, S_G2), fold_offset(c.L, l, 1), T, 256, lp[L_FG1_B]));
+    g = dgrad_fold(c, W(W_DA), 256, fold_offset(c.L, l, 1), W(W_DG), T, 256);
     SGRL_TRY(run_gemm(c, g));
     SGRL_TRY(inv_feature_bwd(W(W_DG), W(W_DF2), c.SL(l, S_Z2), c.SL(l, S_F2), W(W_DZ2), zS, zW, T, c.nb, st));
     // d(dV) = dVg' + dZ2[:, :30] g_proj2 + dZ3[:, :30] g_proj3
@@ -507,8 +561,8 @@ inline int net_backward(const NetCtx& c, const float* dOut, long long zsDo, int 
     g = dgrad(c, W(W_DUA), 256, lp[L_G2_W], 256, W(W_DA2), 256, T, 128, 256);
     g.mask = c.SL(l, S_A1); g.zsMask = zS; g.ldmask = 256;
     SGRL_TRY(run_gemm(c, g));
-    SGRL_TRY(side_w(W(W_DA2), 256, c.SL(l, S_G1), 1024, zS, lp[L_G1_W], 1024, T, 256, 1024, lp[L_G1_B]));
-    g = dgrad(c, W(W_DA2), 256, lp[L_G1_W], 1024, W(W_DG), 1024, T, 256, 1024);
+    SGRL_TRY(side_w_fold(W(W_DA2), 256, c.SL(l, S_G1), fold_offset(c.L, l, 0), T, 256, lp[L_G1_B]));
+    g = dgrad_fold(c, W(W_DA2), 256, fold_offset(c.L, l, 0), W(W_DG), T, 256);
     SGRL_TRY(run_gemm(c, g));
     SGRL_TRY(inv_feature_bwd(W(W_DG), W(W_DF1), c.SL(l, S_Z1), c.SL(l, S_F1), W(W_DZ1), zS, zW, T, c.nb, st));
     SGRL_TRY(side_w(W(W_DZ1), 32, Vg, 128, zS, lp[L_GPROJ], 128, T3, NPJ, 128));
@@ -534,6 +588,11 @@ inline int net_backward(const NetCtx& c, const float* dOut, long long zsDo, int 
     SGRL_TRY(run_gemm(c, g));
   }
   SGRL_TRY(side_join(c));
+  if (wg) {      // gradients of the folded weights -> (rows,1024) gradient tensors
+    const FoldDesc d = fold_desc(c);
+    launch_k(unfold_sym_kernel, dim3(32, d.n, c.nb), 256, 0, st, c.ws + c.wl.gf, c.zsW, c.grads, c.zsG, d);
+    SGRL_LAUNCH_OK();
+  }
   return 0;
 }
 
