@@ -35,23 +35,29 @@ constexpr int TC_CONV_THREADS = 32 * TC_CONV_WARPS;
 constexpr int TC_THREADS = 64 + TC_CONV_THREADS;              // warp0 TMA, warp1 MMA, warps 2.. converters/epilogue
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;                 // 16 KiB per A tile (hi or lo)
 
-template <int BN> struct TcCfg {
+// SM2 = the two-CTAs-per-SM variant for short-K tiles (<= 12 k-blocks) of launches with several tiles per SM: half the
+// shared memory (2 ring stages) and half the tensor memory (ONE accumulator for all three product terms + 2 A slots =
+// 256 columns), so that one CTA's prologue / pipeline fill / epilogue (TMEM read-back and the output burst) overlaps
+// the other CTA's MMAs on the same SM.  Measured motivation (tools/gemm_trace.py, 147456x768x256): 15.1 K cycles per
+// 128x128 tile of which 6.1 K are MMA time; 2.4 K startup and 4.8 K epilogue run with the tensor pipe idle.
+template <int BN, bool SM2 = false> struct TcCfg {
   static constexpr int B_BYTES = BN * TC_BK * 4;                    // one B tile (hi or lo)
   static constexpr int STAGE_BYTES = TC_A_BYTES + 2 * B_BYTES;      // [A raw | B raw/hi | B lo]
-  static constexpr int STAGES = BN == 128 ? 4 : 6;                  // 192 KiB of operand ring either way
+  static constexpr int STAGES = SM2 ? 2 : (BN == 128 ? 4 : 6);      // 192 KiB of operand ring (96 / 64 KiB for SM2)
   // The tensor core ACCUMULATES WITH TRUNCATION (measured on B200: signed bias -3e-8 per add, i.e.
   // -1.1e-5 relative at K=1024 with one accumulator; profiles/r01_accumulator_probe.txt).  The k-blocks are
   // therefore dealt round-robin onto NMAIN independent TMEM accumulators for the hi*hi terms, plus one for
   // the small lo*hi + hi*lo terms (whose truncation is 2^-11 smaller), and summed in fp32 RN in the epilogue.
-  static constexpr int NMAIN = BN == 128 ? 2 : 3;
-  static constexpr int ACC_COLS = (NMAIN + 1) * BN;                 // 384 | 256
+  static constexpr int NMAIN = SM2 ? 1 : (BN == 128 ? 2 : 3);
+  static constexpr int ACC_COLS = SM2 ? BN : (NMAIN + 1) * BN;      // 384 | 256 (SM2: the cross terms share the one accumulator:
+                                                                    // <= 144 truncating adds, ~4e-6 relative, measured in tests/test_gemm_gpu.py)
   // The A operand is fed from TENSOR MEMORY (tcgen05.mma "ts" form): with both operands in shared memory the
   // 128 B/cycle shared-memory path bounds the mainloop (MMA operand reads + TMA writes + converter traffic =
   // 136 KB per 12-MMA k-block at BN=64: 1100 cycles measured against a 384-cycle tensor-pipe floor;
   // profiles/r01b_mma_probe.txt).  TA_STAGES slots of 64 columns hold [hi 32 | lo 32] of one k-block.
-  static constexpr int TA_STAGES = (512 - ACC_COLS) / 64;           // 2 | 4
-  static constexpr int TMEM_COLS = 512;
-  static constexpr int UNROLL = BN == 128 ? 4 : 12;                 // lcm(STAGES, TA_STAGES, NMAIN)
+  static constexpr int TA_STAGES = SM2 ? 2 : (512 - ACC_COLS) / 64; // 2 | 4
+  static constexpr int TMEM_COLS = SM2 ? 256 : 512;
+  static constexpr int UNROLL = SM2 ? 2 : (BN == 128 ? 4 : 12);     // lcm(STAGES, TA_STAGES, NMAIN)
   static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
@@ -317,11 +323,11 @@ __device__ __noinline__ void tc_epi_generic(const GemmP& p, const EpiArgs& ea, u
 
 // BPRE: the B operand arrives already split (raw/hi + lo tensor maps over the weight arenas); otherwise the converter
 // warps also write B's lo part next to the landed tile.
-template <int BN, bool AMN, bool BMN, bool BPRE>
-__global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA,
-                                                                const __grid_constant__ CUtensorMap mapB,
-                                                                const __grid_constant__ CUtensorMap mapBlo, GemmP p) {
-  using Cfg = TcCfg<BN>;
+template <int BN, bool AMN, bool BMN, bool BPRE, bool SM2 = false>
+__global__ void __launch_bounds__(TC_THREADS, SM2 ? 2 : 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA,
+                                                                          const __grid_constant__ CUtensorMap mapB,
+                                                                          const __grid_constant__ CUtensorMap mapBlo, GemmP p) {
+  using Cfg = TcCfg<BN, SM2>;
   constexpr int STAGES = Cfg::STAGES, B_BYTES = Cfg::B_BYTES, STAGE_BYTES = Cfg::STAGE_BYTES, TA = Cfg::TA_STAGES, NMAIN = Cfg::NMAIN;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -414,7 +420,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
       // 64-bit descriptor = {lo word: addr>>4 | (LBO>>4)<<16, hi word: SBO>>4 | version 1<<14 | layout<<29}
       constexpr uint32_t B_HIW = (B_SBO >> 4) | (1u << 14) | (B_LAY << 29), B_LOW = (B_LBO >> 4) << 16;
       const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
-      const uint32_t acc_lo = tb + NMAIN * BN, tab = tb + Cfg::ACC_COLS;
+      const uint32_t acc_lo = SM2 ? tb : tb + NMAIN * BN, tab = tb + Cfg::ACC_COLS;
       const uint32_t bdesc0 = (((smem_base + TC_A_BYTES) >> 4) & 0x3FFFu) | B_LOW;
       // Measured (tools/mma_probe.cu, profiles/r01b_mma_probe.txt): the tensor pipe drains during ANY gap in the issue
       // stream (queue of ~1-2 MMAs), so every instruction between two MMAs is exposed.  The loop is therefore unrolled
@@ -435,7 +441,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
             const uint32_t a_hi = tab + t * 64, a_lo = a_hi + 32;
             const int ai = nrot == NMAIN ? (u % NMAIN) : (nrot == 1 ? 0 : (u & 1));   // UNR is even: (i0 + u) & 1 == u & 1
             const uint32_t acc_hi = tb + ai * BN;                          // main accumulators rotate per k-block (see TcCfg)
-            const uint32_t first_hi = (it > 0 || u >= nrot) ? 1u : 0u, first_lo = (it > 0 || u > 0) ? 1u : 0u;
+            const uint32_t first_hi = (it > 0 || u >= nrot) ? 1u : 0u, first_lo = (SM2 || it > 0 || u > 0) ? 1u : 0u;
             if (elect_one()) {
 #pragma unroll
               for (int k = 0; k < TC_BK / 8; ++k)
@@ -550,12 +556,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
         {
           // two TMEM loads in flight per wait; summed in fp32 RN
           uint32_t r0[32], r1[32];
+          if (SM2) {
+            tmem_ld32(arow + (uint32_t)c0, r0);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int j = 0; j < 32; ++j) sum[j] = __uint_as_float(r0[j]);
+          } else {
           tmem_ld32(arow + (uint32_t)(NMAIN * BN + c0), r0);
           tmem_ld32(arow + (uint32_t)c0, r1);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
           for (int j = 0; j < 32; ++j) sum[j] = __uint_as_float(r0[j]) + __uint_as_float(r1[j]);
-          if (nused > 1) {
+          }
+          if (!SM2 && nused > 1) {
             tmem_ld32(arow + (uint32_t)(BN + c0), r0);
             if (NMAIN > 2 && nused > 2) tmem_ld32(arow + (uint32_t)(2 * BN + c0), r1);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -660,17 +673,17 @@ inline bool gemm_tc_eligible(const GemmP& p) {
   return true;
 }
 
-template <int BN, bool AMN, bool BMN, bool BPRE>
+template <int BN, bool AMN, bool BMN, bool BPRE, bool SM2 = false>
 inline int gemm_tc_launch(const GemmP& p, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mbl, cudaStream_t st) {
-  auto kern = gemm_tc_kernel<BN, AMN, BMN, BPRE>;
+  auto kern = gemm_tc_kernel<BN, AMN, BMN, BPRE, SM2>;
   static bool attr_done = false;
   if (!attr_done) {
-    SGRL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN>::SMEM));
+    SGRL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN, SM2>::SMEM));
     attr_done = true;
   }
   dim3 grid(ceil_div(p.M, TC_BM) * ceil_div(p.N, BN), p.splitk, p.nb);
   prof_begin(PC_GEMM_TC, 2.0 * p.M * p.N * (double)p.K * p.nb, st);
-  launch_k(kern, grid, TC_THREADS, TcCfg<BN>::SMEM, st, ma, mb, mbl, p);
+  launch_k(kern, grid, TC_THREADS, TcCfg<BN, SM2>::SMEM, st, ma, mb, mbl, p);
   prof_end(st);
   SGRL_LAUNCH_OK();
   return 0;
@@ -744,6 +757,19 @@ inline int gemm_tc(const GemmP& p_in, cudaStream_t st) {
   if (p.Blo) {
     if (!p.transB) SGRL_TRY(make_tmap(&mbl, p.Blo, p.K, p.N, nzB, p.ldb, p.zsB, 32, BN, 0));
     else SGRL_TRY(make_tmap(&mbl, p.Blo, p.N, p.K, nzB, p.ldb, p.zsB, 32, 32, 1));
+  }
+  // two-CTAs-per-SM variant: short-K tiles, pre-split weights, K-major A, and enough tiles that SMs hold several of them.
+  // Its single accumulator takes 3x the truncating adds (measured: gradients of a B=100 critic step drift to 6e-4 on a few
+  // tensors when it is forced everywhere), so only passes that keep nothing for a backward (rollout / target networks:
+  // p.sm2_ok) may use it.  SGRL_TC_SM2: 0 never, 1 auto, 2 wherever the shape allows (tests); SGRL_TC_SM2_MIN: tile threshold
+  {
+    static const int sm2_mode = getenv("SGRL_TC_SM2") ? atoi(getenv("SGRL_TC_SM2")) : 1;
+    static const int sm2_min = getenv("SGRL_TC_SM2_MIN") ? atoi(getenv("SGRL_TC_SM2_MIN")) : 2 * NUM_SMS;
+    const long long ctas = (long long)ceil_div(p.M, TC_BM) * ceil_div(p.N, BN) * p.nb * sk;
+    if (sm2_mode && p.Blo && !p.transA && ceil_div(nkb, sk) <= 12 && (sm2_mode == 2 || (p.sm2_ok && ctas >= sm2_min))) {
+      if (BN == 128) return p.transB ? gemm_tc_launch<128, false, true, true, true>(p, ma, mb, mbl, st) : gemm_tc_launch<128, false, false, true, true>(p, ma, mb, mbl, st);
+      return p.transB ? gemm_tc_launch<64, false, true, true, true>(p, ma, mb, mbl, st) : gemm_tc_launch<64, false, false, true, true>(p, ma, mb, mbl, st);
+    }
   }
   if (BN == 128) return p.Blo ? gemm_tc_dispatch<128, true>(p, ma, mb, mbl, st) : gemm_tc_dispatch<128, false>(p, ma, mb, mbl, st);
   return p.Blo ? gemm_tc_dispatch<64, true>(p, ma, mb, mbl, st) : gemm_tc_dispatch<64, false>(p, ma, mb, mbl, st);

@@ -79,6 +79,7 @@ extern Side g_side;
 
 struct NetCtx {
   int kind, L, nb, T;
+  int keep;                               // 0: inference pass (nothing kept for a backward)
   NetLayout lay;
   const float* params; long long zsP;     // live arena; z-stride = lay.live_floats
   const float* phi; const float* plo;     // optional tf32 hi/lo split of the live arena (same layout) for the tcgen05 GEMMs
@@ -101,7 +102,11 @@ struct NetCtx {
 
 inline int run_gemm(const NetCtx& c, const GemmP& g, cudaStream_t st = nullptr) {
   if (!st) st = c.stream;
-  if (c.use_tc && gemm_tc_eligible(g)) return gemm_tc(g, st);
+  if (c.use_tc && gemm_tc_eligible(g)) {
+    if (c.keep) return gemm_tc(g, st);
+    GemmP gi = g; gi.sm2_ok = 1;
+    return gemm_tc(gi, st);
+  }
   return gemm_simt(g, st);
 }
 // stream for the next piece of weight-gradient work: a side stream that has been made to wait for everything

@@ -91,7 +91,7 @@ static int make_ctx(const SgrlNetCall* k, cudaStream_t st, NetCtx& c) {
   SGRL_CHECK(k->nb >= 1 && k->nb <= 4, "nb out of range");
   SGRL_CHECK(k->T >= 1 && k->G >= 1, "empty batch");
   SGRL_CHECK(k->params && k->stash && k->cu_limbs && k->relation && k->rank3, "null device pointer");
-  c.kind = k->kind; c.L = k->n_layers; c.nb = k->nb; c.T = k->T;
+  c.kind = k->kind; c.L = k->n_layers; c.nb = k->nb; c.T = k->T; c.keep = k->keep;
   c.lay = make_layout(k->kind, k->n_layers);
   c.params = k->params; c.zsP = c.lay.live_floats;
   SGRL_CHECK((k->params_hi == nullptr) == (k->params_lo == nullptr), "params_hi and params_lo go together");

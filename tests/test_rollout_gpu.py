@@ -84,3 +84,24 @@ def test_rollout_graph_sees_updated_weights():
     with torch.no_grad():
         want = ag.actor(torch.tensor(obs).cuda()).cpu().numpy()
     assert parity.rel_err(half, want) < 1e-6
+
+
+def test_large_batch_forward_two_cta_gemm_variant():
+    """At rollout sizes (several 128-row tiles per SM) the short-K projections of an inference pass run in the
+    two-CTAs-per-SM tcgen05 variant with ONE TMEM accumulator for all three 3xTF32 terms: same 1e-4 bar."""
+    ag, pa, _ = make_agent()
+    par = M.ALL["3d_walker_7_full"]
+    g = G.build_graph(par, device="cuda")
+    ag.change_morphology(g)
+    obs = synth.make_obs(8192, len(par), seed=21).cuda()              # 57 344 tokens: 448 row tiles
+    with torch.no_grad():
+        got = ag.actor(obs)
+        want = O.actor_forward({k: v.cuda() for k, v in pa.items()}, obs, g)
+    err = parity.rel_err(got, want)
+    print(f"rollout forward at 57k tokens: rel err {err:.2e}")
+    assert err < parity.RTOL
+    rot = synth.rotate_about_gravity(obs.cpu(), len(par), 0.7).cuda()
+    with torch.no_grad():
+        err_rot = parity.rel_err(ag.actor(rot), got)
+    print(f"rotation about gravity at 57k tokens: rel err {err_rot:.2e}")
+    assert err_rot < parity.RTOL_ROT
