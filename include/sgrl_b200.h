@@ -114,10 +114,11 @@ int sgrl_inv_feature_bwd(const float* dG, const float* dF, const float* Z, const
  * Outputs o (T,256), og (T,3,256), p (T,2,16). */
 int sgrl_attention_fwd(const float* qkv, const float* vgp, const float* gd, const float* rel_w, const float* rel_b,
                        const int32_t* cu_limbs, const int32_t* rel_off, const float* relation, int G,
+                       int max_limbs /* largest graph (2..16), 0 = unknown: sizes the shared-memory staging */,
                        float* o, float* og, float* p, sgrl_stream_t stream);
 int sgrl_attention_bwd(const float* qkv, const float* vgp, const float* gd, const float* p,
                        const float* d_o, const float* d_og, const int32_t* cu_limbs, const int32_t* rel_off,
-                       const float* relation, int G, float* dqkv, float* dvgp, float* drel_w /*nullable, accumulates*/,
+                       const float* relation, int G, int max_limbs, float* dqkv, float* dvgp, float* drel_w /*nullable, accumulates*/,
                        sgrl_stream_t stream);
 /* K3: C[M,N] = epi(alpha * A B^T): every nn.Linear call site.
  * trans_a/trans_b as in csrc/gemm_simt.cuh; bias/rowdiv nullable; relu 0/1; use_tc as above. */
@@ -157,6 +158,12 @@ int sgrl_adam_clip(float* p, const float* g, float* m, float* v, int64_t n, cons
 int sgrl_bump_step(int32_t* step, sgrl_stream_t stream);
 int sgrl_polyak(float* target, const float* source, int64_t n, float tau,
                 float* t_hi /*nullable: refreshed tf32 split of target[0:n_split]*/, float* t_lo, int64_t n_split, sgrl_stream_t stream);
+
+/* Call before recording an event on `stream` that another stream will wait on when the last work on `stream` was a
+ * kernel of this library and the stream is not being captured: enqueues an empty non-programmatic launch (see
+ * csrc/net.cuh, stream_fence: events recorded right after a programmatic-launch kernel did not reliably order the
+ * waiting stream in eager execution).  No-op during stream capture or with SGRL_PDL=0. */
+int sgrl_stream_fence(sgrl_stream_t stream);
 
 /* ---- K7: device-resident replay storage (common/buffer.py:35-126) --------
  * One transition = one packed row [obs (obs_dim) | action (act_dim) | next_obs (obs_dim) | reward | done] of

@@ -62,8 +62,8 @@ _PROTOS = {
     "sgrl_set_backward": (c_int, [C.POINTER(NetCall), c_f, c_i64, c_int, c_f, c_i64, c_f]),
     "sgrl_inv_feature_fwd": (c_int, [c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_int, c_f]),
     "sgrl_inv_feature_bwd": (c_int, [c_f, c_f, c_f, c_f, c_f, c_int, c_f]),
-    "sgrl_attention_fwd": (c_int, [c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_int, c_f, c_f, c_f, c_f]),
-    "sgrl_attention_bwd": (c_int, [c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_int, c_f, c_f, c_f, c_f]),
+    "sgrl_attention_fwd": (c_int, [c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_int, c_int, c_f, c_f, c_f, c_f]),
+    "sgrl_attention_bwd": (c_int, [c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_int, c_int, c_f, c_f, c_f, c_f]),
     "sgrl_gemm": (c_int, [c_f, c_int, c_int, c_f, c_int, c_int, c_f, c_int, c_int, c_int, c_int, C.c_float, c_f, c_f,
                           c_int, c_int, c_int, c_int, c_f]),
     "sgrl_gemm_presplit": (c_int, [c_f, c_int, c_int, c_f, c_f, c_int, c_int, c_f, c_int, c_int, c_int, c_int, C.c_float, c_f, c_f,
@@ -76,6 +76,7 @@ _PROTOS = {
     "sgrl_adam_clip": (c_int, [c_f, c_f, c_f, c_f, c_i64, c_f, c_f, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, c_f, c_f, c_f]),
     "sgrl_bump_step": (c_int, [c_f, c_f]),
     "sgrl_polyak": (c_int, [c_f, c_f, c_i64, C.c_float, c_f, c_f, c_i64, c_f]),
+    "sgrl_stream_fence": (c_int, [c_f]),
     "sgrl_replay_gather": (c_int, [c_f, c_i64, c_i64, c_f, c_int, c_int, c_int, c_f, c_f, c_f, c_f, c_f, c_f]),
     "sgrl_replay_scatter": (c_int, [c_f, c_i64, c_i64, c_f, c_f, c_int, c_f]),
 }

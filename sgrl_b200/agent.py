@@ -394,12 +394,14 @@ class Agent(nn.Module):
             check(lib.sgrl_td3_smooth_action(ptr(p.a_t), ptr(p.noise), ptr(p.next_action), float(a.noise_clip), float(a.max_action), T * 3,
                                              stream()))
             self.critic_target.forward_raw(tb, p.nobs, p.next_action, keep=False, nb=2, trusted_split=True, out=p.tq, stash=p.stash_ct)
+            check(lib.sgrl_stream_fence(stream()))       # eager runs only (no-op under capture): see csrc/net.cuh stream_fence
             p.ev_a.record(p.s1)
         # ---- chain C (stream s2, delayed actor step only): pi(s) — independent of the critic step           agent.py:167
         if actor_step:
             with torch.cuda.stream(p.s2):
                 p.s2.wait_event(p.ev_start)
                 self.actor.forward_raw(tb, p.obs, None, keep=True, trusted_split=True, out=p.pi, stash=p.stash_a)
+                check(lib.sgrl_stream_fence(stream()))
                 p.ev_c.record(p.s2)
         # ---- chain B (main): critic step                                                                    agent.py:142-156
         self.critic.forward_raw(tb, p.obs, p.act, keep=True, nb=2, trusted_split=True, out=p.q, stash=p.stash_c)

@@ -31,19 +31,31 @@ struct AttnGraphs {
 };
 inline int attn_rows(const AttnGraphs& gr) { return (gr.nmax >= 2 && gr.nmax <= MAXN) ? gr.nmax : MAXN; }
 
+// Ampere-style asynchronous copies global -> shared (LDGSTS): a thread issues all of its copies back to back and waits
+// once, instead of one exposed global-load latency per loop iteration (the first version staged a 9-limb graph with ~40
+// dependent load->store round trips per thread: 25 us per graph and CTA, 27 % of HBM at 147 K tokens).
+__device__ __forceinline__ void cp_async16(float* dst, const float* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async8(float* dst, const float* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+
 __device__ __forceinline__ void attn_stage_common(float* qs, float* vs, const float* __restrict__ QKV,
                                                   const float* __restrict__ VGP, const float* __restrict__ GD,
                                                   int t0, int n, int tid, int nthr) {
   for (int i = tid; i < n * 192; i += nthr) {
     const int tk = i / 192, c4 = (i % 192) * 4;
-    *reinterpret_cast<float4*>(qs + tk * A_RS + c4) = ldg4(QKV + (long long)(t0 + tk) * 768 + c4);
+    cp_async16(qs + tk * A_RS + c4, QKV + (long long)(t0 + tk) * 768 + c4);
   }
   // vg rows: (t, r, h) -> 126 learned channels, 8-byte aligned
   for (int i = tid; i < n * 6 * 63; i += nthr) {
     const int c2 = i % 63, rh = (i / 63) % 6, tk = i / (63 * 6);
     const int r = rh >> 1, h = rh & 1;
-    const float2 v = __ldg(reinterpret_cast<const float2*>(VGP + (long long)(t0 + tk) * 756 + r * 252 + h * 126) + c2);
-    *reinterpret_cast<float2*>(vs + tk * A_RS + r * 256 + h * 128 + c2 * 2) = v;
+    cp_async8(vs + tk * A_RS + r * 256 + h * 128 + c2 * 2, VGP + (long long)(t0 + tk) * 756 + r * 252 + h * 126 + c2 * 2);
   }
   for (int i = tid; i < n * 6; i += nthr) {
     const int tk = i / 6, r = (i % 6) >> 1, k = i & 1;
@@ -61,9 +73,12 @@ __global__ void __launch_bounds__(A_FWD_THREADS) attention_fwd_kernel(
   SGRL_PDL_ENTER();
   extern __shared__ __align__(16) float smem[];
   const int nr = (gr.nmax >= 2 && gr.nmax <= MAXN) ? gr.nmax : MAXN;
+  // (a second staging buffer with the next graph's copies in flight under the arithmetic was measured SLOWER: it halves
+  //  the CTAs per SM to 2 x 4 warps and the arithmetic phases are latency-bound: 1 506 vs 3 156 GB/s at 147 K tokens)
   float* qs = smem;                     // [nr][A_RS]   q | k | v
   float* vs = qs + nr * A_RS;           // [nr][A_RS]   vgx: [r][h][128]
-  float* S = vs + nr * A_RS;            // [2][16][16]
+  float* S = vs + nr * A_RS;            // [2][16][16]  scores
+  float* PT = S + 512;                  // [2][16][16]  probabilities, transposed: [h][j][i]
   const int tid = threadIdx.x, z = blockIdx.y;
   QKV += z * zsS; VGP += z * zsS; GD += z * zsS; O += z * zsS; OG += z * zsS; P += z * zsS;
   float wr[HEADS][3] = {{0, 0, 0}, {0, 0, 0}}, br[HEADS] = {0, 0};
@@ -78,6 +93,7 @@ __global__ void __launch_bounds__(A_FWD_THREADS) attention_fwd_kernel(
     const float* rel = has_bias ? gr.relation + (gr.rel_off ? gr.rel_off[g] : 0) : nullptr;
     __syncthreads();
     attn_stage_common(qs, vs, QKV, VGP, GD, t0, n, tid, A_FWD_THREADS);
+    cp_async_wait_all();
     __syncthreads();
     // ---- scores S[h][i][j] = q_i . k_j (+ bias)
     for (int idx = tid; idx < HEADS * n * n; idx += A_FWD_THREADS) {
@@ -98,7 +114,8 @@ __global__ void __launch_bounds__(A_FWD_THREADS) attention_fwd_kernel(
       S[(h * 16 + i) * 16 + j] = s;
     }
     __syncthreads();
-    // ---- softmax over the graph's own limbs: 16-lane shuffle groups, one row each
+    // ---- softmax over the graph's own limbs: 16-lane shuffle groups, one row each.  The probabilities are kept
+    // TRANSPOSED in shared memory (S[h][j][i]) so that the weighted sums below fetch P[0..15][j] with four 128-bit loads.
     for (int row = tid >> 4; row < HEADS * 16; row += A_FWD_THREADS / 16) {
       const int h = row >> 4, i = row & 15, j = tid & 15;
       const bool valid = (i < n) && (j < n);          // uniform per 16-lane group in i
@@ -111,36 +128,52 @@ __global__ void __launch_bounds__(A_FWD_THREADS) attention_fwd_kernel(
 #pragma unroll
       for (int o = 8; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o, 16);
       const float p = valid ? e / sum : 0.f;
-      S[row * 16 + j] = p;
+      PT[(h * 16 + j) * 16 + i] = p;
       if (i < n) P[(long long)(t0 + i) * 32 + h * 16 + j] = p;
     }
     __syncthreads();
-    // ---- weighted sums: thread = output column; 256 scalar-stream + 768 vector-stream columns
-    for (int col = tid; col < 1024; col += A_FWD_THREADS) {
-      const bool sc = col < 256;
-      const int cc = sc ? col : col - 256;
+    // ---- weighted sums: 256 scalar-stream + 768 vector-stream columns.  A thread owns 4 consecutive columns x all rows
+    // (64 accumulators): per key j one 128-bit load of the values and up to four of P^T[j][.] feed 64 FMAs (the first
+    // version re-read P from shared memory for every column: 17 loads per 16 FMAs, shared-memory bound at 27 % of HBM).
+    const int ng4 = (n + 3) >> 2;
+    for (int col4 = tid * 4; col4 < 1024; col4 += A_FWD_THREADS * 4) {
+      const bool sc = col4 < 256;
+      const int cc = sc ? col4 : col4 - 256;
       const int h = (cc & 255) >> 7;
       const float* src = sc ? qs + 512 + cc : vs + cc;
-      const float* Ph = S + h * 256;
-      float acc[MAXN];
+      const float* Ph = PT + h * 256;
+      float acc[4][MAXN];
 #pragma unroll
-      for (int i = 0; i < MAXN; ++i) acc[i] = 0.f;
+      for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int i = 0; i < MAXN; ++i) acc[c][i] = 0.f;
       for (int j = 0; j < n; ++j) {
-        const float vv = src[j * A_RS];
+        const float4 vv = *reinterpret_cast<const float4*>(src + j * A_RS);
 #pragma unroll
-        for (int i = 0; i < MAXN; ++i) acc[i] = fmaf(Ph[i * 16 + j], vv, acc[i]);   // rows i>=n hold p=0
+        for (int g4 = 0; g4 < MAXN / 4; ++g4) {
+          if (g4 < ng4) {
+            const float4 p4 = *reinterpret_cast<const float4*>(Ph + j * 16 + g4 * 4);
+            const float pv[4] = {p4.x, p4.y, p4.z, p4.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              acc[0][g4 * 4 + k] = fmaf(pv[k], vv.x, acc[0][g4 * 4 + k]);
+              acc[1][g4 * 4 + k] = fmaf(pv[k], vv.y, acc[1][g4 * 4 + k]);
+              acc[2][g4 * 4 + k] = fmaf(pv[k], vv.z, acc[2][g4 * 4 + k]);
+              acc[3][g4 * 4 + k] = fmaf(pv[k], vv.w, acc[3][g4 * 4 + k]);
+            }
+          }
+        }
       }
+      float* dst = sc ? O + (long long)t0 * 256 + cc : OG + (long long)t0 * 768 + cc;
+      const int ldo = sc ? 256 : 768;
 #pragma unroll
       for (int i = 0; i < MAXN; ++i)
-        if (i < n) {
-          if (sc) O[(long long)(t0 + i) * 256 + cc] = acc[i];
-          else OG[(long long)(t0 + i) * 768 + cc] = acc[i];
-        }
+        if (i < n) stg4(dst + (long long)i * ldo, make_float4(acc[0][i], acc[1][i], acc[2][i], acc[3][i]));
     }
   }
 }
 
-constexpr size_t attn_fwd_smem(int nr = MAXN) { return sizeof(float) * (2 * nr * A_RS + 512); }
+constexpr size_t attn_fwd_smem(int nr = MAXN) { return sizeof(float) * (2 * nr * A_RS + 1024); }
 constexpr size_t attn_bwd_smem(int nr = MAXN) { return sizeof(float) * (2 * nr * A_RS + nr * A_DS + 1024 + 16); }
 
 // Backward.  Inputs dO (T,256), dOG (T,768) [workspace], saved P, QKV, VGP, GD [stash].
@@ -172,13 +205,13 @@ __global__ void __launch_bounds__(A_BWD_THREADS) attention_bwd_kernel(
     attn_stage_common(qs, vs, QKV, VGP, GD, t0, n, tid, A_BWD_THREADS);
     for (int i = tid; i < n * 256; i += A_BWD_THREADS) {
       const int tk = i >> 8, c4 = (i & 255) * 4;
-      const float4 v = c4 < 256 ? ldg4(dO + (long long)(t0 + tk) * 256 + c4) : ldg4(dOG + (long long)(t0 + tk) * 768 + (c4 - 256));
-      *reinterpret_cast<float4*>(ds + tk * A_DS + c4) = v;
+      cp_async16(ds + tk * A_DS + c4, c4 < 256 ? dO + (long long)(t0 + tk) * 256 + c4 : dOG + (long long)(t0 + tk) * 768 + (c4 - 256));
     }
     for (int i = tid; i < 512; i += A_BWD_THREADS) {
       const int h = i >> 8, ii = (i >> 4) & 15, j = i & 15;
       Ps[i] = (ii < n) ? __ldg(P + (long long)(t0 + ii) * 32 + h * 16 + j) : 0.f;
     }
+    cp_async_wait_all();
     __syncthreads();
     // ---- dP[h][i][j] = dO_i . v_j + sum_r dOG_i,r . vgx_j,r
     for (int idx = tid; idx < HEADS * n * n; idx += A_BWD_THREADS) {

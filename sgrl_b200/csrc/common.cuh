@@ -35,6 +35,13 @@ inline bool pdl_enabled() {
 #define SGRL_PDL_TRIGGER() asm volatile("griddepcontrol.launch_dependents;" ::: "memory")
 #define SGRL_PDL_WAIT() asm volatile("griddepcontrol.wait;" ::: "memory")
 #define SGRL_PDL_ENTER() do { SGRL_PDL_TRIGGER(); SGRL_PDL_WAIT(); } while (0)
+// streams on which kernels are launched WITHOUT the programmatic attribute (experiment knob SGRL_PDL_SIDE=0: the side lanes)
+extern cudaStream_t g_nopdl_streams[32];
+extern int g_nopdl_count;
+inline bool pdl_stream_ok(cudaStream_t st) {
+  for (int i = 0; i < g_nopdl_count; ++i) if (g_nopdl_streams[i] == st) return false;
+  return true;
+}
 template <typename... KArgs, typename... Args>
 inline void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
   cudaLaunchConfig_t cfg;
@@ -43,7 +50,7 @@ inline void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem,
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cfg.attrs = at; cfg.numAttrs = (pdl_enabled() && pdl_stream_ok(st)) ? 1 : 0;
   cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 

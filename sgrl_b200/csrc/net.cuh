@@ -44,6 +44,21 @@ inline WsLayout make_ws(int n_layers, long long T) {
 // ---- side streams: weight-gradient work (dW GEMMs, bias column sums) forks off the data-gradient chain ----------
 // fork = record an event on the main stream, make a side stream wait for it, launch there; join = main waits for
 // every side stream.  Under CUDA-graph capture this becomes plain fork/join edges of the graph.  SGRL_SIDE=0 disables.
+// Measured on B200 (CUDA 12.9 / driver 580, tests/test_backward_gpu.py, humanoid B=100): with programmatic dependent launch
+// on, a cross-stream dependency built from cudaEventRecord (timing-disabled event) right after a kernel launched with the
+// programmatic attribute + cudaStreamWaitEvent does NOT reliably order the waiting stream after that kernel in EAGER
+// execution — a forked weight-gradient GEMM occasionally read a dY the data-gradient chain was still writing (errors of
+// 1e-4..6e-2 in a few layer-1 gradients, 3 runs out of 4; SGRL_PDL=0 or SGRL_SIDE=0 cured it).  A plain, non-programmatic
+// launch between the kernel and the event restores the ordering (0 failures in 4), so outside stream capture every fork /
+// join event is preceded by this empty kernel.  Inside a captured graph the same record/wait pairs become explicit full
+// dependency edges and no fence is needed (Agent.update's hot path is the replayed graph).  SGRL_FORK_FENCE=0 disables.
+__global__ void fence_kernel() {}
+inline int stream_fence(cudaStream_t st) {
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  SGRL_CUDA(cudaStreamIsCapturing(st, &cs));
+  if (cs == cudaStreamCaptureStatusNone && pdl_enabled()) fence_kernel<<<1, 1, 0, st>>>();
+  return 0;
+}
 struct SideSet {
   static constexpr int N = 4;              // lane 0: independent branch of the dependency chain; lanes 1..3: dW / bias-gradient work
   cudaStream_t s[N]; cudaEvent_t fork_ev; cudaEvent_t join_ev[N];
@@ -52,7 +67,7 @@ struct SideSet {
 struct Side {
   static constexpr int NSETS = 6;          // one set per distinct main stream seen (main, the agent's two forward streams, a capture stream, ...)
   SideSet set[NSETS];
-  bool made = false; int enabled = -1; int nowners = 0;
+  bool made = false; int enabled = -1; int nowners = 0; int fork_fence = 0;
   int init() {
     if (enabled < 0) { const char* e = getenv("SGRL_SIDE"); enabled = e ? atoi(e) : 1; }
     if (!made && enabled) {              // everything is created up front: nothing but event record/wait happens later (capture-safe)
@@ -65,6 +80,11 @@ struct Side {
         SGRL_CUDA(cudaEventCreateWithFlags(&set[k].fork_ev, cudaEventDisableTiming));
         set[k].rr = 0; set[k].owner = nullptr;
       }
+      { const char* e = getenv("SGRL_PDL_SIDE");
+        if (e && atoi(e) == 0)
+          for (int k = 0; k < NSETS && g_nopdl_count + SideSet::N <= 32; ++k)
+            for (int i = 0; i < SideSet::N; ++i) g_nopdl_streams[g_nopdl_count++] = set[k].s[i]; }
+      { const char* e = getenv("SGRL_FORK_FENCE"); fork_fence = e ? atoi(e) : 1; }
       made = true;
     }
     return 0;
@@ -120,6 +140,7 @@ inline int side_fork(const NetCtx& c, cudaStream_t* out, int lane = -1, cudaStre
   if (i < 0) { i = 1 + ss.rr; ss.rr = (ss.rr + 1) % (SideSet::N - 1); }
   if (!from) from = c.stream;
   if (from == ss.s[i]) { *out = from; return 0; }      // same queue: already ordered
+  if (sd.fork_fence) SGRL_TRY(stream_fence(from));
   SGRL_CUDA(cudaEventRecord(ss.fork_ev, from));
   SGRL_CUDA(cudaStreamWaitEvent(ss.s[i], ss.fork_ev, 0));
   ss.used[i] = true;
@@ -133,6 +154,7 @@ inline int side_join(const NetCtx& c, int lane = -1) {
   SideSet& ss = sd.of(c.stream);
   for (int i = 0; i < SideSet::N; ++i) {
     if (!ss.used[i] || (lane >= 0 && i != lane)) continue;
+    if (sd.fork_fence) SGRL_TRY(stream_fence(ss.s[i]));
     SGRL_CUDA(cudaEventRecord(ss.join_ev[i], ss.s[i]));
     SGRL_CUDA(cudaStreamWaitEvent(c.stream, ss.join_ev[i], 0));
     ss.used[i] = false;

@@ -11,6 +11,8 @@ long long g_launches = 0;
 Prof g_prof;
 long long* g_gemm_trace = nullptr;
 int g_pdl = -1;
+cudaStream_t g_nopdl_streams[32];
+int g_nopdl_count = 0;
 Side g_side;
 }
 using namespace sgrl;
@@ -140,19 +142,19 @@ int sgrl_inv_feature_bwd(const float* dG, const float* dF, const float* Z, const
 }
 
 int sgrl_attention_fwd(const float* qkv, const float* vgp, const float* gd, const float* rel_w, const float* rel_b,
-                       const int32_t* cu_limbs, const int32_t* rel_off, const float* relation, int G, float* o, float* og, float* p,
-                       sgrl_stream_t stream) {
+                       const int32_t* cu_limbs, const int32_t* rel_off, const float* relation, int G, int max_limbs, float* o, float* og,
+                       float* p, sgrl_stream_t stream) {
   SGRL_CHECK(qkv && vgp && gd && cu_limbs && o && og && p, "null pointer");
   SGRL_CHECK((rel_w == nullptr) || (rel_b && relation), "bias needs rel_b and relation");
-  AttnGraphs gr{cu_limbs, rel_off, relation, G, 0, 0};
+  AttnGraphs gr{cu_limbs, rel_off, relation, G, 0, max_limbs};
   return attention_fwd(qkv, vgp, gd, o, og, p, 0, rel_w, rel_b, 0, gr, 1, ST(stream));
 }
 
 int sgrl_attention_bwd(const float* qkv, const float* vgp, const float* gd, const float* p, const float* d_o, const float* d_og,
-                       const int32_t* cu_limbs, const int32_t* rel_off, const float* relation, int G, float* dqkv, float* dvgp,
-                       float* drel_w, sgrl_stream_t stream) {
+                       const int32_t* cu_limbs, const int32_t* rel_off, const float* relation, int G, int max_limbs, float* dqkv,
+                       float* dvgp, float* drel_w, sgrl_stream_t stream) {
   SGRL_CHECK(qkv && vgp && gd && p && d_o && d_og && cu_limbs && dqkv && dvgp, "null pointer");
-  AttnGraphs gr{cu_limbs, rel_off, relation, G, 0, 0};
+  AttnGraphs gr{cu_limbs, rel_off, relation, G, 0, max_limbs};
   return attention_bwd(qkv, vgp, gd, p, 0, d_o, d_og, dqkv, dvgp, 0, drel_w, 0, gr, 1, ST(stream));
 }
 
@@ -254,6 +256,8 @@ int sgrl_polyak(float* target, const float* source, int64_t n, float tau, float*
   SGRL_LAUNCH_OK();
   return 0;
 }
+
+int sgrl_stream_fence(sgrl_stream_t stream) { return stream_fence(ST(stream)); }
 
 int sgrl_replay_gather(const float* rows, int64_t row_floats, int64_t capacity, const int64_t* idx, int batch, int obs_dim, int act_dim,
                        float* obs, float* action, float* next_obs, float* reward, float* done, sgrl_stream_t stream) {
