@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(A_FWD_THREADS) attention_fwd_kernel(
 }
 
 constexpr size_t attn_fwd_smem(int nr = MAXN) { return sizeof(float) * (2 * nr * A_RS + 1024); }
-constexpr size_t attn_bwd_smem(int nr = MAXN) { return sizeof(float) * (2 * nr * A_RS + nr * A_DS + 1024 + 16); }
+constexpr size_t attn_bwd_smem(int nr = MAXN) { return sizeof(float) * (2 * nr * A_RS + nr * A_DS + 1536 + 16); }
 
 // Backward.  Inputs dO (T,256), dOG (T,768) [workspace], saved P, QKV, VGP, GD [stash].
 // Outputs dQKV (T,768) — gradient w.r.t. the *stored* (post /F, post-scale) q|k|v — and
@@ -191,7 +191,8 @@ __global__ void __launch_bounds__(A_BWD_THREADS) attention_bwd_kernel(
   float* ds = vs + nr * A_RS;            // [nr][A_DS]  dO | dOG
   float* Ps = ds + nr * A_DS;            // [2][16][16]
   float* dS = Ps + 512;                  // [2][16][16]
-  float* wacc = dS + 512;                // [6]
+  float* dST = dS + 512;                 // [2][16][16]  transposed: [h][j][i]
+  float* wacc = dST + 512;               // [6]
   const int tid = threadIdx.x, z = blockIdx.y;
   QKV += z * zsS; VGP += z * zsS; GD += z * zsS; P += z * zsS;
   dO += z * zsW; dOG += z * zsW; dQKV += z * zsW; dVGP += z * zsW;
@@ -248,6 +249,7 @@ __global__ void __launch_bounds__(A_BWD_THREADS) attention_bwd_kernel(
       for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o, 16);
       const float v = p * (dp - s);
       dS[row * 16 + j] = v;
+      dST[((row >> 4) * 16 + j) * 16 + i] = v;
       if (has_bias && valid) {
         const int h = row >> 4;
         const float* rr = rel + (i * n + j) * 3;
@@ -257,40 +259,56 @@ __global__ void __launch_bounds__(A_BWD_THREADS) attention_bwd_kernel(
       }
     }
     __syncthreads();
-    // ---- column sweeps: 256 dq + 256 dk + 256 dv + 768 dvg columns
-    for (int task = tid; task < 1536; task += A_BWD_THREADS) {
-      const int kind = task < 768 ? task >> 8 : 3;
-      const int col = kind < 3 ? (task & 255) : task - 768;
+    // ---- column sweeps: 256 dq + 256 dk + 256 dv + 768 dvg columns.  A thread owns 4 consecutive columns x all rows
+    // (64 accumulators); per source row one 128-bit load of the operand and up to four of the weight row feed 64 FMAs
+    // (same restructuring as the forward's weighted sums: the first version re-read the weights for every column).
+    const int ng4 = (n + 3) >> 2;
+    for (int task = tid; task < 384; task += A_BWD_THREADS) {
+      const int col4 = task * 4;
+      const int kind = col4 < 768 ? col4 >> 8 : 3;
+      const int col = kind < 3 ? (col4 & 255) : col4 - 768;
       const int h = (col & 255) >> 7;
-      float acc[MAXN];
+      // kind 0: dq_i = sum_j dS[i][j] k_j (weights dS^T[j][.]); 1: dk_j = sum_i dS[i][j] q_i; 2: dv_j = sum_i P[i][j] dO_i; 3: dvg_j = sum_i P[i][j] dOG_i
+      const float* W = (kind == 0 ? dST : kind == 1 ? dS : Ps) + h * 256;
+      const float* src = kind == 0 ? qs + 256 + col : kind == 1 ? qs + col : kind == 2 ? ds + col : ds + 256 + col;
+      const int stride = kind < 2 ? A_RS : A_DS;
+      float acc[4][MAXN];
 #pragma unroll
-      for (int i = 0; i < MAXN; ++i) acc[i] = 0.f;
-      if (kind == 0) {            // dq_i = sum_j dS[i][j] k_j
-        for (int j = 0; j < n; ++j) {
-          const float kv = qs[j * A_RS + 256 + col];
+      for (int c = 0; c < 4; ++c)
 #pragma unroll
-          for (int i = 0; i < MAXN; ++i) acc[i] = fmaf(dS[(h * 16 + i) * 16 + j], kv, acc[i]);
-        }
-      } else {                    // dk_j, dv_j, dvg_j = sum_i W[i][j] x_i   (W = dS for dk, P otherwise)
-        const float* W = (kind == 1 ? dS : Ps) + h * 256;
-        const float* src = kind == 1 ? qs + col : kind == 2 ? ds + col : ds + 256 + col;
-        const int stride = kind == 1 ? A_RS : A_DS;
-        for (int i = 0; i < n; ++i) {
-          const float xv = src[i * stride];
+        for (int i = 0; i < MAXN; ++i) acc[c][i] = 0.f;
+      for (int sr = 0; sr < n; ++sr) {
+        const float4 xv = *reinterpret_cast<const float4*>(src + sr * stride);
 #pragma unroll
-          for (int j = 0; j < MAXN; ++j) acc[j] = fmaf(W[i * 16 + j], xv, acc[j]);
+        for (int g4 = 0; g4 < MAXN / 4; ++g4) {
+          if (g4 < ng4) {
+            const float4 w4 = *reinterpret_cast<const float4*>(W + sr * 16 + g4 * 4);
+            const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              acc[0][g4 * 4 + k] = fmaf(wv[k], xv.x, acc[0][g4 * 4 + k]);
+              acc[1][g4 * 4 + k] = fmaf(wv[k], xv.y, acc[1][g4 * 4 + k]);
+              acc[2][g4 * 4 + k] = fmaf(wv[k], xv.z, acc[2][g4 * 4 + k]);
+              acc[3][g4 * 4 + k] = fmaf(wv[k], xv.w, acc[3][g4 * 4 + k]);
+            }
+          }
         }
       }
       if (kind < 3) {
+        float* dst = dQKV + (long long)t0 * 768 + kind * 256 + col;
 #pragma unroll
         for (int i = 0; i < MAXN; ++i)
-          if (i < n) dQKV[(long long)(t0 + i) * 768 + kind * 256 + col] = acc[i];
+          if (i < n) stg4(dst + (long long)i * 768, make_float4(acc[0][i], acc[1][i], acc[2][i], acc[3][i]));
       } else {
-        const int c = col & 127, r = col >> 8;
+        const int c = col & 127, r = col >> 8;      // channels 126,127 of each (r, h) are inputs (gravity, direction): no gradient
         if (c < 126) {
+          float* dst = dVGP + (long long)t0 * 756 + r * 252 + h * 126 + c;   // 8-byte aligned
 #pragma unroll
           for (int i = 0; i < MAXN; ++i)
-            if (i < n) dVGP[(long long)(t0 + i) * 756 + r * 252 + h * 126 + c] = acc[i];
+            if (i < n) {
+              *reinterpret_cast<float2*>(dst + (long long)i * 756) = make_float2(acc[0][i], acc[1][i]);
+              if (c + 2 < 126) *reinterpret_cast<float2*>(dst + (long long)i * 756 + 2) = make_float2(acc[2][i], acc[3][i]);
+            }
         }
       }
     }

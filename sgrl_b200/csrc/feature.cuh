@@ -32,6 +32,23 @@ constexpr TriLut make_tri_lut() {
   return t;
 }
 __constant__ TriLut c_tri = make_tri_lut();
+// the 144 four-column chunks (i, jq) of the 32x32 Gram that touch the upper triangle (4*jq + 3 >= i), row-major; code = i << 8 | jq
+constexpr int GCH = 144, GCH_PAD = 160;
+struct ChunkLut { unsigned short v[GCH_PAD]; };
+constexpr ChunkLut make_chunk_lut() {
+  ChunkLut t{};
+  int n = 0;
+  for (int i = 0; i < CH; ++i)
+    for (int jq = 0; jq < CH / 4; ++jq)
+      if (4 * jq + 3 >= i) t.v[n++] = (unsigned short)((i << 8) | jq);
+  for (; n < GCH_PAD; ++n) t.v[n] = 0xFFFFu;
+  return t;
+}
+__constant__ ChunkLut c_chunk = make_chunk_lut();
+
+__device__ __forceinline__ void feat_cp_async16(float* dst, const float* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
 
 constexpr int F_TT = 32;        // tokens per tile (16-token tiles at 4 CTAs/SM measured slower: 2 204 vs 2 783 GB/s at 147 K tokens)
 constexpr int F_THREADS = 256;
@@ -41,7 +58,9 @@ struct FeatSmem {
   static constexpr int C = 128 + CE;
   static constexpr int PJ = 32 * NPROJ;
   static constexpr int XS = 3 * C + 4;  // padded token stride (floats)
-  static constexpr size_t bytes = sizeof(float) * ((size_t)C * PJ + (size_t)F_TT * XS + (size_t)F_TT * 3 * PJ + F_TT * 8 + GP_K / 2);
+  // Ps | Xs (the projected Z tile later overwrites the head of Xs) | gd | chunk table
+  static constexpr size_t bytes = sizeof(float) * ((size_t)C * PJ + (size_t)F_TT * XS + F_TT * 8 + GCH_PAD / 2);
+  static_assert(F_TT * 3 * PJ <= F_TT * XS, "Z tile must fit into the X staging it replaces");
 };
 
 // X = [V0 (T,3,8) if CE==8 | Xg (T,3,128)], P1/P2 (30,C) row-major, gd (T,3,2)
@@ -58,9 +77,9 @@ __global__ void __launch_bounds__(F_THREADS) inv_feature_fwd_kernel(
   extern __shared__ __align__(16) float smem[];
   float* Ps = smem;                       // [C][PJ]
   float* Xs = Ps + C * PJ;                // [TT][XS]
-  float* Zs = Xs + F_TT * XS;             // [TT][3][PJ]
-  float* gds = Zs + F_TT * 3 * PJ;        // [TT][8] (6 used)
-  unsigned short* tri = reinterpret_cast<unsigned short*>(gds + F_TT * 8);   // [GP_K] (divergent lookups: not from constant memory)
+  float* Zs = Xs;                         // [TT][3][PJ]: written over the X tile once every thread has finished projecting
+  float* gds = Xs + F_TT * XS;            // [TT][8] (6 used)
+  unsigned short* chk = reinterpret_cast<unsigned short*>(gds + F_TT * 8);   // [GCH_PAD] (divergent lookups: not from constant memory)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, z = blockIdx.y;
   Xg += z * zsXg; gd += z * zsGd; P1 += z * zsP;
   if (CE) V0 += z * zsV0;
@@ -68,7 +87,7 @@ __global__ void __launch_bounds__(F_THREADS) inv_feature_fwd_kernel(
   Z += z * zsAct; G += z * zsAct; Fn += z * zsAct;
   if (NPROJ == 2) Z2 += z * zsAct;
 
-  for (int i = tid; i < GP_K; i += F_THREADS) tri[i] = c_tri.v[i];
+  for (int i = tid; i < GCH_PAD; i += F_THREADS) chk[i] = c_chunk.v[i];
   // stage P transposed: Ps[c][j] = P[j][c]; columns 30,31 (and 62,63) are zero
   for (int i = tid; i < C * PJ; i += F_THREADS) {
     const int j = i / C, c = i % C;        // coalesced along c in global
@@ -82,12 +101,12 @@ __global__ void __launch_bounds__(F_THREADS) inv_feature_fwd_kernel(
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int t0 = tile * F_TT;
     __syncthreads();   // previous tile fully consumed (and Ps staged on first pass)
-    // ---- stage X tile (coalesced float4 over the 128-wide part)
+    // ---- stage X tile: asynchronous 16-byte copies, all of a thread's 12 in flight at once
     for (int i = tid; i < F_TT * 3 * 32; i += F_THREADS) {
       const int tk = i / 96, rem = i % 96, r = rem / 32, c4 = (rem % 32) * 4;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (t0 + tk < T) v = ldg4(Xg + ((long long)(t0 + tk) * 3 + r) * 128 + c4);
-      *reinterpret_cast<float4*>(&Xs[tk * XS + r * C + CE + c4]) = v;
+      float* dst = &Xs[tk * XS + r * C + CE + c4];
+      if (t0 + tk < T) feat_cp_async16(dst, Xg + ((long long)(t0 + tk) * 3 + r) * 128 + c4);
+      else *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     if (CE) {
       for (int i = tid; i < F_TT * 24; i += F_THREADS) {
@@ -99,15 +118,23 @@ __global__ void __launch_bounds__(F_THREADS) inv_feature_fwd_kernel(
       const int tk = i / 6;
       gds[tk * 8 + i % 6] = (t0 + tk < T) ? __ldg(gd + (long long)(t0 + tk) * 6 + i % 6) : 0.f;
     }
+    asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();
-    // ---- projection: each thread owns (token, 4 output channels) x 3 spatial rows
-    for (int w = tid; w < F_TT * JQ; w += F_THREADS) {
-      const int tk = w / JQ, jq = w % JQ;
-      float acc[3][4];
+    // ---- projection: each thread owns (token, 4 output channels) x 3 spatial rows, NW of them; results stay in registers.
+    // lane = token, warp = channel quad: the P loads are warp-uniform (one broadcast wavefront) and the X loads are
+    // conflict-free (token rows 4 banks apart); with lanes = 8 channel quads x 4 tokens every 128-bit load cost four
+    // wavefronts and the phase ran at the shared-memory limit (7 loads per 48 FMAs).
+    constexpr int NW = F_TT * JQ / F_THREADS;
+    static_assert(NW * F_THREADS == F_TT * JQ && F_TT == 32, "work items per thread; lane = token");
+    float acc[NW][3][4];
+#pragma unroll
+    for (int u = 0; u < NW; ++u) {
+      const int w = tid + u * F_THREADS;
+      const int tk = w & 31, jq = w >> 5;
 #pragma unroll
       for (int r = 0; r < 3; ++r)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[r][j] = 0.f;
+        for (int j = 0; j < 4; ++j) acc[u][r][j] = 0.f;
       const float* xr = Xs + tk * XS;
       const float* pj = Ps + jq * 4;
 #pragma unroll 2
@@ -121,20 +148,26 @@ __global__ void __launch_bounds__(F_THREADS) inv_feature_fwd_kernel(
 #pragma unroll
           for (int r = 0; r < 3; ++r) {
             const float xv = cc == 0 ? x[r].x : cc == 1 ? x[r].y : cc == 2 ? x[r].z : x[r].w;
-            acc[r][0] = fmaf(xv, pv.x, acc[r][0]);
-            acc[r][1] = fmaf(xv, pv.y, acc[r][1]);
-            acc[r][2] = fmaf(xv, pv.z, acc[r][2]);
-            acc[r][3] = fmaf(xv, pv.w, acc[r][3]);
+            acc[u][r][0] = fmaf(xv, pv.x, acc[u][r][0]);
+            acc[u][r][1] = fmaf(xv, pv.y, acc[u][r][1]);
+            acc[u][r][2] = fmaf(xv, pv.z, acc[u][r][2]);
+            acc[u][r][3] = fmaf(xv, pv.w, acc[u][r][3]);
           }
         }
       }
       if ((jq & 7) == 7) {   // channels 30,31 of each Z are [gravity, direction]
 #pragma unroll
-        for (int r = 0; r < 3; ++r) { acc[r][2] = gds[tk * 8 + r * 2 + 0]; acc[r][3] = gds[tk * 8 + r * 2 + 1]; }
+        for (int r = 0; r < 3; ++r) { acc[u][r][2] = gds[tk * 8 + r * 2 + 0]; acc[u][r][3] = gds[tk * 8 + r * 2 + 1]; }
       }
+    }
+    __syncthreads();   // every thread is done with the X tile: Z may overwrite it
+#pragma unroll
+    for (int u = 0; u < NW; ++u) {
+      const int w = tid + u * F_THREADS;
+      const int tk = w & 31, jq = w >> 5;
 #pragma unroll
       for (int r = 0; r < 3; ++r)
-        *reinterpret_cast<float4*>(&Zs[(tk * 3 + r) * PJ + jq * 4]) = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+        *reinterpret_cast<float4*>(&Zs[(tk * 3 + r) * PJ + jq * 4]) = make_float4(acc[u][r][0], acc[u][r][1], acc[u][r][2], acc[u][r][3]);
     }
     __syncthreads();
     // ---- write Z (and Z') coalesced
@@ -146,26 +179,38 @@ __global__ void __launch_bounds__(F_THREADS) inv_feature_fwd_kernel(
         stg4((which ? Z2 : Z) + ((long long)t0 * 3 + row) * 32 + q * 4, v);
       }
     }
-    // ---- Gram (upper triangle) + Frobenius norm: one warp per token, 17 x 32 coalesced outputs
+    // ---- Gram (upper triangle) + Frobenius norm: one warp per token.  The 144 four-column chunks (i, jq) that touch
+    // the triangle are dealt to the lanes in row-major order: 3 scalar + 3 128-bit loads and 12 FMAs per chunk
+    // (the per-element table walk of the first packed version cost 7 shared loads per output).
     for (int tk = warp; tk < F_TT; tk += F_THREADS / 32) {
       if (t0 + tk >= T) break;
       const float* zr = Zs + tk * 3 * PJ;
       float ss = 0.f;
       float* g = G + (long long)(t0 + tk) * GP_K;
 #pragma unroll
-      for (int n = 0; n < GP_K / 32; ++n) {
-        const int p = n * 32 + lane;
-        const unsigned code = tri[p];
-        float o = 0.f;
-        if (code != 0xFFFFu) {
-          const int i = code >> 8, j = code & 255;
-          o = zr[i] * zr[j];
-          o = fmaf(zr[PJ + i], zr[PJ + j], o);
-          o = fmaf(zr[2 * PJ + i], zr[2 * PJ + j], o);
-          ss = fmaf(i == j ? o : 2.f * o, o, ss);     // ||G||_F^2 over the full symmetric matrix
+      for (int n = 0; n < GCH_PAD / 32; ++n) {
+        const unsigned code = chk[n * 32 + lane];
+        if (code == 0xFFFFu) continue;
+        const int i = code >> 8, jq = code & 255;
+        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+          const float zi = zr[r * PJ + i];
+          const float4 zj = *reinterpret_cast<const float4*>(zr + r * PJ + jq * 4);
+          o.x = fmaf(zi, zj.x, o.x); o.y = fmaf(zi, zj.y, o.y); o.z = fmaf(zi, zj.z, o.z); o.w = fmaf(zi, zj.w, o.w);
         }
-        g[p] = o;
+        const int j0 = jq * 4;
+        float* gr = g + (i * CH - (i * (i - 1)) / 2 - i + j0);     // &g[tri_index(i, j0)] when j0 >= i
+        const float ov[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (j0 + k >= i) {
+            gr[k] = ov[k];
+            ss = fmaf(j0 + k == i ? ov[k] : 2.f * ov[k], ov[k], ss);     // ||G||_F^2 over the full symmetric matrix
+          }
+        }
       }
+      if (lane < GP_K - GP) g[GP + lane] = 0.f;
       ss = warp_sum(ss);
       if (lane == 0) Fn[t0 + tk] = sqrtf(ss) + 1.0f;
     }
@@ -189,7 +234,8 @@ inline int inv_feature_fwd_launch(const FeatFwdP& p, cudaStream_t st) {
     attr_done = true;
   }
   const int ntiles = ceil_div(p.T, F_TT);
-  const int gx = ntiles < 2 * NUM_SMS ? ntiles : 2 * NUM_SMS;
+  const int per_sm = (int)((227 * 1024) / (S::bytes + 1024)) < 4 ? (int)((227 * 1024) / (S::bytes + 1024)) : 4;
+  const int gx = ntiles < per_sm * NUM_SMS ? ntiles : per_sm * NUM_SMS;
   // algorithmic bytes per token: read X (12*C) + gd (24), write G (4*GP_K = 2176: packed triangle) + F (4) + Z (384 per projection)
   prof_begin(PC_FEATURE, (double)p.T * p.nb * (12.0 * S::C + 24 + 4.0 * GP_K + 4 + 384.0 * NPROJ), st);
   launch_k(kern, dim3(gx, p.nb), F_THREADS, S::bytes, st, p.Xg, p.zsXg, p.V0, p.zsV0, p.gd, p.zsGd, p.P1, p.P2, p.zsP,
