@@ -341,25 +341,18 @@ __global__ void __launch_bounds__(256) fold_sym_kernel(const float* __restrict__
   }
 }
 
-// gradient of the fold: dW[o][32i+j] += dW'[o][p], dW[o][32j+i] += dW'[o][p]  (G symmetric: both get the same value)
+// gradient of the fold: dW[o][32a+b] += dW'[o][p(min(a,b), max(a,b))]  (G symmetric: both orderings get the same value).
+// One thread per element of the (rows,1024) gradient: coalesced read-modify-write, the triangle is gathered (L2-resident).
 __global__ void __launch_bounds__(256) unfold_sym_kernel(const float* __restrict__ gf, long long zsW, float* __restrict__ grads, long long zsG, FoldDesc d) {
   SGRL_PDL_ENTER();
-  __shared__ unsigned short tri[GP_K];
-  for (int i = threadIdx.x; i < GP_K; i += 256) tri[i] = c_tri.v[i];
-  __syncthreads();
   const int m = blockIdx.y, z = blockIdx.z;
   const float* src = gf + z * zsW + d.dst[m];
   float* G = grads + z * zsG + d.src[m];
-  const int total = d.rows[m] * GP_K;
+  const int total = d.rows[m] * (CH * CH);
   for (int idx = blockIdx.x * 256 + threadIdx.x; idx < total; idx += gridDim.x * 256) {
-    const int o = idx / GP_K, p = idx - o * GP_K;
-    const unsigned code = tri[p];
-    if (code == 0xFFFFu) continue;
-    const int i = code >> 8, j = code & 255;
-    const float v = src[idx];
-    float* g = G + (long long)o * (CH * CH);
-    g[i * CH + j] += v;
-    if (i != j) g[j * CH + i] += v;
+    const int o = idx >> 10, a = (idx >> 5) & 31, b = idx & 31;
+    const int lo = min(a, b), hi = max(a, b);
+    G[idx] += __ldg(src + (long long)o * GP_K + tri_index(lo, hi));
   }
 }
 

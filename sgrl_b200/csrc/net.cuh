@@ -229,7 +229,7 @@ inline GemmP wgrad_fold(const NetCtx& c, const float* dY, int lddy, const float*
 }
 inline int fold_weights(const NetCtx& c, cudaStream_t st) {
   const FoldDesc d = fold_desc(c);
-  launch_k(fold_sym_kernel, dim3(32, d.n, c.nb), 256, 0, st, c.params, c.zsP, c.stash + c.st.wf, c.zsS, c.st.wf_plane, c.phi ? 1 : 0, d);
+  launch_k(fold_sym_kernel, dim3(48, d.n, c.nb), 256, 0, st, c.params, c.zsP, c.stash + c.st.wf, c.zsS, c.st.wf_plane, c.phi ? 1 : 0, d);
   SGRL_LAUNCH_OK();
   return 0;
 }
@@ -617,7 +617,7 @@ inline int net_backward(const NetCtx& c, const float* dOut, long long zsDo, int 
   SGRL_TRY(side_join(c));
   if (wg) {      // gradients of the folded weights -> (rows,1024) gradient tensors
     const FoldDesc d = fold_desc(c);
-    launch_k(unfold_sym_kernel, dim3(32, d.n, c.nb), 256, 0, st, c.ws + c.wl.gf, c.zsW, c.grads, c.zsG, d);
+    launch_k(unfold_sym_kernel, dim3(64, d.n, c.nb), 256, 0, st, c.ws + c.wl.gf, c.zsW, c.grads, c.zsG, d);
     SGRL_LAUNCH_OK();
   }
   return 0;
