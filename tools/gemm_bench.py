@@ -38,8 +38,8 @@ def main():
     dev = "cuda"
     g = torch.Generator(device=dev).manual_seed(0)
     # (name, M, N, K) forward Y = X W^T ; dgrad dX = dY W (M, K<-N) ; wgrad dW = dY^T X
-    lin = [("G1", T, 256, 1024), ("G2", T, 128, 256), ("QKV", T, 768, 256), ("VG", 3 * T, 252, 128), ("NGO", T, 128, 256),
-           ("GO", 3 * T, 128, 256), ("L3L1", T, 512, 256), ("L4", T, 1024, 256), ("L2", T, 128, 256), ("H1G", T, 128, 1024),
+    lin = [("G1", T, 256, 544), ("G2", T, 128, 256), ("QKV", T, 768, 256), ("VG", 3 * T, 252, 128), ("NGO", T, 128, 256),
+           ("GO", 3 * T, 128, 256), ("L3L1", T, 512, 256), ("L4", T, 1024, 256), ("L2", T, 128, 256), ("H1G", T, 128, 544),
            ("H2G", T, 128, 128)]
     print(f"# T={T} tokens, {nrep} launches each; us = device time per launch, CUDA graph of back-to-back launches, warm L2")
     print(f"# {'shape':34s} {'tc us':>8s} {'pre us':>8s} {'simt us':>8s} {'tc TF':>7s} {'pre TF':>7s} {'simt TF':>7s}  err tc/pre/simt")
