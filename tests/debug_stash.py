@@ -1,5 +1,5 @@
 """Not a test: prints per-intermediate and per-gradient errors of the CUDA path vs the oracle.
-usage (on the GPU box): python tests/debug_gpu.py [morph] [B] [use_tc]"""
+usage (on the GPU box): python tests/debug_stash.py [morph] [B] [use_tc]"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
