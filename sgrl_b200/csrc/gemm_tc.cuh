@@ -714,7 +714,7 @@ inline int gemm_tc(const GemmP& p_in, cudaStream_t st) {
   // Block times are the measured mainloop periods (tools/gemm_trace.py), the fixed part covers prologue, pipeline
   // fill and epilogue.  The step runs several kernels concurrently (three forward chains, dW GEMMs on side streams),
   // so what matters is SM-time (CTAs x duration) more than the duration of one kernel alone: the "wave" is therefore
-  // a third of the machine, not 148 (swept on B200: tools/sweep.sh, 6.27 ms/update at 48 vs 7.0 ms at 148).  A caller passes splitk > 1 to say "the epilogue is linear and C is pre-zeroed/accumulated":
+  // a third of the machine, not 148 (swept on B200, tools/sweep_tiles.sh: 5.36 ms/update at 32, 5.49 at 48, 6.23 at 148; profiles/r01n_tile_sweep.txt).  A caller passes splitk > 1 to say "the epilogue is linear and C is pre-zeroed/accumulated":
   // only then may K be split (atomics); the factor itself is chosen here.
   const int nkb = ceil_div(p.K, TC_BK);
   int BN = 64, sk = 1;
@@ -725,7 +725,7 @@ inline int gemm_tc(const GemmP& p_in, cudaStream_t st) {
       Tune t;
       t.blk64 = env("SGRL_TC_BLK64", 860.0); t.blk128 = env("SGRL_TC_BLK128", 960.0);
       t.fix64 = env("SGRL_TC_FIX64", 3000.0); t.fix128 = env("SGRL_TC_FIX128", 4000.0);
-      t.split_fix = env("SGRL_TC_SPLITFIX", 1500.0); t.wave = (int)env("SGRL_TC_WAVE", 48.0);
+      t.split_fix = env("SGRL_TC_SPLITFIX", 1500.0); t.wave = (int)env("SGRL_TC_WAVE", 32.0);
       return t;
     }();
     const bool may_split = p.splitk > 1;
