@@ -719,13 +719,13 @@ inline int gemm_tc(const GemmP& p_in, cudaStream_t st) {
   const int nkb = ceil_div(p.K, TC_BK);
   int BN = 64, sk = 1;
   {
-    struct Tune { double blk64, blk128, fix64, fix128, split_fix; int wave; };
+    struct Tune { double blk64, blk128, fix64, fix128, split_fix; int wave, wave_split; };
     static const Tune tn = [] {
       auto env = [](const char* k, double d) { const char* e = getenv(k); return e ? atof(e) : d; };
       Tune t;
       t.blk64 = env("SGRL_TC_BLK64", 860.0); t.blk128 = env("SGRL_TC_BLK128", 960.0);
       t.fix64 = env("SGRL_TC_FIX64", 3000.0); t.fix128 = env("SGRL_TC_FIX128", 4000.0);
-      t.split_fix = env("SGRL_TC_SPLITFIX", 1500.0); t.wave = (int)env("SGRL_TC_WAVE", 32.0);
+      t.split_fix = env("SGRL_TC_SPLITFIX", 1500.0); t.wave = (int)env("SGRL_TC_WAVE", 32.0); t.wave_split = (int)env("SGRL_TC_WAVE_SPLIT", (double)t.wave);
       return t;
     }();
     const bool may_split = p.splitk > 1;
@@ -737,7 +737,8 @@ inline int gemm_tc(const GemmP& p_in, cudaStream_t st) {
       const int sk_max = may_split ? (nkb / 4 < 1 ? 1 : (nkb / 4 > 64 ? 64 : nkb / 4)) : 1;
       for (int k = 1; k <= sk_max; ++k) {
         const long long ctas = base * k;
-        const double waves = (double)((ctas + tn.wave - 1) / tn.wave);
+        const int wave = may_split ? tn.wave_split : tn.wave;      // weight-gradient GEMMs (side lanes) may be given a different share
+        const double waves = (double)((ctas + wave - 1) / wave);
         const double cost = waves * (fixed + (k > 1 ? tn.split_fix : 0.0) + ceil_div(nkb, k) * blk);
         if (cost < best * 0.98) { best = cost; BN = bn; sk = k; }
       }
@@ -765,8 +766,9 @@ inline int gemm_tc(const GemmP& p_in, cudaStream_t st) {
   {
     static const int sm2_mode = getenv("SGRL_TC_SM2") ? atoi(getenv("SGRL_TC_SM2")) : 1;
     static const int sm2_min = getenv("SGRL_TC_SM2_MIN") ? atoi(getenv("SGRL_TC_SM2_MIN")) : 2 * NUM_SMS;
+    static const int sm2_maxkb = getenv("SGRL_TC_SM2_MAXKB") ? atoi(getenv("SGRL_TC_SM2_MAXKB")) : 12;     // k-blocks on the one accumulator
     const long long ctas = (long long)ceil_div(p.M, TC_BM) * ceil_div(p.N, BN) * p.nb * sk;
-    if (sm2_mode && p.Blo && !p.transA && ceil_div(nkb, sk) <= 12 && (sm2_mode == 2 || (p.sm2_ok && ctas >= sm2_min))) {
+    if (sm2_mode && p.Blo && !p.transA && ceil_div(nkb, sk) <= sm2_maxkb && (sm2_mode == 2 || (p.sm2_ok && ctas >= sm2_min))) {
       if (BN == 128) return p.transB ? gemm_tc_launch<128, false, true, true, true>(p, ma, mb, mbl, st) : gemm_tc_launch<128, false, false, true, true>(p, ma, mb, mbl, st);
       return p.transB ? gemm_tc_launch<64, false, true, true, true>(p, ma, mb, mbl, st) : gemm_tc_launch<64, false, false, true, true>(p, ma, mb, mbl, st);
     }
