@@ -314,7 +314,7 @@ __device__ __noinline__ void tc_epi_generic(const GemmP& p, const EpiArgs& ea, u
       if (ea.res1) v += ea.res1[(long long)(4 * it) * p.ldr1 + c0 + e];
       if (ea.res2) v += ea.res2[(long long)(4 * it) * p.ldr2 + c0 + e];
       float* c = ea.C + (long long)(4 * it) * p.ldc + c0 + e;
-      if (p.splitk > 1) atomicAdd(c, v);
+      if (p.splitk > 1 && !p.csk) atomicAdd(c, v);
       else if (p.accumulate) *c += v;
       else *c = v;
     }
@@ -512,11 +512,78 @@ __global__ void __launch_bounds__(TC_THREADS, SM2 ? 2 : 1) gemm_tc_kernel(const 
         s += 2; if (s >= STAGES) { s -= STAGES; ph ^= 1u; }
         t += 2; if (t >= TA) { t -= TA; pht ^= 1u; }
       }
-      // ===================== epilogue: TMEM -> registers -> smem transpose -> coalesced global =====================
-      // 8 warps: warp w owns TMEM lane quarter w & 3 (hardware rule) and column half (w - 2) >> 2 of the tile
-      mbar_wait(acc_bar, 0);
+      mbar_wait(acc_bar, 0);                       // every MMA of this CTA has retired: accumulators complete, ring stages idle
       tc_fence_after();
       if (tid == 64) TC_STAMP(2);
+    }
+  }
+  // ===================== cluster split-K (p.csk): the CTAs of a (1, splitk, 1) cluster each accumulated a K range of the
+  // SAME tile; ranks > 0 hand their partial sums to rank 0 through distributed shared memory and rank 0 runs the
+  // (possibly non-linear) epilogue.  For projections with few tiles and a long K (K = 544..1024 at 2 304 tokens: 36 CTAs
+  // walking 17-32 k-blocks) this spreads the serial k-loop over 2-3 SMs without the pre-zeroed C / atomics that plain
+  // split-K needs.  Slot layout in rank 0's idle ring: [32-column chunk][float4 k][128 rows] (conflict-free both ways).
+  constexpr uint32_t CSK_SLOT0 = 65536u, CSK_SLOT = 128u * BN * 4u;
+  static_assert(SM2 || CSK_SLOT0 + 2 * CSK_SLOT <= (uint32_t)(STAGES * STAGE_BYTES), "two partial-sum slots must fit into the idle ring");
+  const bool csk = !SM2 && p.csk != 0;
+  uint32_t crank = 0;
+  if (csk) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+  // sum of this CTA's accumulators for one 32-column chunk (thread = tile row = TMEM lane)
+  const int q_e = warp & 3, g_e = (warp - 2) >> 2;
+  const int nused_e = min(nrot, nloc);         // main accumulators that received at least one k-block
+  const uint32_t arow_e = tmem_base + ((uint32_t)(q_e * 32) << 16);
+  auto load_sum = [&](int c0, float (&sum)[32]) {
+    uint32_t r0[32], r1[32];
+    if (SM2) {
+      tmem_ld32(arow_e + (uint32_t)c0, r0);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+      for (int j = 0; j < 32; ++j) sum[j] = __uint_as_float(r0[j]);
+    } else {
+      // two TMEM loads in flight per wait; summed in fp32 RN
+      tmem_ld32(arow_e + (uint32_t)(NMAIN * BN + c0), r0);
+      tmem_ld32(arow_e + (uint32_t)c0, r1);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+      for (int j = 0; j < 32; ++j) sum[j] = __uint_as_float(r0[j]) + __uint_as_float(r1[j]);
+      if (nused_e > 1) {
+        tmem_ld32(arow_e + (uint32_t)(BN + c0), r0);
+        if (NMAIN > 2 && nused_e > 2) tmem_ld32(arow_e + (uint32_t)(2 * BN + c0), r1);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int j = 0; j < 32; ++j) sum[j] += __uint_as_float(r0[j]);
+        if (NMAIN > 2 && nused_e > 2) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) sum[j] += __uint_as_float(r1[j]);
+        }
+      }
+    }
+  };
+  if (csk) {
+    // B1: every CTA of the cluster is past its main loop (rank 0's ring stages may now be overwritten)
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    if (crank != 0 && warp >= 2 && nloc > 0) {
+      const int row = q_e * 32 + lane;
+#pragma unroll 1
+      for (int c0 = g_e * (BN / 2); c0 < (g_e + 1) * (BN / 2); c0 += 32) {
+        float sum[32];
+        load_sum(c0, sum);
+        const uint32_t local = smem_base + CSK_SLOT0 + (crank - 1) * CSK_SLOT + (uint32_t)(((c0 >> 5) * 8) * 128 + row) * 16u;
+        uint32_t remote;
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(0u));
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(remote + (uint32_t)k * 2048u), "f"(sum[4 * k]),
+                       "f"(sum[4 * k + 1]), "f"(sum[4 * k + 2]), "f"(sum[4 * k + 3]) : "memory");
+      }
+    }
+    // B2: the partial sums have landed in rank 0's shared memory
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  }
+  if (nloc > 0 && warp >= 2 && (!csk || crank == 0)) {
+    {
+      // ===================== epilogue: TMEM -> registers -> smem transpose -> coalesced global =====================
+      // 8 warps: warp w owns TMEM lane quarter w & 3 (hardware rule) and column half (w - 2) >> 2 of the tile
+      const int g = g_e, q = q_e;
       const int hf = g;                            // column half
       const uint32_t stg = smem_base + (warp - 2) * (32 * TC_EPI_LD * 4);   // pipeline stages are idle now (shared address)
       const int cq = lane & 7, rsub = lane >> 3;
@@ -539,7 +606,7 @@ __global__ void __launch_bounds__(TC_THREADS, SM2 ? 2 : 1) gemm_tc_kernel(const 
       int ekind;
       {
         const bool lin = !p.rowdiv && !p.mask && !p.res1 && !p.res2 && p.colscale_n == 0;
-        if (p.splitk > 1) ekind = 5;
+        if (p.splitk > 1 && !csk) ekind = 5;
         else if (p.accumulate) ekind = (lin && !p.relu && !p.bias) ? 4 : 6;
         else if (lin) ekind = 0;
         else if (p.rowdiv && !p.mask && !p.res1 && !p.res2) ekind = 1;
@@ -547,36 +614,18 @@ __global__ void __launch_bounds__(TC_THREADS, SM2 ? 2 : 1) gemm_tc_kernel(const 
         else if (p.res1 && !p.rowdiv && !p.mask && p.colscale_n == 0 && !p.relu && !p.bias) ekind = 3;
         else ekind = 6;
       }
-      const int nused = min(nrot, nloc);       // main accumulators that received at least one k-block
-      const uint32_t arow = tmem_base + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
       for (int c0 = hf * (BN / 2); c0 < (hf + 1) * (BN / 2); c0 += 32) {
         if (n0 + c0 >= p.N) break;
         float sum[32];
-        {
-          // two TMEM loads in flight per wait; summed in fp32 RN
-          uint32_t r0[32], r1[32];
-          if (SM2) {
-            tmem_ld32(arow + (uint32_t)c0, r0);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        load_sum(c0, sum);
+        if (csk) {
+          const uint32_t slot = smem_base + CSK_SLOT0 + (uint32_t)(((c0 >> 5) * 8) * 128 + q * 32 + lane) * 16u;
+          for (uint32_t r = 0; r + 1 < (uint32_t)p.splitk; ++r) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) sum[j] = __uint_as_float(r0[j]);
-          } else {
-          tmem_ld32(arow + (uint32_t)(NMAIN * BN + c0), r0);
-          tmem_ld32(arow + (uint32_t)c0, r1);
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-          for (int j = 0; j < 32; ++j) sum[j] = __uint_as_float(r0[j]) + __uint_as_float(r1[j]);
-          }
-          if (!SM2 && nused > 1) {
-            tmem_ld32(arow + (uint32_t)(BN + c0), r0);
-            if (NMAIN > 2 && nused > 2) tmem_ld32(arow + (uint32_t)(2 * BN + c0), r1);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-            for (int j = 0; j < 32; ++j) sum[j] += __uint_as_float(r0[j]);
-            if (NMAIN > 2 && nused > 2) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) sum[j] += __uint_as_float(r1[j]);
+            for (int k = 0; k < 8; ++k) {
+              const float4 v = lds128(slot + r * CSK_SLOT + (uint32_t)k * 2048u);
+              sum[4 * k] += v.x; sum[4 * k + 1] += v.y; sum[4 * k + 2] += v.z; sum[4 * k + 3] += v.w;
             }
           }
         }
@@ -683,6 +732,18 @@ inline int gemm_tc_launch(const GemmP& p, const CUtensorMap& ma, const CUtensorM
   }
   dim3 grid(ceil_div(p.M, TC_BM) * ceil_div(p.N, BN), p.splitk, p.nb);
   prof_begin(PC_GEMM_TC, 2.0 * p.M * p.N * (double)p.K * p.nb, st);
+  if (p.csk) {      // thread-block cluster along the split-K dimension (+ programmatic dependent launch as everywhere)
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid; cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = TcCfg<BN, SM2>::SMEM; cfg.stream = st;
+    cudaLaunchAttribute at[2];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 1; at[0].val.clusterDim.y = (unsigned)p.splitk; at[0].val.clusterDim.z = 1;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = (pdl_enabled() && pdl_stream_ok(st)) ? 2 : 1;
+    cudaLaunchKernelEx(&cfg, kern, ma, mb, mbl, p);
+  } else
   launch_k(kern, grid, TC_THREADS, TcCfg<BN, SM2>::SMEM, st, ma, mb, mbl, p);
   prof_end(st);
   SGRL_LAUNCH_OK();
@@ -745,6 +806,23 @@ inline int gemm_tc(const GemmP& p_in, cudaStream_t st) {
     }
   }
   p.splitk = sk;
+  p.csk = 0;
+  {
+    // cluster split-K for launches that may NOT use atomics (non-linear epilogue or C not pre-zeroed), have few tiles and a
+    // long K: 2-3 CTAs of a cluster share one tile's k-loop (SGRL_TC_CSK=0 disables; _MAXT: most tiles, _MINKB: fewest k-blocks).
+    // Measured (tools/gemm_bench.py, tools/sweep_csk.sh; profiles/r01o_*): alone, dgrad 2304x256x1024 drops 22.2 -> 16.7 us and
+    // 2304x256x768 18.2 -> 15.0 us, but the two cluster barriers + DSMEM hand-over cost ~4.5 us, so K = 544 gains nothing
+    // (14.5 -> 13.7 us) and with every eligible launch clustered the whole update got SLOWER (5.45 vs 5.37 ms: clusters of
+    // full-SM CTAs are harder to place next to the other streams' kernels).  Hence the conservative defaults: K >= 768, <= 40 tiles.
+    static const int csk_on = getenv("SGRL_TC_CSK") ? atoi(getenv("SGRL_TC_CSK")) : 1;
+    static const int csk_maxt = getenv("SGRL_TC_CSK_MAXT") ? atoi(getenv("SGRL_TC_CSK_MAXT")) : 40;
+    static const int csk_minkb = getenv("SGRL_TC_CSK_MINKB") ? atoi(getenv("SGRL_TC_CSK_MINKB")) : 24;
+    const long long tiles = (long long)ceil_div(p.M, TC_BM) * ceil_div(p.N, BN) * p.nb;
+    if (csk_on && p_in.splitk <= 1 && sk == 1 && nkb >= csk_minkb && tiles <= csk_maxt) {
+      p.splitk = (tiles * 3 <= 2 * csk_maxt && nkb >= 3 * csk_minkb / 2) ? 3 : 2;
+      p.csk = 1;
+    }
+  }
   p.vecE = host_vec_ok(p.C, p.ldc, p.zsC) && (!p.mask || host_vec_ok(p.mask, p.ldmask, p.zsMask)) &&
            (!p.res1 || host_vec_ok(p.res1, p.ldr1, p.zsR1)) && (!p.res2 || host_vec_ok(p.res2, p.ldr2, p.zsR2));
   const long long nzA = p.zsA ? p.nb : 1, nzB = p.zsB ? p.nb : 1;
@@ -768,7 +846,7 @@ inline int gemm_tc(const GemmP& p_in, cudaStream_t st) {
     static const int sm2_min = getenv("SGRL_TC_SM2_MIN") ? atoi(getenv("SGRL_TC_SM2_MIN")) : 2 * NUM_SMS;
     static const int sm2_maxkb = getenv("SGRL_TC_SM2_MAXKB") ? atoi(getenv("SGRL_TC_SM2_MAXKB")) : 12;     // k-blocks on the one accumulator
     const long long ctas = (long long)ceil_div(p.M, TC_BM) * ceil_div(p.N, BN) * p.nb * sk;
-    if (sm2_mode && p.Blo && !p.transA && ceil_div(nkb, sk) <= sm2_maxkb && (sm2_mode == 2 || (p.sm2_ok && ctas >= sm2_min))) {
+    if (!p.csk && sm2_mode && p.Blo && !p.transA && ceil_div(nkb, sk) <= sm2_maxkb && (sm2_mode == 2 || (p.sm2_ok && ctas >= sm2_min))) {
       if (BN == 128) return p.transB ? gemm_tc_launch<128, false, true, true, true>(p, ma, mb, mbl, st) : gemm_tc_launch<128, false, false, true, true>(p, ma, mb, mbl, st);
       return p.transB ? gemm_tc_launch<64, false, true, true, true>(p, ma, mb, mbl, st) : gemm_tc_launch<64, false, false, true, true>(p, ma, mb, mbl, st);
     }
