@@ -137,3 +137,47 @@ def test_select_action_matches_forward():
     assert isinstance(a, np.ndarray) and a.shape == (1, 3 * len(par)) and a.dtype == np.float32
     ref = O.actor_forward(pa, torch.tensor(obs, dtype=torch.float32)[None], G.build_graph(par))
     assert parity.rel_err(a, ref) < parity.RTOL
+
+
+def _arena_grads(mod):
+    """{name: gradient view} out of a module's flat gradient arena (what Agent.update's backward kernels wrote)."""
+    names = {id(p): k for k, p in mod.named_parameters()}
+    ga, live = mod.grad_arena(), mod._nb * mod._live
+    return {names[id(p)]: (ga[a:a + n].view(p.shape) if a < live else None) for p, a, n in mod._slots}
+
+
+def test_replayed_graph_gradients_equal_eager_gradients():
+    """Race detector for the captured update: two agents with identical state take the same eight steps (humanoid-9,
+    B=100, the size where a cross-stream ordering hazard once showed), one replaying the captured CUDA graphs
+    (iterations 2-7), the other running every launch eagerly.  The forward passes are deterministic and the only
+    run-to-run freedom in the backward is the order of the split-K atomics (~1e-7), so the raw gradients of both must
+    agree far below the parity bar; a forked weight-gradient GEMM reading a half-written dY would not.
+
+    (Comparing LATER steps tensor by tensor against an fp64 oracle is not meaningful: of the ~6 M relu evaluations of a
+    step a handful have |pre-activation| < 1e-6 of their row scale, and their sign - hence a gradient contribution of up
+    to 1e-2 of one sample - is decided by fp32 summation order; tests/debug_relu_masks.py lists them.  Fresh-weight
+    gradients are checked against the oracle in tests/test_backward_gpu.py.)"""
+    ag, _, _ = make_agent()
+    eg, _, _ = make_agent()
+    eg.use_graphs = False
+    par = M.ALL["3d_humanoid_9_full"]
+    g = G.build_graph(par, device="cuda")
+    ag.change_morphology(g); eg.change_morphology(g)
+    B = 100
+    for it in range(8):
+        # both start every step from bit-identical state (the atomics-order noise of the previous step would otherwise grow,
+        # through a relu kink, into a 1e-4 difference within a few steps)
+        eg.load_state_dict(ag.state_dict())
+        eg.critic_optimizer.load_state_dict(ag.critic_optimizer.state_dict())
+        eg.actor_optimizer.load_state_dict(ag.actor_optimizer.state_dict())
+        b = {k: v.cuda() for k, v in synth.make_batch(B, len(par), seed=50 + it).items()}
+        noise = torch.randn(B, 27, generator=torch.Generator().manual_seed(100 + it)).cuda() * 0.2
+        la, le = ag.update(b, it, noise=noise), eg.update(b, it, noise=noise)
+        assert abs(la["loss/critic_loss"].item() - le["loss/critic_loss"].item()) <= 1e-6 * abs(le["loss/critic_loss"].item()), it
+        assert parity.rel_err(ag.critic.grad_arena(), eg.critic.grad_arena()) < 1e-5, it
+        if it % 2 == 0:
+            assert parity.rel_err(ag.actor.grad_arena(), eg.actor.grad_arena()) < 1e-5, it
+        for ma, me in ((ag.critic, eg.critic), (ag.actor, eg.actor), (ag.critic_target, eg.critic_target)):
+            assert parity.rel_err(ma.full_arena, me.full_arena) < 1e-6, it
+    plan = next(iter(ag._plans.values()))
+    assert set(plan.graphs) == {True, False} and not eg._plans[next(iter(eg._plans))].graphs
