@@ -167,6 +167,8 @@ class ReplayBuffer(object):
         for t, w in ((obs, self.obs_dim), (action, self.action_dim), (next_obs, self.obs_dim), (reward, 1), (done, 1)):
             if t.numel() != B * w or not t.is_contiguous() or t.dtype != torch.float32:
                 raise ValueError(f"gather_into: expected a contiguous fp32 buffer of {B}x{w}, got {tuple(t.shape)}")
+        if B == 0:           # an empty buffer samples an empty batch (buffer.py:88-91 clamps batch_size to max_sample_size)
+            return 0
         check(lib.sgrl_replay_gather(ptr(self.rows), self.row_floats, self.max_buffer_size, ptr(idx), B, self.obs_dim, self.action_dim,
                                      ptr(obs), ptr(action), ptr(next_obs), ptr(reward), ptr(done), stream()), "sgrl_replay_gather")
         return B

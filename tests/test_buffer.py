@@ -100,6 +100,9 @@ def test_host_logic_matches_oracle_on_cpu_storage():
     buf.resize(60); assert buf.max_buffer_size == 60 and buf.rows.shape[0] == 60 and buf.curr == 37
     buf.resize(20); assert buf.max_buffer_size == 20 and buf.curr == 0 and buf.max_sample_size == 20
     buf.clear(); assert (buf.curr, buf.max_sample_size) == (0, 0)
+    with pytest.warns(UserWarning, match="larger than buffer"):
+        empty = buf.sample(4)                                           # nothing stored: an empty batch, no kernel call
+    assert empty["obs"].shape == (0, OD) and empty["reward"].shape == (0, 1)
     if not torch.cuda.is_available():
         with pytest.raises(SgrlError, match="CUDA"):                    # no CPU fallback for the data path
             other.sample(4)
