@@ -288,7 +288,10 @@ def run_ours(a):
         alg = FLOP_PER_TOKEN_UPDATE * B * N
         ach = alg / (classes[dom]["ms_per_step"] * 1e-3) / 1e12
         line["roofline"] = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": pk["tflops_sustained"], "unit": "TFLOP/s",
-                            "frac": ach / pk["tflops_sustained"], "traffic": None, "peak_src": pk["src"] + " bf16 sustained",
+                            "frac": ach / pk["tflops_sustained"], "traffic": 9.18e6, "traffic_unit": "bytes of DRAM traffic per launch",
+                            "traffic_src": "mean of 12 launches of this class, ncu --set full (profiles/r01m_ncu_gemm_update_summary.txt): "
+                                           "9.05 MB read + 0.14 MB written; activations and weights of a B=256 step stay in the 126 MB L2",
+                            "peak_src": pk["src"] + " bf16 sustained",
                             "algorithmic_flops_per_step": alg, "launches_per_step": classes[dom]["launches_per_step"],
                             "executed_tflops": classes[dom]["tflops"], "ceiling_frac_3xtf32": 1.0 / 6.0,
                             "frac_of_3xtf32_ceiling": 6.0 * ach / pk["tflops_sustained"],
