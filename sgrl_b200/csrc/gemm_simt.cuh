@@ -168,6 +168,88 @@ __global__ void __launch_bounds__(G_THREADS) gemm_simt_kernel(GemmP p) {
   }
 }
 
+// ---- skinny GEMM: C[M<=32, N] = epi(alpha * A[M,K] B[N,K]^T) — the projections of a B=1..3 rollout forward
+// (Agent.select_action, src/agent.py:189-198: 9..27 token rows).  The 64x64-tile kernel above spends ~23 us per launch there
+// (4-16 CTAs walking K in 16-wide steps with two barriers each: 75 % of a 0.87 ms select_action).  Here the whole A panel
+// sits in shared memory, one warp owns one output column, lanes stride over K with 128-bit loads of the weight row
+// (coalesced, each weight read exactly once per CTA) and the M partial sums are reduced with shuffles.  Weight-read bound.
+constexpr int SK_MAXM = 32, SK_WARPS = 8;
+constexpr size_t SK_MAX_SMEM = 160 * 1024;
+
+__global__ void __launch_bounds__(32 * SK_WARPS) gemm_skinny_kernel(GemmP p) {
+  SGRL_PDL_ENTER();
+  extern __shared__ __align__(16) float sk_As[];          // [M][K]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, z = blockIdx.z;
+  const float* A = p.A + z * p.zsA;
+  const float* B = p.B + z * p.zsB;
+  const int M = p.M, K4 = p.K >> 2;
+  float4* As4 = reinterpret_cast<float4*>(sk_As);
+  for (int i = tid; i < M * K4; i += 32 * SK_WARPS) {
+    const int m = i / K4, k4 = i - m * K4;
+    As4[i] = ldg4(A + (long long)m * p.lda + 4 * k4);
+  }
+  __syncthreads();
+  float* C = p.C + z * p.zsC;
+  const float* bias = p.bias ? p.bias + z * p.zsBias : nullptr;
+  const float* rowdiv = p.rowdiv ? p.rowdiv + z * p.zsRow : nullptr;
+  const float* res1 = p.res1 ? p.res1 + z * p.zsR1 : nullptr;
+  const float* res2 = p.res2 ? p.res2 + z * p.zsR2 : nullptr;
+  for (int n = blockIdx.x * SK_WARPS + warp; n < p.N; n += gridDim.x * SK_WARPS) {
+    float acc[SK_MAXM];
+#pragma unroll
+    for (int m = 0; m < SK_MAXM; ++m) acc[m] = 0.f;
+    const float4* brow = reinterpret_cast<const float4*>(B + (long long)n * p.ldb);
+    for (int k4 = lane; k4 < K4; k4 += 32) {
+      const float4 b = __ldg(brow + k4);
+#pragma unroll
+      for (int m = 0; m < SK_MAXM; ++m) {
+        if (m < M) {
+          const float4 a = As4[m * K4 + k4];
+          acc[m] = fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, fmaf(a.w, b.w, acc[m]))));
+        }
+      }
+    }
+    float mine = 0.f;                                     // lane m keeps the total of row m
+#pragma unroll
+    for (int m = 0; m < SK_MAXM; ++m) {
+      if (m < M) {
+        const float t = warp_sum(acc[m]);
+        if (lane == m) mine = t;
+      }
+    }
+    if (lane < M) {
+      const int m = lane;
+      float v = p.alpha * mine;
+      if (bias) v += bias[n];
+      if (p.relu) v = fmaxf(v, 0.f);
+      if (rowdiv) v = v / rowdiv[m];
+      if (n < p.colscale_n) v *= p.colscale;
+      if (res1) v += res1[(long long)m * p.ldr1 + n];
+      if (res2) v += res2[(long long)m * p.ldr2 + n];
+      C[(long long)m * p.ldc + n] = v;
+    }
+  }
+}
+
+inline bool gemm_skinny_eligible(const GemmP& p) {
+  return p.M >= 1 && p.M <= SK_MAXM && !p.transA && !p.transB && !p.accumulate && p.splitk <= 1 && !p.mask && (p.K & 3) == 0 &&
+         host_vec_ok(p.A, p.lda, p.zsA) && host_vec_ok(p.B, p.ldb, p.zsB) && (size_t)p.M * p.K * sizeof(float) <= SK_MAX_SMEM;
+}
+
+inline int gemm_skinny(const GemmP& p, cudaStream_t st) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    SGRL_CUDA(cudaFuncSetAttribute(gemm_skinny_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SK_MAX_SMEM));
+    attr_done = true;
+  }
+  int gx = ceil_div(p.N, SK_WARPS); if (gx > 4 * NUM_SMS) gx = 4 * NUM_SMS;
+  prof_begin(PC_GEMM, 2.0 * p.M * p.N * (double)p.K * p.nb, st);
+  launch_k(gemm_skinny_kernel, dim3(gx, 1, p.nb), 32 * SK_WARPS, (size_t)p.M * p.K * sizeof(float), st, p);
+  prof_end(st);
+  SGRL_LAUNCH_OK();
+  return 0;
+}
+
 inline int gemm_simt(const GemmP& p_in, cudaStream_t st) {
   GemmP p = p_in;
   p.vecA = host_vec_ok(p.A, p.lda, p.zsA);
@@ -177,6 +259,7 @@ inline int gemm_simt(const GemmP& p_in, cudaStream_t st) {
   SGRL_CHECK(p.splitk >= 1, "gemm: splitk");
   SGRL_CHECK(p.splitk == 1 || (!p.relu && !p.rowdiv && !p.mask && !p.res1 && !p.res2 && p.colscale_n == 0),
              "gemm: split-K only with a linear epilogue");
+  if (gemm_skinny_eligible(p)) return gemm_skinny(p, st);
   const int tiles = ceil_div(p.M, GB_M) * ceil_div(p.N, GB_N);
   dim3 grid(tiles, p.splitk, p.nb);
   prof_begin(PC_GEMM, 2.0 * p.M * p.N * (double)p.K * p.nb, st);

@@ -20,7 +20,8 @@ def rel(a, b):
 
 
 TOL = {0: 2e-6, 1: 2e-5}   # tcgen05 accumulates with truncation: ~5e-6 at K=1024, still 20x inside the 1e-4 budget
-FWD = [(300, 256, 1024), (2304, 768, 256), (77, 252, 128), (128, 128, 32), (1000, 1024, 256), (129, 130, 100)]
+FWD = [(300, 256, 1024), (2304, 768, 256), (77, 252, 128), (128, 128, 32), (1000, 1024, 256), (129, 130, 100),
+       (9, 256, 544), (27, 252, 128), (1, 1024, 256), (32, 130, 148), (16, 3, 256)]   # M <= 32: the skinny kernel of B=1..3 rollouts
 
 
 @pytest.mark.parametrize("use_tc", [0, 1])
