@@ -1,23 +1,22 @@
-// K3 — fp32-accurate tensor-core GEMM for sm_100a: tcgen05.mma (kind::tf32) with the
-// accumulator in TMEM, operands streamed by TMA (cp.async.bulk.tensor, SWIZZLE_128B) through
-// a 3-4 stage mbarrier ring, error-compensated "3xTF32" split formed in shared memory.
+// K3 — fp32-accurate tensor-core GEMM for sm_100a: tcgen05.mma (kind::tf32) with the accumulators in TMEM, operands
+// streamed by TMA (cp.async.bulk.tensor) through an mbarrier ring, error-compensated "3xTF32" split.
 //
 //   C[z][m][n] (op)= epi( alpha * sum_k A(m,k) B(n,k) )        (same contract as gemm_simt.cuh)
 //
-// fp32 parity: every fp32 operand element x is split as x = hi + lo with hi = tf32(x) and
-// lo = tf32(x - hi); the tile accumulates hi*hi + lo*hi + hi*lo in the same fp32 TMEM
-// accumulator (3 MMAs per k-step), which recovers ~21 mantissa bits (SURVEY.md §7 "fp32
-// parity on tensor cores").  The split is elementwise, so it is done in place on the
-// TMA-landed (swizzled) tile without knowing the swizzle.
+// fp32 parity: every fp32 operand element x is split as x = hi + lo (hi = the tf32 the tensor core reads out of the raw
+// word, lo = tf32(x - hi)); a tile accumulates hi*hi + lo*hi + hi*lo (3 MMAs per k-step, ~21 mantissa bits), the hi*hi
+// terms round-robin over up to three accumulators because the tensor core accumulates with truncation (TcCfg).
 //
-// Operand majors: K-major (nn.Linear weights (N,K) and activations (M,K): the forward
-// projections) and MN-major (the same buffers read "transposed": dX = dY W and
-// dW = dY^T X) are both expressed through the TMA box shape + UMMA descriptor, so no
-// transposed copies of weights or activations are ever made.
+// Operand majors: K-major (nn.Linear weights (N,K) and activations (M,K): the forward projections) and MN-major (the
+// same buffers read "transposed": dX = dY W and dW = dY^T X) are both expressed through the TMA box shape + UMMA
+// descriptor, so no transposed copies of weights or activations are ever made.
 //
-// CTA = 6 warps: warp0 = TMA producer, warp1 = TMEM owner + MMA issuer (one thread),
-// warps2-5 = hi/lo converters during the main loop, then the TMEM->register epilogue
-// (bias, relu, /F, column scale, relu-mask, residuals, accumulate / split-K atomics).
+// CTA = 10 warps: warp0 = TMA producer, warp1 = TMEM owner + MMA issuer (one elected lane), warps 2-9 = two converter
+// groups that move each landed A k-block into TMEM as [hi | lo] (the A operand is fed from tensor memory, ".ts" form)
+// and then run the fused epilogue (TMEM -> registers -> shared transpose -> coalesced global: bias, relu, /F, column
+// scale, relu-mask, residuals, accumulate / split-K atomics).  Weights arrive pre-split (hi / lo arenas).
+// Variants: SM2 = two CTAs per SM for short-K tiles of inference passes; cluster split-K (p.csk) = a (1, 2..3, 1) cluster
+// shares one tile's k-loop and reduces through distributed shared memory.  DESIGN.md §4 has the measurements behind each.
 #pragma once
 #include <cuda.h>
 
