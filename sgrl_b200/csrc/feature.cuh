@@ -219,6 +219,85 @@ __global__ void __launch_bounds__(F_THREADS) inv_feature_fwd_kernel(
   }
 }
 
+// ---- tiny-batch variant: one warp per token, no block-level barrier ---------------------------------------------
+// For the 9..128 tokens of an acting forward (Agent.select_action) the tiled kernel above is one or two CTAs walking
+// block-wide phases.  Here lane = output channel: the token's X row sits in the warp's slice of shared memory (128-bit
+// broadcast loads), each lane streams its own row of P from L1/L2, keeps Z in registers, and the Gram column j is formed
+// from shuffled z_i.  Measured: select_action 416 -> 393 us.  NOT a win at 2 304 tokens (20.5 us per launch like the tiled
+// kernel, and the update slowed from 5.38 to 5.79 ms: 2 304 warps each streaming 16 KB of P rows, uncoalesced), so it is
+// used for T <= 128 only.
+template <int CE, int NPROJ>
+__global__ void __launch_bounds__(256) inv_feature_small_fwd_kernel(
+    const float* __restrict__ Xg, long long zsXg, const float* __restrict__ V0, long long zsV0,
+    const float* __restrict__ gd, long long zsGd,
+    const float* __restrict__ P1, const float* __restrict__ P2, long long zsP,
+    float* __restrict__ Z, float* __restrict__ Z2, float* __restrict__ G, float* __restrict__ Fn, long long zsAct,
+    int T) {
+  SGRL_PDL_ENTER();
+  constexpr int C = 128 + CE;
+  __shared__ __align__(16) float Xw[8][3 * C];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, z = blockIdx.y;
+  Xg += z * zsXg; gd += z * zsGd; P1 += z * zsP;
+  if (CE) V0 += z * zsV0;
+  if (NPROJ == 2) P2 += z * zsP;
+  Z += z * zsAct; G += z * zsAct; Fn += z * zsAct;
+  if (NPROJ == 2) Z2 += z * zsAct;
+  const int t = blockIdx.x * 8 + warp;
+  if (t >= T) return;                          // warp-uniform; nothing below synchronises across warps
+  float* xw = Xw[warp];
+  for (int i = lane; i < 96; i += 32) {
+    const int r = i >> 5, c4 = (i & 31) * 4;
+    *reinterpret_cast<float4*>(&xw[r * C + CE + c4]) = ldg4(Xg + ((long long)t * 3 + r) * 128 + c4);
+  }
+  if (CE && lane < 24) xw[(lane >> 3) * C + (lane & 7)] = __ldg(V0 + (long long)t * 24 + lane);
+  __syncwarp();
+  const int j = lane;
+  const bool learned = j < 30;                 // channels 30, 31 are [gravity, direction]
+  const float* p1 = P1 + (learned ? j : 0) * C;
+  const float* p2 = NPROJ == 2 ? P2 + (learned ? j : 0) * C : nullptr;
+  float z1[3] = {0.f, 0.f, 0.f}, z2[3] = {0.f, 0.f, 0.f};
+#pragma unroll 2
+  for (int c = 0; c < C; c += 4) {
+    const float4 pa = ldg4(p1 + c);
+    float4 pb = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (NPROJ == 2) pb = ldg4(p2 + c);
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const float4 x = *reinterpret_cast<const float4*>(&xw[r * C + c]);
+      z1[r] = fmaf(x.x, pa.x, fmaf(x.y, pa.y, fmaf(x.z, pa.z, fmaf(x.w, pa.w, z1[r]))));
+      if (NPROJ == 2) z2[r] = fmaf(x.x, pb.x, fmaf(x.y, pb.y, fmaf(x.z, pb.z, fmaf(x.w, pb.w, z2[r]))));
+    }
+  }
+  if (!learned) {
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      z1[r] = __ldg(gd + (long long)t * 6 + r * 2 + (j - 30));
+      z2[r] = z1[r];
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    Z[((long long)t * 3 + r) * 32 + j] = z1[r];
+    if (NPROJ == 2) Z2[((long long)t * 3 + r) * 32 + j] = z2[r];
+  }
+  float ss = 0.f;
+  float* g = G + (long long)t * GP_K;
+#pragma unroll 4
+  for (int i = 0; i < CH; ++i) {
+    const float a0 = __shfl_sync(0xffffffffu, z1[0], i), a1 = __shfl_sync(0xffffffffu, z1[1], i), a2 = __shfl_sync(0xffffffffu, z1[2], i);
+    float o = a0 * z1[0];
+    o = fmaf(a1, z1[1], o);
+    o = fmaf(a2, z1[2], o);
+    if (j >= i) {
+      g[tri_index(i, j)] = o;
+      ss = fmaf(j == i ? o : 2.f * o, o, ss);
+    }
+  }
+  if (lane < GP_K - GP) g[GP + lane] = 0.f;
+  ss = warp_sum(ss);
+  if (lane == 0) Fn[t] = sqrtf(ss) + 1.0f;
+}
+
 struct FeatFwdP {
   const float* Xg; long long zsXg; const float* V0; long long zsV0; const float* gd; long long zsGd;
   const float* P1; const float* P2; long long zsP;
@@ -236,6 +315,14 @@ inline int inv_feature_fwd_launch(const FeatFwdP& p, cudaStream_t st) {
     attr_done = true;
   }
   const int ntiles = ceil_div(p.T, F_TT);
+  if (p.T <= 128) {      // a handful of graphs (acting): one warp per token (see inv_feature_small_fwd_kernel)
+    prof_begin(PC_FEATURE, (double)p.T * p.nb * (12.0 * S::C + 24 + 4.0 * GP_K + 4 + 384.0 * NPROJ), st);
+    launch_k(inv_feature_small_fwd_kernel<CE, NPROJ>, dim3(ceil_div(p.T, 8), p.nb), 256, 0, st, p.Xg, p.zsXg, p.V0, p.zsV0, p.gd, p.zsGd,
+             p.P1, p.P2, p.zsP, p.Z, p.Z2, p.G, p.Fn, p.zsAct, p.T);
+    prof_end(st);
+    SGRL_LAUNCH_OK();
+    return 0;
+  }
   const int per_sm = (int)((227 * 1024) / (S::bytes + 1024)) < 4 ? (int)((227 * 1024) / (S::bytes + 1024)) : 4;
   const int gx = ntiles < per_sm * NUM_SMS ? ntiles : per_sm * NUM_SMS;
   // algorithmic bytes per token: read X (12*C) + gd (24), write G (4*GP_K = 2176: packed triangle) + F (4) + Z (384 per projection)
