@@ -1,10 +1,14 @@
 #!/bin/bash
-# ncu --set full captures of the dominant kernel variants (1 GPU, eager single-stream so that launch indices are stable)
-export SGRL_GRAPHS=0 SGRL_SIDE=0
-CMD="python bench.py --steps 2 --warmup 4 --no-cpu-baseline --no-rollout"
-cap() { ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k "regex:$1" -s $2 -c 2 -f -o gpurun_out/$3 $CMD > gpurun_out/ncu_$3.log 2>&1; }
-cap 'gemm_tc_kernel<\(int\)64, \(bool\)0, \(bool\)0, \(bool\)1>' 300 prof_gemm_fwd64
-cap 'gemm_tc_kernel<\(int\)128, \(bool\)0, \(bool\)0, \(bool\)1>' 100 prof_gemm_fwd128
-cap 'gemm_tc_kernel<\(int\)64, \(bool\)1, \(bool\)1, \(bool\)0>' 150 prof_gemm_wgrad64
-cap 'gemm_tc_kernel<\(int\)128, \(bool\)1, \(bool\)1, \(bool\)0>' 20 prof_gemm_wgrad128
+# ncu --set full captures of the dominant kernels (1 GPU; never under torchrun).  Reports land in gpurun_out/; summarise them
+# here with `python tools/ncu_summary.py gpurun_out/<name>.ncu-rep > profiles/<round>_<name>_summary.txt`.
+# --kernel-name-base demangled makes -k match the full C++ name (namespace + template arguments).
+NCU="ncu --set full --clock-control none --import-source on --kernel-name-base demangled"
+BENCH="python bench.py --steps 2 --warmup 4 --no-cpu-baseline"
+# tcgen05 GEMM launches of the B=256 update (gemm_tc_kernel<BN, AMN, BMN, BPRE, SM2>)
+$NCU -k "regex:gemm_tc_kernel" -s 60 -c 12 -f -o gpurun_out/prof_gemm_update $BENCH --no-rollout > gpurun_out/ncu_gemm_update.log 2>&1
+# the two-CTAs-per-SM variant only runs in the rollout leg
+$NCU -k "regex:gemm_tc_kernel<\(int\)128, \(bool\)0, \(bool\)[01], \(bool\)1, \(bool\)1>" -s 10 -c 6 -f -o gpurun_out/prof_gemm_sm2 $BENCH > gpurun_out/ncu_gemm_sm2.log 2>&1
+# K1 / K2 at rollout size through the C ABI
+$NCU -k "regex:inv_feature_fwd_kernel<\(int\)0, \(int\)1>" -s 4 -c 1 -f -o gpurun_out/prof_k1 python tools/k_bench.py > gpurun_out/ncu_k1.log 2>&1
+$NCU -k "regex:attention_fwd_kernel" -s 6 -c 1 -f -o gpurun_out/prof_k2 python tools/k_bench.py > gpurun_out/ncu_k2.log 2>&1
 ls -la gpurun_out/*.ncu-rep
