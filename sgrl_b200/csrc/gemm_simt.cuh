@@ -36,6 +36,8 @@ struct GemmP {
   int csk;                                  // tcgen05 path, set by the launcher: K is split over a (1, splitk, 1) cluster, rank 0 reduces through DSMEM
   int sm2_ok;                               // tcgen05 path: the single-accumulator two-CTAs-per-SM variant may be used (inference passes only)
   long long* dbg;                           // optional (tools/gemm_trace.py): SM-clock timestamps of CTA 0's pipeline phases
+  float* rowsum; long long zsRowsum;        // optional: rowsum[m] += alpha * sum_k A(m,k)  (bias gradient of a weight-gradient GEMM, A = dY^T); tcgen05 path
+                                            // fuses it into the operand conversion, elsewhere a column-sum kernel follows the GEMM (run_gemm, net.cuh)
 };
 
 inline GemmP gemm_defaults() {

@@ -479,6 +479,10 @@ __global__ void __launch_bounds__(TC_THREADS, SM2 ? 2 : 1) gemm_tc_kernel(const 
       const uint32_t trow = ta_base + ((uint32_t)(q * 32) << 16);
       static_assert(STAGES % 2 == 0 && TA % 2 == 0, "two converter groups take alternate ring slots");
       int s = g, t = g; uint32_t ph = 0, pht = 0;
+      // bias gradient of a weight-gradient GEMM (A = dY^T, row m = output feature): every A element passes through this
+      // thread's registers anyway, so the row sums cost 32 adds per k-block instead of a column-sum kernel per tensor
+      const bool do_rs = p.rowsum != nullptr && n0 == 0;
+      float rs = 0.f;
       for (int i = g; i < nloc; i += 2) {
         mbar_wait(full_bar(s), ph);
         if (tid == 64 && i < 12) TC_STAMP(20 + i);
@@ -496,6 +500,12 @@ __global__ void __launch_bounds__(TC_THREADS, SM2 ? 2 : 1) gemm_tc_kernel(const 
           for (int k = 0; k < 32; ++k) raw[k] = __float_as_uint(lds32(st + (uint32_t)k * 512u + (uint32_t)row * 4u));
         }
         if (!BPRE) split_tile_lo<B_BYTES / 16, B_BYTES, 128>(st + TC_A_BYTES, cgt);
+        if (do_rs) {
+          float s4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int j = 0; j < 32; ++j) s4[j & 3] += __uint_as_float(raw[j]);
+          rs += (s4[0] + s4[1]) + (s4[2] + s4[3]);
+        }
 #pragma unroll
         for (int j = 0; j < 32; ++j) lo[j] = lo_of_trunc(__uint_as_float(raw[j]));
         mbar_wait(ta_empty(t), pht ^ 1u);
@@ -511,6 +521,7 @@ __global__ void __launch_bounds__(TC_THREADS, SM2 ? 2 : 1) gemm_tc_kernel(const 
         s += 2; if (s >= STAGES) { s -= STAGES; ph ^= 1u; }
         t += 2; if (t >= TA) { t -= TA; pht ^= 1u; }
       }
+      if (do_rs && m0 + row < p.M) atomicAdd(p.rowsum + z * p.zsRowsum + m0 + row, p.alpha * rs);
       mbar_wait(acc_bar, 0);                       // every MMA of this CTA has retired: accumulators complete, ring stages idle
       tc_fence_after();
       if (tid == 64) TC_STAMP(2);

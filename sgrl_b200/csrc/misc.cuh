@@ -237,7 +237,128 @@ __global__ void __launch_bounds__(256) matapply_bwd_kernel(
     }
     float* o = dZ + (long long)t * 96;
     o[lane] = a0; o[32 + lane] = a1; o[64 + lane] = a2;
-    if (lane == 0) dF[t] -= facc * invF;
+    if (lane == 0) atomicAdd(dF + t, -facc * invF);     // the other divisions by the same F add their term from a concurrent lane (net.cuh)
+  }
+}
+
+// =====================================================================================
+// K4 fused with linear5 and the two residuals (SEActor.py:107-114):
+//   R_t = Z3_t (3x32) . M_t (32x32);   Vg'_t = Vg_t + dV_t + R_t W5^T      (W5 = linear5.weight (128,32), no bias)
+// One warp per token.  Phase 1 as matapply_fwd_kernel (lane = column j of R); phase 2: lane owns the four output
+// channels c = lane + 32 q, R's columns are broadcast with shuffles and W5 is read transposed from shared memory
+// (W5t[j][c]: conflict-free).  12 K MACs per token: far below one tcgen05 tile, and it removes the K = 32 GEMM launch
+// (8 us at 2 304 tokens) that used to follow the matrix apply on the critical path of every layer.
+// R is written only when the caller keeps activations for a backward (dW5 = dVg'^T R).
+// =====================================================================================
+__global__ void __launch_bounds__(256) matapply_l5_fwd_kernel(
+    const float* __restrict__ Z, const float* __restrict__ M, const float* __restrict__ W5, long long zsP,
+    const float* __restrict__ Vg, const float* __restrict__ dV, float* __restrict__ R, float* __restrict__ Vn, long long zsS, int T) {
+  SGRL_PDL_ENTER();
+  __shared__ float W5t[32 * 128];
+  const int lane = threadIdx.x & 31, z = blockIdx.y;
+  Z += z * zsS; M += z * zsS; Vg += z * zsS; dV += z * zsS; Vn += z * zsS; W5 += z * zsP;
+  if (R) R += z * zsS;
+  // W5t[j][c] = W5[c][j]: consecutive threads take consecutive c (conflict-free writes; the strided reads are independent and L2-resident)
+  for (int i = threadIdx.x; i < 32 * 128; i += 256) W5t[i] = __ldg(W5 + (i & 127) * 32 + (i >> 7));
+  __syncthreads();
+  for (int t = blockIdx.x * 8 + (threadIdx.x >> 5); t < T; t += gridDim.x * 8) {
+    const float z0 = Z[(long long)t * 96 + lane], z1 = Z[(long long)t * 96 + 32 + lane], z2 = Z[(long long)t * 96 + 64 + lane];
+    const float* m = M + (long long)t * 1024 + lane;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+#pragma unroll 8
+    for (int i = 0; i < 32; ++i) {
+      const float mv = __ldg(m + i * 32);
+      a0 = fmaf(__shfl_sync(0xffffffffu, z0, i), mv, a0);
+      a1 = fmaf(__shfl_sync(0xffffffffu, z1, i), mv, a1);
+      a2 = fmaf(__shfl_sync(0xffffffffu, z2, i), mv, a2);
+    }
+    if (R) { float* r = R + (long long)t * 96; r[lane] = a0; r[32 + lane] = a1; r[64 + lane] = a2; }
+    float o[3][4];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const long long at = ((long long)t * 3 + r) * 128 + lane + 32 * q;
+        o[r][q] = Vg[at] + dV[at];
+      }
+    float s[3][4];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) s[r][q] = 0.f;
+#pragma unroll 8
+    for (int j = 0; j < 32; ++j) {
+      const float r0 = __shfl_sync(0xffffffffu, a0, j), r1 = __shfl_sync(0xffffffffu, a1, j), r2 = __shfl_sync(0xffffffffu, a2, j);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float w = W5t[j * 128 + lane + 32 * q];
+        s[0][q] = fmaf(r0, w, s[0][q]); s[1][q] = fmaf(r1, w, s[1][q]); s[2][q] = fmaf(r2, w, s[2][q]);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) Vn[((long long)t * 3 + r) * 128 + lane + 32 * q] = o[r][q] + s[r][q];
+  }
+}
+
+// backward of the fused pair:  dR = dVg' W5  (3x128 . 128x32), then matapply_bwd_kernel's math:
+//   dZ3 = dR M^T;  dM = Z3^T dR;  M = Tm/F  =>  dTm = dM/F,  dF -= sum(dM.M)/F.   dR is also written (dW5's operand is dVg', R).
+__global__ void __launch_bounds__(256) matapply_l5_bwd_kernel(
+    const float* __restrict__ dVn, const float* __restrict__ W5, long long zsP, const float* __restrict__ Z, const float* __restrict__ M,
+    const float* __restrict__ Fn, long long zsS, float* __restrict__ dZ, float* __restrict__ dT, float* __restrict__ dF, long long zsW, int T) {
+  SGRL_PDL_ENTER();
+  __shared__ float Ms[8][32][33];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, z = blockIdx.y;
+  Z += z * zsS; M += z * zsS; Fn += z * zsS; dVn += z * zsW; dZ += z * zsW; dT += z * zsW; dF += z * zsW; W5 += z * zsP;
+  for (int t = blockIdx.x * 8 + warp; t < T; t += gridDim.x * 8) {
+    // dR[r][lane] = sum_c dVg'[r][c] W5[c][lane]; lane holds dVg'[r][4*lane .. 4*lane+3]
+    float r0 = 0.f, r1 = 0.f, r2 = 0.f;
+    {
+      const float4 d0 = *reinterpret_cast<const float4*>(dVn + ((long long)t * 3 + 0) * 128 + lane * 4);
+      const float4 d1 = *reinterpret_cast<const float4*>(dVn + ((long long)t * 3 + 1) * 128 + lane * 4);
+      const float4 d2 = *reinterpret_cast<const float4*>(dVn + ((long long)t * 3 + 2) * 128 + lane * 4);
+#pragma unroll 4
+      for (int cl = 0; cl < 32; ++cl) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float w = __ldg(W5 + (cl * 4 + e) * 32 + lane);      // natural layout W5[c][j], lane = j: one coalesced 128 B line, L1-resident (16 KB)
+          const float v0 = e == 0 ? d0.x : e == 1 ? d0.y : e == 2 ? d0.z : d0.w;
+          const float v1 = e == 0 ? d1.x : e == 1 ? d1.y : e == 2 ? d1.z : d1.w;
+          const float v2 = e == 0 ? d2.x : e == 1 ? d2.y : e == 2 ? d2.z : d2.w;
+          r0 = fmaf(__shfl_sync(0xffffffffu, v0, cl), w, r0);
+          r1 = fmaf(__shfl_sync(0xffffffffu, v1, cl), w, r1);
+          r2 = fmaf(__shfl_sync(0xffffffffu, v2, cl), w, r2);
+        }
+      }
+    }
+    const float z0 = Z[(long long)t * 96 + lane], z1 = Z[(long long)t * 96 + 32 + lane], z2 = Z[(long long)t * 96 + 64 + lane];
+    const float invF = 1.f / Fn[t];
+    const float* m = M + (long long)t * 1024 + lane;
+    float* dt = dT + (long long)t * 1024 + lane;
+    float facc = 0.f;
+    __syncwarp();
+#pragma unroll 8
+    for (int i = 0; i < 32; ++i) {
+      const float mv = __ldg(m + i * 32);
+      Ms[warp][i][lane] = mv;
+      const float dm = __shfl_sync(0xffffffffu, z0, i) * r0 + __shfl_sync(0xffffffffu, z1, i) * r1 + __shfl_sync(0xffffffffu, z2, i) * r2;
+      dt[i * 32] = dm * invF;
+      facc = fmaf(dm, mv, facc);
+    }
+    facc = warp_sum(facc);
+    __syncwarp();
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+#pragma unroll 8
+    for (int j = 0; j < 32; ++j) {
+      const float mv = Ms[warp][lane][j];
+      a0 = fmaf(__shfl_sync(0xffffffffu, r0, j), mv, a0);
+      a1 = fmaf(__shfl_sync(0xffffffffu, r1, j), mv, a1);
+      a2 = fmaf(__shfl_sync(0xffffffffu, r2, j), mv, a2);
+    }
+    float* o = dZ + (long long)t * 96;
+    o[lane] = a0; o[32 + lane] = a1; o[64 + lane] = a2;
+    if (lane == 0) atomicAdd(dF + t, -facc * invF);     // the other divisions by the same F add their term from a concurrent lane (net.cuh)
   }
 }
 
@@ -320,7 +441,7 @@ __global__ void __launch_bounds__(256) rowdiv_bwd_kernel(
       dy[(long long)t * lddy + n] = d * invF * (n < cs_n ? colscale : 1.f);
     }
     s = warp_sum(s);
-    if (lane == 0) dF[t] -= s * invF;
+    if (lane == 0) atomicAdd(dF + t, -s * invF);
   }
 }
 

@@ -127,7 +127,14 @@ inline int run_gemm(const NetCtx& c, const GemmP& g, cudaStream_t st = nullptr) 
     GemmP gi = g; gi.sm2_ok = 1;
     return gemm_tc(gi, st);
   }
-  return gemm_simt(g, st);
+  SGRL_TRY(gemm_simt(g, st));
+  if (g.rowsum) {      // the SIMT kernel has no fused row sum: rowsum[m] += alpha * sum_k A(m,k) as a column sum of dY (A = dY^T)
+    SGRL_CHECK(g.transA, "rowsum: only for weight-gradient GEMMs (A = dY^T)");
+    int gy = ceil_div(g.K, 64); if (gy > 32) gy = 32; if (gy < 1) gy = 1;
+    launch_k(colsum_kernel, dim3(ceil_div(g.M, 32), gy, g.nb), 256, 0, st, g.A, g.lda, g.zsA, g.rowsum, g.zsRowsum, g.K, g.M, g.alpha);
+    SGRL_LAUNCH_OK();
+  }
+  return 0;
 }
 // stream for the next piece of weight-gradient work: a side stream that has been made to wait for everything
 // enqueued on the main stream so far (or the main stream itself when side streams are off / profiling is on)
@@ -358,11 +365,10 @@ inline int net_forward(const NetCtx& c, const float* obs, long long zsObs, const
     g = lin(c, c.SL(l, S_T31), 512, zS, lp[L_L4_W], lp[L_L4_B], c.SL(l, S_MM), 1024, zS, T, 1024, 256);
     g.rowdiv = c.SL(l, S_F2); g.zsRow = zS;
     SGRL_TRY(run_gemm(c, g));
-    launch_k(matapply_fwd_kernel, dim3(grid_for_warps(T), c.nb), 256, 0, st, c.SL(l, S_Z3), c.SL(l, S_MM), c.SL(l, S_R), zS, T);
+    // Vg' = Vg + dV + linear5(Z3 . M): matrix apply, the K = 32 projection and both residuals in one launch (misc.cuh)
+    launch_k(matapply_l5_fwd_kernel, dim3(grid_for_warps(T), c.nb), 256, 0, st, c.SL(l, S_Z3), c.SL(l, S_MM), c.P(lp[L_L5_W]), c.zsP, Vg, c.SL(l, S_DV),
+             c.keep ? c.SL(l, S_R) : nullptr, Vg_next, zS, T);
     SGRL_LAUNCH_OK();
-    g = lin(c, c.SL(l, S_R), 32, zS, lp[L_L5_W], -1, Vg_next, 128, zS, T3, 128, 32);
-    g.res1 = Vg; g.zsR1 = zS; g.ldr1 = 128; g.res2 = c.SL(l, S_DV); g.zsR2 = zS; g.ldr2 = 128;
-    SGRL_TRY(run_gemm(c, g));
     SGRL_TRY(side_join(c));
   }
   // final LayerNorm -> right part of SH = [s0 | h]
@@ -429,8 +435,8 @@ inline int net_backward(const NetCtx& c, const float* dOut, long long zsDo, int 
     SGRL_TRY(side_fork(c, &ss, -1, from));
     GemmP w = wgrad(c, dY, lddy, X, ldx, zsX, dw_off, ldw, M, Nw, Kw);
     w.alpha = alpha;
+    if (db_off >= 0) { w.rowsum = c.Gr(db_off); w.zsRowsum = c.zsG; }      // bias gradient rides on the dW GEMM
     SGRL_TRY(run_gemm(c, w, ss));
-    if (db_off >= 0) SGRL_TRY(colsum(c, dY, lddy, db_off, M, Nw, alpha, ss));
     return 0;
   };
 
@@ -440,8 +446,8 @@ inline int net_backward(const NetCtx& c, const float* dOut, long long zsDo, int 
     cudaStream_t ss;
     SGRL_TRY(side_fork(c, &ss, -1, nullptr));
     GemmP w = wgrad_fold(c, dY, lddy, Gp, fold_off, M, Nw);
+    w.rowsum = c.Gr(db_off); w.zsRowsum = c.zsG;
     SGRL_TRY(run_gemm(c, w, ss));
-    SGRL_TRY(colsum(c, dY, lddy, db_off, M, Nw, 1.f, ss));
     return 0;
   };
   if (wg)
@@ -527,11 +533,10 @@ inline int net_backward(const NetCtx& c, const float* dOut, long long zsDo, int 
     g.mask = T31 + 256; g.zsMask = zS; g.ldmask = 512;
     SGRL_TRY(run_gemm(c, g, sb));
     // ---- main: Vg' = Vg + dV + linear5([g_proj3(dV)|gd] . M)
-    g = dgrad(c, Wn(W_DVG), 128, lp[L_L5_W], 32, W(W_DR), 32, T3, 128, 32);
-    SGRL_TRY(run_gemm(c, g));
     SGRL_TRY(side_w(Wn(W_DVG), 128, c.SL(l, S_R), 32, zS, lp[L_L5_W], 32, T3, 128, 32));
-    launch_k(matapply_bwd_kernel, dim3(grid_for_warps(T), c.nb), 256, 0, st, W(W_DR), c.SL(l, S_Z3), c.SL(l, S_MM), c.SL(l, S_F2), zS, W(W_DZ3),
-             W(W_DT4), W(W_DF2), zW, T);
+    // dR = dVg' W5 and the matrix-apply backward in one launch (misc.cuh)
+    launch_k(matapply_l5_bwd_kernel, dim3(grid_for_warps(T), c.nb), 256, 0, st, Wn(W_DVG), c.P(lp[L_L5_W]), c.zsP, c.SL(l, S_Z3), c.SL(l, S_MM),
+             c.SL(l, S_F2), zS, W(W_DZ3), W(W_DT4), W(W_DF2), zW, T);
     SGRL_LAUNCH_OK();
     SGRL_TRY(side_w(W(W_DT4), 1024, T31, 512, zS, lp[L_L4_W], 256, T, 1024, 256, lp[L_L4_B]));
     g = dgrad(c, W(W_DT4), 1024, lp[L_L4_W], 256, W(W_DT31), 512, T, 1024, 256);
