@@ -130,6 +130,30 @@ int sgrl_gemm(const float* A, int lda, int trans_a, const float* B, int ldb, int
 int sgrl_gemm_presplit(const float* A, int lda, int trans_a, const float* B_hi, const float* B_lo, int ldb, int trans_b, float* C,
                        int ldc, int M, int N, int K, float alpha, const float* bias, const float* rowdiv, int relu, int accumulate,
                        int splitk, sgrl_stream_t stream);
+/* The fused projections of the tcgen05 forward schedule (csrc/net.cuh; unit tests and micro-benchmarks call them here).
+ * All take the weight pre-split (W_hi / W_lo, sgrl_split_tf32) and run one tcgen05 launch.
+ *  sgrl_gemm_gram: C (T,N) = epi( tri(Z_t^T Z_t) W'^T + b ), the vec(G) consumers linear_g1 / linear1_g
+ *    (subequivariant_attentions.py:93-97, SEActor.py:96-101, 259-263) with the Gram rows generated inside the GEMM from
+ *    Z (T,3,32) instead of being read from HBM; W' (N,544) is the triangle-folded weight.  F (T, nullable) = ||G||_F + 1,
+ *    G (T,544, nullable) = the generated rows (what sgrl_inv_feature_fwd writes).
+ *  sgrl_gemm_gd: Z (T3,32) = [A W^T | gd]: the invariant projections g_proj / g_proj2 / g_proj3 (W (30,K) inside a matrix of
+ *    row stride ldw whose two following rows are readable) with columns 30,31 of row 3t+r taken from gd (T,3,2)
+ *    (subequivariant_attentions.py:91-92, SEActor.py:94-95, 109-110).
+ *  sgrl_gemm_ln: N = 128.  x0 = (A W^T + b) [/ rowdiv];  x = x0 + res;  y = LayerNorm(x; gamma, beta) (eps 1e-5);
+ *    optionally y2 = LayerNorm(y; gamma2, beta2): ng_out + norm1, linear2 + norm2 (+ the encoder's final norm)
+ *    (SEActor.py:89-91, 121-123, 164-165).  x, x0 (T,128), stats, stats2 (T,2: mean, rstd) nullable.
+ *  sgrl_gemm_pair: two independent projections C_i = A_i W_i^T + b_i [relu] in ONE grouped launch. */
+int sgrl_gemm_gram(const float* Z, const float* W_hi, const float* W_lo, const float* bias, float* C, int ldc, float* F, float* G,
+                   int T, int N, int relu, sgrl_stream_t stream);
+int sgrl_gemm_gd(const float* A, int lda, const float* W_hi, const float* W_lo, int ldw, const float* gd, float* Z, int T3, int K,
+                 sgrl_stream_t stream);
+int sgrl_gemm_ln(const float* A, int lda, const float* W_hi, const float* W_lo, const float* bias, const float* rowdiv,
+                 const float* res, int ldres, const float* gamma, const float* beta, const float* gamma2, const float* beta2,
+                 float* y, int ldy, float* x, float* x0, float* stats, float* y2, int ldy2, float* stats2, int T, int K,
+                 sgrl_stream_t stream);
+int sgrl_gemm_pair(const float* A0, int lda0, const float* W0_hi, const float* W0_lo, const float* b0, float* C0, int ldc0, int M0, int N0,
+                   int K0, const float* A1, int lda1, const float* W1_hi, const float* W1_lo, const float* b1, float* C1, int ldc1, int M1,
+                   int N1, int K1, int relu, sgrl_stream_t stream);
 /* hi = tf32_rna(w), lo = tf32_rna(w - hi): the operand split of the 3xTF32 tensor-core projections, done once per
  * optimizer step for weights instead of once per tile load */
 int sgrl_split_tf32(const float* w, float* hi, float* lo, int64_t n, sgrl_stream_t stream);

@@ -68,6 +68,12 @@ _PROTOS = {
                           c_int, c_int, c_int, c_int, c_f]),
     "sgrl_gemm_presplit": (c_int, [c_f, c_int, c_int, c_f, c_f, c_int, c_int, c_f, c_int, c_int, c_int, c_int, C.c_float, c_f, c_f,
                                    c_int, c_int, c_int, c_f]),
+    "sgrl_gemm_gram": (c_int, [c_f, c_f, c_f, c_f, c_f, c_int, c_f, c_f, c_int, c_int, c_int, c_f]),
+    "sgrl_gemm_gd": (c_int, [c_f, c_int, c_f, c_f, c_int, c_f, c_f, c_int, c_int, c_f]),
+    "sgrl_gemm_ln": (c_int, [c_f, c_int, c_f, c_f, c_f, c_f, c_f, c_int, c_f, c_f, c_f, c_f, c_f, c_int, c_f, c_f, c_f, c_f, c_int, c_f,
+                             c_int, c_int, c_f]),
+    "sgrl_gemm_pair": (c_int, [c_f, c_int, c_f, c_f, c_f, c_f, c_int, c_int, c_int, c_int, c_f, c_int, c_f, c_f, c_f, c_f, c_int, c_int,
+                               c_int, c_int, c_int, c_f]),
     "sgrl_split_tf32": (c_int, [c_f, c_f, c_f, c_i64, c_f]),
     "sgrl_td3_smooth_action": (c_int, [c_f, c_f, c_f, C.c_float, C.c_float, c_i64, c_f]),
     "sgrl_td3_critic_loss": (c_int, [c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, C.c_float, C.c_float, c_int, c_f]),

@@ -21,14 +21,13 @@
 
 namespace sgrl {
 
-// p -> (i << 8 | j) of the packed upper triangle; 0xFFFF for the zero padding p >= GP
+// p -> (i << 8 | j) of the packed upper triangle (layout.h tri_index); 0xFFFF for the zero padding slots
 struct TriLut { unsigned short v[GP_K]; };
 constexpr TriLut make_tri_lut() {
   TriLut t{};
-  int p = 0;
+  for (int p = 0; p < GP_K; ++p) t.v[p] = 0xFFFFu;
   for (int i = 0; i < CH; ++i)
-    for (int j = i; j < CH; ++j) t.v[p++] = (unsigned short)((i << 8) | j);
-  for (; p < GP_K; ++p) t.v[p] = 0xFFFFu;
+    for (int j = i; j < CH; ++j) t.v[tri_index(i, j)] = (unsigned short)((i << 8) | j);
   return t;
 }
 __constant__ TriLut c_tri = make_tri_lut();
@@ -202,7 +201,8 @@ __global__ void __launch_bounds__(F_THREADS) inv_feature_fwd_kernel(
           o.x = fmaf(zi, zj.x, o.x); o.y = fmaf(zi, zj.y, o.y); o.z = fmaf(zi, zj.z, o.z); o.w = fmaf(zi, zj.w, o.w);
         }
         const int j0 = jq * 4;
-        float* gr = g + (i * CH - (i * (i - 1)) / 2 - i + j0);     // &g[tri_index(i, j0)] when j0 >= i
+        // the chunk's valid entries (j >= i) are contiguous in the packed order: a row of a 4x4 block (layout.h)
+        float* gr = g + tri_index(i, max(i, j0)) - max(i - j0, 0);
         const float ov[4] = {o.x, o.y, o.z, o.w};
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -212,7 +212,10 @@ __global__ void __launch_bounds__(F_THREADS) inv_feature_fwd_kernel(
           }
         }
       }
-      if (lane < GP_K - GP) g[GP + lane] = 0.f;
+      if (lane < 16) {     // zero padding slots of the packed layout: 30, 31 of k-blocks 14 and 15, 20..31 of k-block 16
+        const int pz = lane < 2 ? GP_OFF + 30 + lane : lane < 4 ? GP_OFF + 62 + (lane - 2) : GP_OFF + 84 + (lane - 4);
+        g[pz] = 0.f;
+      }
       ss = warp_sum(ss);
       if (lane == 0) Fn[t0 + tk] = sqrtf(ss) + 1.0f;
     }
@@ -293,7 +296,10 @@ __global__ void __launch_bounds__(256) inv_feature_small_fwd_kernel(
       ss = fmaf(j == i ? o : 2.f * o, o, ss);
     }
   }
-  if (lane < GP_K - GP) g[GP + lane] = 0.f;
+  if (lane < 16) {
+    const int pz = lane < 2 ? GP_OFF + 30 + lane : lane < 4 ? GP_OFF + 62 + (lane - 2) : GP_OFF + 84 + (lane - 4);
+    g[pz] = 0.f;
+  }
   ss = warp_sum(ss);
   if (lane == 0) Fn[t] = sqrtf(ss) + 1.0f;
 }

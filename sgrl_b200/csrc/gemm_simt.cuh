@@ -36,6 +36,23 @@ struct GemmP {
   int csk;                                  // tcgen05 path, set by the launcher: K is split over a (1, splitk, 1) cluster, rank 0 reduces through DSMEM
   int sm2_ok;                               // tcgen05 path: the single-accumulator two-CTAs-per-SM variant may be used (inference passes only)
   long long* dbg;                           // optional (tools/gemm_trace.py): SM-clock timestamps of CTA 0's pipeline phases
+  // ---- tcgen05 path only (gemm_tc.cuh) ----
+  int sk_x;                                 // set by the launcher: the split-K index is folded into blockIdx.x (grouped launches)
+  // A operand generated on the fly: row m of A is the packed upper triangle (GP_K = 544 floats, layout.h) of G_m = Z_m^T Z_m,
+  // Z_m (3 x 32) read from gramZ (T, 96).  K must be GP_K, transA = 0, splitk = 1.  Replaces the Gram phase of the
+  // invariant-feature kernel and its 2.2 KB/token round trip (subequivariant_attentions.py:93-97, SEActor.py:96-101, 259-263).
+  const float* gramZ; long long zsGramZ;
+  float* gramF;                             // out (nullable): F_m = ||G_m||_F + 1     (z-stride zsGramZ)
+  float* gramG;                             // out (nullable): the generated rows (T, GP_K), kept for the weight-gradient GEMM (z-stride zsGramZ)
+  // epilogue: columns 30, 31 of row m (= 3 t + r) are REPLACED by gd[t][r][0..1] (gdcols (T, 3, 2)): Z = [X P^T | gd] with N = 32
+  const float* gdcols; long long zsGd;
+  // epilogue: residual + LayerNorm over the 128 columns of a row (N == 128, one tile per row; SEActor.py:90-91, 122-123, 164-165):
+  //   x = epi(acc) (+ res1);  C = LN(x; ln_gamma, ln_beta);  ln_x (nullable, ld 128) = x;  ln_stats (T, 2) = (mean, rstd)
+  //   optional second norm (the encoder's final LayerNorm after the last layer): ln2_y (ld ln2_ldy) = LN(C; ln2_gamma, ln2_beta), ln2_stats
+  // gamma/beta use zsBias as their z-stride, ln_x / ln_stats / ln2_y / ln2_stats use zsC.
+  const float* ln_gamma; const float* ln_beta; float* ln_x; float* ln_stats;
+  float* ln_x0;                             // nullable, ld 128: epi(acc) before the residual is added (linear2(..)/F, needed by the backward of the division)
+  const float* ln2_gamma; const float* ln2_beta; float* ln2_y; int ln2_ldy; float* ln2_stats;
   float* rowsum; long long zsRowsum;        // optional: rowsum[m] += alpha * sum_k A(m,k)  (bias gradient of a weight-gradient GEMM, A = dY^T); tcgen05 path
                                             // fuses it into the operand conversion, elsewhere a column-sum kernel follows the GEMM (run_gemm, net.cuh)
 };

@@ -26,13 +26,25 @@ constexpr int MAX_NODE = 15;  // rows of each positional table
 constexpr int MAX_LAYERS = 8;
 constexpr int ALIGN = 16;     // floats (64 B): keeps every tensor 16B-aligned for float4/TMA
 // The Gram G = Z^T Z is symmetric, so vec(G) (1024 floats per token) is stored and contracted as its upper triangle:
-// GP = 528 entries in row-major (i <= j) order, zero-padded to GP_K = 544 = 17 k-blocks of 32.  The three weights that
-// consume vec(G) (self_attn.linear_g1, linear_g1, linear1_g) are folded once per pass into
+// GP = 528 entries zero-padded to GP_K = 544 = 17 k-blocks of 32.  The three weights that consume vec(G)
+// (self_attn.linear_g1, linear_g1, linear1_g) are folded once per pass into
 // W'[o][p(i,j)] = W[o][32i+j] + W[o][32j+i] (i<j), W[o][33i] (i=j): the same contraction with 47 % fewer MACs and
 // 1.9 KB instead of 4 KB of HBM traffic per token and Gram.  Parameters, gradients and state_dict stay (rows,1024).
-constexpr int GP = CH * (CH + 1) / 2;   // 528
+//
+// Packing order p(i,j), i <= j — chosen so that a k-block of 32 entries is cheap to GENERATE inside the consuming GEMM
+// (gemm_tc.cuh, GRAM operand): the 32 channels are cut into 8 blocks of 4;
+//   k-blocks 0..13  : the 28 off-diagonal block pairs (Ib < Jb) in lexicographic order, two per k-block, each 4x4
+//                     row-major (16 entries from 2 x 12 values of Z);
+//   k-blocks 14..16 : the 8 diagonal blocks, three per k-block, each its 10 entries (a <= b) row-major; the slots
+//                     30, 31 of k-blocks 14, 15 and 20..31 of k-block 16 are zero padding.
+constexpr int GP = CH * (CH + 1) / 2;   // 528 real entries
 constexpr int GP_K = 544;
-__host__ __device__ constexpr int tri_index(int i, int j) { return i * CH - (i * (i - 1)) / 2 + (j - i); }   // i <= j
+constexpr int GP_OFF = 448;             // first entry of the diagonal blocks (28 pairs x 16)
+__host__ __device__ constexpr int tri_index(int i, int j) {   // i <= j
+  const int ib = i >> 2, jb = j >> 2, a = i & 3, b = j & 3;
+  if (ib < jb) return (ib * 7 - (ib * (ib - 1)) / 2 + (jb - ib - 1)) * 16 + a * 4 + b;
+  return GP_OFF + (ib / 3) * 32 + (ib % 3) * 10 + (a * 4 - (a * (a - 1)) / 2 + (b - a));
+}
 
 enum Kind { ACTOR = 0, CRITIC = 1 };
 

@@ -136,6 +136,18 @@ inline int run_gemm(const NetCtx& c, const GemmP& g, cudaStream_t st = nullptr) 
   }
   return 0;
 }
+// 1..4 independent projections hanging off the same point of the dependency chain.  Small passes (launch-bound: every
+// projection of a 2 304-token step is a 18..144-CTA launch) run them as ONE grouped tcgen05 launch; large passes, where each
+// projection fills the machine by itself, as one launch each on the same stream (the two-CTAs-per-SM variant stays available).
+inline int run_group(const NetCtx& c, const GemmP* gs, int n, cudaStream_t st = nullptr) {
+  if (!st) st = c.stream;
+  static const long long group_maxt = getenv("SGRL_GROUP_MAXT") ? atoll(getenv("SGRL_GROUP_MAXT")) : 32768;
+  bool all_tc = c.use_tc && n > 1 && (long long)c.T * c.nb <= group_maxt;
+  for (int i = 0; i < n && all_tc; ++i) all_tc = gemm_tc_eligible(gs[i]);
+  if (all_tc) return gemm_tc_group(gs, n, st);
+  for (int i = 0; i < n; ++i) SGRL_TRY(run_gemm(c, gs[i], st));
+  return 0;
+}
 // stream for the next piece of weight-gradient work: a side stream that has been made to wait for everything
 // enqueued on the main stream so far (or the main stream itself when side streams are off / profiling is on)
 // `from`: the stream whose work so far the forked stream must wait for (default: the main stream)
@@ -308,6 +320,10 @@ inline int net_forward(const NetCtx& c, const float* obs, long long zsObs, const
         c.S(T_V0), c.S(T_GD), c.S(T_SH), KS, c.SL(0, S_VGIN), c.SL(0, S_UA) + 128, 256, zS, T, ng);
     SGRL_LAUNCH_OK();
   }
+  // fused schedule: needs the pre-split weights (tcgen05 path) and enough rows for the N = 32 projections to be worth a tile
+  static const int fused_env = getenv("SGRL_FUSED") ? atoi(getenv("SGRL_FUSED")) : 1;
+  const bool fused = fused_env && c.use_tc && c.phi != nullptr && (long long)T3 * 32 * 128 >= (1 << 21);
+  if (fused) SGRL_TRY(fold_weights(c, st));        // triangle-folded vec(G) consumers of every layer
   for (int l = 0; l < c.L; ++l) {
     const long long* lp = Y.lp[l];
     float* Vg = c.SL(l, S_VGIN);
@@ -317,6 +333,69 @@ inline int net_forward(const NetCtx& c, const float* obs, long long zsObs, const
     float* Vg_next = last ? c.S(T_VGF) : c.SL(l + 1, S_VGIN);
     float* h_next = last ? c.S(T_HL) : c.SL(l + 1, S_UA) + 128;
     const int ld_hn = last ? 128 : 256;
+    if (fused) {
+      // ---- fused schedule (tcgen05 path): 12 launches per layer on ONE stream, no forks ----
+      //  Z1 = [Vg g_proj^T | gd]                                  projection on the tensor pipe, gd columns in the epilogue
+      //  a1 = relu(linear_g1(tri(Z1^T Z1)))  (+ F1, + G1 if kept)  Gram rows generated inside the GEMM as its A operand
+      //  [ u[:, :128] = linear_g2(a1)  ||  vg = vg_proj(Vg) ]      grouped launch
+      //  q|k|v = (W u + b)/F1                                      one N = 768 GEMM
+      //  attention core
+      //  [ h1 = LN1(h + ng_out(o))  ||  dV = g_out(og) ]           grouped, residual + LayerNorm in the epilogue
+      //  [ Z2 = [dV g_proj2^T | gd]  ||  Z3 = [dV g_proj3^T | gd] ] grouped
+      //  a2 = relu(linear_g1'(tri(Z2^T Z2)))  (+ F2, + G2)
+      //  u'[:, :128] = linear_g2'(a2)
+      //  t31 = relu([linear3 | linear1](u'))
+      //  [ h' = LN2(h1 + linear2(t1)/F2) (+ final norm)  ||  M = linear4(t3)/F2 ]   grouped
+      //  Vg' = Vg + dV + linear5(Z3 . M)                           matrix apply + linear5 + residuals
+      GemmP gz = lin(c, Vg, 128, zS, lp[L_GPROJ], -1, c.SL(l, S_Z1), 32, zS, T3, 32, 128);
+      gz.gdcols = c.S(T_GD); gz.zsGd = zS;
+      SGRL_TRY(run_gemm(c, gz));
+      GemmP g1 = lin_fold(c, nullptr, fold_offset(c.L, l, 0), lp[L_G1_B], c.SL(l, S_A1), 256, T, 256); g1.relu = 1;
+      g1.gramZ = c.SL(l, S_Z1); g1.zsGramZ = zS; g1.gramF = c.SL(l, S_F1); g1.gramG = c.keep ? c.SL(l, S_G1) : nullptr;
+      SGRL_TRY(run_gemm(c, g1));
+      GemmP pr[2];
+      pr[0] = lin(c, c.SL(l, S_A1), 256, zS, lp[L_G2_W], lp[L_G2_B], ua, 256, zS, T, 128, 256);
+      pr[1] = lin(c, Vg, 128, zS, lp[L_VG_W], -1, c.SL(l, S_VGP), 252, zS, T3, 252, 128);
+      SGRL_TRY(run_group(c, pr, 2));
+      GemmP g = lin(c, ua, 256, zS, lp[L_Q_W], lp[L_Q_B], c.SL(l, S_QKV), 768, zS, T, 768, 256);
+      g.rowdiv = c.SL(l, S_F1); g.zsRow = zS; g.colscale = QSCALE; g.colscale_n = 256;
+      SGRL_TRY(run_gemm(c, g));
+      SGRL_TRY(attention_fwd(c.SL(l, S_QKV), c.SL(l, S_VGP), c.S(T_GD), c.SL(l, S_O), c.SL(l, S_OG), c.SL(l, S_P), zS,
+                             l == 0 ? c.P(Y.gp[G_REL_W]) : nullptr, l == 0 ? c.P(Y.gp[G_REL_B]) : nullptr, c.zsP, c.gr, c.nb, st));
+      pr[0] = lin(c, c.SL(l, S_O), 256, zS, lp[L_NGO_W], lp[L_NGO_B], ub + 128, 256, zS, T, 128, 256);
+      pr[0].res1 = ua + 128; pr[0].zsR1 = zS; pr[0].ldr1 = 256;
+      pr[0].ln_gamma = c.P(lp[L_N1_W]); pr[0].ln_beta = c.P(lp[L_N1_B]); pr[0].ln_x = c.SL(l, S_X1); pr[0].ln_stats = c.SL(l, S_ST1);
+      pr[1] = lin(c, c.SL(l, S_OG), 256, zS, lp[L_GO_W], -1, c.SL(l, S_DV), 128, zS, T3, 128, 256);
+      SGRL_TRY(run_group(c, pr, 2));
+      pr[0] = lin(c, c.SL(l, S_DV), 128, zS, lp[L_GP2], -1, c.SL(l, S_Z2), 32, zS, T3, 32, 128);
+      pr[0].gdcols = c.S(T_GD); pr[0].zsGd = zS;
+      pr[1] = lin(c, c.SL(l, S_DV), 128, zS, lp[L_GP3], -1, c.SL(l, S_Z3), 32, zS, T3, 32, 128);
+      pr[1].gdcols = c.S(T_GD); pr[1].zsGd = zS;
+      SGRL_TRY(run_group(c, pr, 2));
+      g1 = lin_fold(c, nullptr, fold_offset(c.L, l, 1), lp[L_FG1_B], c.SL(l, S_A2), 256, T, 256); g1.relu = 1;
+      g1.gramZ = c.SL(l, S_Z2); g1.zsGramZ = zS; g1.gramF = c.SL(l, S_F2); g1.gramG = c.keep ? c.SL(l, S_G2) : nullptr;
+      SGRL_TRY(run_gemm(c, g1));
+      g = lin(c, c.SL(l, S_A2), 256, zS, lp[L_FG2_W], lp[L_FG2_B], ub, 256, zS, T, 128, 256);
+      SGRL_TRY(run_gemm(c, g));
+      g = lin(c, ub, 256, zS, lp[L_L3_W], lp[L_L3_B], c.SL(l, S_T31), 512, zS, T, 512, 256); g.relu = 1;   // [linear3 | linear1]
+      SGRL_TRY(run_gemm(c, g));
+      pr[0] = lin(c, c.SL(l, S_T31) + 256, 512, zS, lp[L_L2_W], lp[L_L2_B], h_next, ld_hn, zS, T, 128, 256);
+      pr[0].rowdiv = c.SL(l, S_F2); pr[0].zsRow = zS;
+      pr[0].res1 = ub + 128; pr[0].zsR1 = zS; pr[0].ldr1 = 256;
+      pr[0].ln_gamma = c.P(lp[L_N2_W]); pr[0].ln_beta = c.P(lp[L_N2_B]); pr[0].ln_x = c.SL(l, S_X2); pr[0].ln_stats = c.SL(l, S_ST2);
+      pr[0].ln_x0 = c.SL(l, S_FF);
+      if (last) {        // the encoder's final LayerNorm rides on the last layer's norm2: h_final -> right part of SH = [s0 | h]
+        pr[0].ln2_gamma = c.P(Y.gp[G_NORM_W]); pr[0].ln2_beta = c.P(Y.gp[G_NORM_B]);
+        pr[0].ln2_y = c.S(T_SH) + ng; pr[0].ln2_ldy = KS; pr[0].ln2_stats = c.S(T_STF);
+      }
+      pr[1] = lin(c, c.SL(l, S_T31), 512, zS, lp[L_L4_W], lp[L_L4_B], c.SL(l, S_MM), 1024, zS, T, 1024, 256);
+      pr[1].rowdiv = c.SL(l, S_F2); pr[1].zsRow = zS;
+      SGRL_TRY(run_group(c, pr, 2));
+      launch_k(matapply_l5_fwd_kernel, dim3(grid_for_warps(T), c.nb), 256, 0, st, c.SL(l, S_Z3), c.SL(l, S_MM), c.P(lp[L_L5_W]), c.zsP, Vg, c.SL(l, S_DV),
+               c.keep ? c.SL(l, S_R) : nullptr, Vg_next, zS, T);
+      SGRL_LAUNCH_OK();
+      continue;
+    }
     // -- attention block: invariant features of Vg -> u = [g-mlp | h]
     FeatFwdP f{}; f.Xg = Vg; f.zsXg = zS; f.gd = c.S(T_GD); f.zsGd = zS; f.P1 = c.P(lp[L_GPROJ]); f.zsP = c.zsP;
     f.Z = c.SL(l, S_Z1); f.G = c.SL(l, S_G1); f.Fn = c.SL(l, S_F1); f.zsAct = zS; f.T = T; f.nb = c.nb;
@@ -372,7 +451,7 @@ inline int net_forward(const NetCtx& c, const float* obs, long long zsObs, const
     SGRL_TRY(side_join(c));
   }
   // final LayerNorm -> right part of SH = [s0 | h]
-  SGRL_TRY(layernorm_fwd(c, c.S(T_HL), 128, nullptr, 0, Y.gp[G_NORM_W], Y.gp[G_NORM_B], nullptr, c.S(T_SH) + ng, KS, c.S(T_STF)));
+  if (!fused) SGRL_TRY(layernorm_fwd(c, c.S(T_HL), 128, nullptr, 0, Y.gp[G_NORM_W], Y.gp[G_NORM_B], nullptr, c.S(T_SH) + ng, KS, c.S(T_STF)));
   // -- heads
   FeatFwdP fh{}; fh.head = 1; fh.Xg = c.S(T_VGF); fh.zsXg = zS; fh.V0 = c.S(T_V0); fh.zsV0 = zS; fh.gd = c.S(T_GD); fh.zsGd = zS;
   fh.P1 = c.P(Y.gp[G_GG_W]); fh.P2 = c.kind == ACTOR ? c.P(Y.gp[G_GPH_W]) : nullptr; fh.zsP = c.zsP;

@@ -185,6 +185,56 @@ int sgrl_gemm_presplit(const float* A, int lda, int trans_a, const float* B_hi, 
   return gemm_tc(g, ST(stream));
 }
 
+int sgrl_gemm_gram(const float* Z, const float* W_hi, const float* W_lo, const float* bias, float* C, int ldc, float* F, float* G,
+                   int T, int N, int relu, sgrl_stream_t stream) {
+  SGRL_CHECK(Z && W_hi && W_lo && C, "null pointer");
+  GemmP g = gemm_defaults();
+  g.gramZ = Z; g.gramF = F; g.gramG = G;
+  g.B = W_hi; g.Bhi = W_hi; g.Blo = W_lo; g.ldb = GP_K; g.C = C; g.ldc = ldc;
+  g.M = T; g.N = N; g.K = GP_K; g.bias = bias; g.relu = relu;
+  SGRL_CHECK(gemm_tc_eligible(g), "shape not eligible for the tcgen05 path");
+  return gemm_tc(g, ST(stream));
+}
+
+int sgrl_gemm_gd(const float* A, int lda, const float* W_hi, const float* W_lo, int ldw, const float* gd, float* Z, int T3, int K,
+                 sgrl_stream_t stream) {
+  SGRL_CHECK(A && W_hi && W_lo && gd && Z, "null pointer");
+  GemmP g = gemm_defaults();
+  g.A = A; g.lda = lda; g.B = W_hi; g.Bhi = W_hi; g.Blo = W_lo; g.ldb = ldw; g.C = Z; g.ldc = 32;
+  g.M = T3; g.N = 32; g.K = K; g.gdcols = gd;
+  SGRL_CHECK(gemm_tc_eligible(g), "shape not eligible for the tcgen05 path");
+  return gemm_tc(g, ST(stream));
+}
+
+int sgrl_gemm_ln(const float* A, int lda, const float* W_hi, const float* W_lo, const float* bias, const float* rowdiv,
+                 const float* res, int ldres, const float* gamma, const float* beta, const float* gamma2, const float* beta2,
+                 float* y, int ldy, float* x, float* x0, float* stats, float* y2, int ldy2, float* stats2, int T, int K,
+                 sgrl_stream_t stream) {
+  SGRL_CHECK(A && W_hi && W_lo && gamma && beta && y, "null pointer");
+  GemmP g = gemm_defaults();
+  g.A = A; g.lda = lda; g.B = W_hi; g.Bhi = W_hi; g.Blo = W_lo; g.ldb = K; g.C = y; g.ldc = ldy;
+  g.M = T; g.N = 128; g.K = K; g.bias = bias; g.rowdiv = rowdiv; g.res1 = res; g.ldr1 = ldres;
+  g.ln_gamma = gamma; g.ln_beta = beta; g.ln_x = x; g.ln_x0 = x0; g.ln_stats = stats;
+  g.ln2_gamma = gamma2; g.ln2_beta = beta2; g.ln2_y = y2; g.ln2_ldy = ldy2; g.ln2_stats = stats2;
+  SGRL_CHECK(gemm_tc_eligible(g), "shape not eligible for the tcgen05 path");
+  return gemm_tc(g, ST(stream));
+}
+
+int sgrl_gemm_pair(const float* A0, int lda0, const float* W0_hi, const float* W0_lo, const float* b0, float* C0, int ldc0, int M0, int N0,
+                   int K0, const float* A1, int lda1, const float* W1_hi, const float* W1_lo, const float* b1, float* C1, int ldc1, int M1,
+                   int N1, int K1, int relu, sgrl_stream_t stream) {
+  SGRL_CHECK(A0 && W0_hi && W0_lo && C0 && A1 && W1_hi && W1_lo && C1, "null pointer");
+  GemmP g[2];
+  g[0] = gemm_defaults();
+  g[0].A = A0; g[0].lda = lda0; g[0].B = W0_hi; g[0].Bhi = W0_hi; g[0].Blo = W0_lo; g[0].ldb = K0; g[0].C = C0; g[0].ldc = ldc0;
+  g[0].M = M0; g[0].N = N0; g[0].K = K0; g[0].bias = b0; g[0].relu = relu;
+  g[1] = gemm_defaults();
+  g[1].A = A1; g[1].lda = lda1; g[1].B = W1_hi; g[1].Bhi = W1_hi; g[1].Blo = W1_lo; g[1].ldb = K1; g[1].C = C1; g[1].ldc = ldc1;
+  g[1].M = M1; g[1].N = N1; g[1].K = K1; g[1].bias = b1; g[1].relu = relu;
+  SGRL_CHECK(gemm_tc_eligible(g[0]) && gemm_tc_eligible(g[1]), "shape not eligible for the tcgen05 path");
+  return gemm_tc_group(g, 2, ST(stream));
+}
+
 int sgrl_td3_smooth_action(const float* pi_target, const float* noise, float* next_action, float noise_clip, float max_action,
                            int64_t n, sgrl_stream_t stream) {
   SGRL_CHECK(pi_target && noise && next_action, "null pointer");

@@ -49,11 +49,12 @@ def compare_stash(mod, stash, tb, nb, z, trace, n_layers=3, tol=2e-5, skip=()):
             pad = torch.zeros(B, N, 2, 16, device=ref.device, dtype=ref.dtype)
             pad[..., :N] = ref
             ref = pad
-        if name in ("G1", "G2", "GH"):   # the kernels keep vec(G) as its upper triangle (528 entries, row-major i<=j) padded to 544
-            iu = torch.triu_indices(32, 32)
+        if name in ("G1", "G2", "GH"):   # the kernels keep vec(G) as its packed upper triangle (sgrl_b200/packing.py) padded to 544
+            from sgrl_b200.packing import pack_indices
+            slots, ri, ci = pack_indices()
             full = ref.reshape(-1, 32, 32)
             ref = torch.zeros(full.shape[0], 544, device=ref.device, dtype=ref.dtype)
-            ref[:, :528] = full[:, iu[0], iu[1]]
+            ref[:, slots] = full[:, ri, ci]
         ref = ref.reshape(tb.T, -1).to(got.device)
         assert ref.shape == got.shape, (key, ref.shape, got.shape)
         out.append((key, parity.rel_err(got, ref)))

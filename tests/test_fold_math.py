@@ -5,15 +5,22 @@ import numpy as np
 import torch
 
 
-def tri_index(i, j):                      # csrc/layout.h tri_index, i <= j
-    return i * 32 - (i * (i - 1)) // 2 + (j - i)
+from sgrl_b200.packing import GP_K, pack_indices, tri_index, tri_table
 
 
-def test_tri_index_matches_row_major_upper_triangle():
-    iu = torch.triu_indices(32, 32)
-    for p, (i, j) in enumerate(zip(iu[0].tolist(), iu[1].tolist())):
-        assert tri_index(i, j) == p
-    assert tri_index(31, 31) == 527
+def test_packing_is_a_bijection_with_the_documented_block_structure():
+    tab = tri_table()
+    assert len(tab) == GP_K and sum(e is not None for e in tab) == 528
+    pads = [p for p, e in enumerate(tab) if e is None]
+    assert pads == [478, 479, 510, 511] + list(range(532, 544))
+    # k-blocks 0..13: two off-diagonal 4x4 blocks each, row-major inside a block
+    for kb in range(14):
+        for h in range(2):
+            blk = tab[kb * 32 + h * 16: kb * 32 + h * 16 + 16]
+            i0, j0 = blk[0]
+            assert i0 % 4 == 0 and j0 % 4 == 0 and i0 < j0
+            assert blk == [(i0 + a, j0 + b) for a in range(4) for b in range(4)]
+    assert tri_index(0, 4) == 0 and tri_index(31, 31) == 448 + 64 + 19
 
 
 def test_folded_contraction_and_gradients():
@@ -23,7 +30,8 @@ def test_folded_contraction_and_gradients():
     W = torch.randn(O_, 1024, generator=g, dtype=torch.float64, requires_grad=True)
     G = torch.einsum("tri,trj->tij", Z, Z)
     y = G.reshape(T, 1024) @ W.T
-    iu = torch.triu_indices(32, 32)
+    _, ri, ci = pack_indices()
+    iu = (torch.tensor(ri), torch.tensor(ci))                           # the 528 real slots in packed order
     Gp = G[:, iu[0], iu[1]]                                             # (T, 528) packed triangle
     W3 = W.detach().reshape(O_, 32, 32)
     Wf = (W3 + W3.transpose(1, 2))[:, iu[0], iu[1]]
