@@ -11,7 +11,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsgrl_b200.so")
+LIB_PATH = os.environ.get("SGRL_LIB") or os.path.join(_HERE, "libsgrl_b200.so")      # SGRL_LIB: A/B runs of two builds (tools/)
 
 ACTOR, CRITIC = 0, 1
 

@@ -324,6 +324,9 @@ inline int net_forward(const NetCtx& c, const float* obs, long long zsObs, const
   static const int fused_env = getenv("SGRL_FUSED") ? atoi(getenv("SGRL_FUSED")) : 1;
   const bool fused = fused_env && c.use_tc && c.phi != nullptr && (long long)T3 * 32 * 128 >= (1 << 21);
   if (fused) SGRL_TRY(fold_weights(c, st));        // triangle-folded vec(G) consumers of every layer
+  // residual + LayerNorm inside the N = 128 GEMMs' epilogue (gemm_tc.cuh) — measured slower than GEMM + layernorm kernel on
+  // the branch lane at 2 304 tokens (23.2 vs 11.0 + 3.5 us, tools/fused_bench.py), so off by default
+  static const int ln_epi = getenv("SGRL_LN_EPI") ? atoi(getenv("SGRL_LN_EPI")) : 0;
   for (int l = 0; l < c.L; ++l) {
     const long long* lp = Y.lp[l];
     float* Vg = c.SL(l, S_VGIN);
@@ -362,11 +365,19 @@ inline int net_forward(const NetCtx& c, const float* obs, long long zsObs, const
       SGRL_TRY(run_gemm(c, g));
       SGRL_TRY(attention_fwd(c.SL(l, S_QKV), c.SL(l, S_VGP), c.S(T_GD), c.SL(l, S_O), c.SL(l, S_OG), c.SL(l, S_P), zS,
                              l == 0 ? c.P(Y.gp[G_REL_W]) : nullptr, l == 0 ? c.P(Y.gp[G_REL_B]) : nullptr, c.zsP, c.gr, c.nb, st));
-      pr[0] = lin(c, c.SL(l, S_O), 256, zS, lp[L_NGO_W], lp[L_NGO_B], ub + 128, 256, zS, T, 128, 256);
-      pr[0].res1 = ua + 128; pr[0].zsR1 = zS; pr[0].ldr1 = 256;
-      pr[0].ln_gamma = c.P(lp[L_N1_W]); pr[0].ln_beta = c.P(lp[L_N1_B]); pr[0].ln_x = c.SL(l, S_X1); pr[0].ln_stats = c.SL(l, S_ST1);
+      if (ln_epi) {
+        pr[0] = lin(c, c.SL(l, S_O), 256, zS, lp[L_NGO_W], lp[L_NGO_B], ub + 128, 256, zS, T, 128, 256);
+        pr[0].res1 = ua + 128; pr[0].zsR1 = zS; pr[0].ldr1 = 256;
+        pr[0].ln_gamma = c.P(lp[L_N1_W]); pr[0].ln_beta = c.P(lp[L_N1_B]); pr[0].ln_x = c.SL(l, S_X1); pr[0].ln_stats = c.SL(l, S_ST1);
+      } else {
+        pr[0] = lin(c, c.SL(l, S_O), 256, zS, lp[L_NGO_W], lp[L_NGO_B], c.SL(l, S_X1), 128, zS, T, 128, 256);
+      }
       pr[1] = lin(c, c.SL(l, S_OG), 256, zS, lp[L_GO_W], -1, c.SL(l, S_DV), 128, zS, T3, 128, 256);
       SGRL_TRY(run_group(c, pr, 2));
+      if (!ln_epi) {     // h1 = LN1(h + ng_out(o)) on the branch lane: first needed by [linear3 | linear1]
+        SGRL_TRY(side_fork(c, &sb, 0));
+        SGRL_TRY(layernorm_fwd(c, ua + 128, 256, c.SL(l, S_X1), 128, lp[L_N1_W], lp[L_N1_B], c.SL(l, S_X1), ub + 128, 256, c.SL(l, S_ST1), sb));
+      }
       pr[0] = lin(c, c.SL(l, S_DV), 128, zS, lp[L_GP2], -1, c.SL(l, S_Z2), 32, zS, T3, 32, 128);
       pr[0].gdcols = c.S(T_GD); pr[0].zsGd = zS;
       pr[1] = lin(c, c.SL(l, S_DV), 128, zS, lp[L_GP3], -1, c.SL(l, S_Z3), 32, zS, T3, 32, 128);
@@ -377,23 +388,34 @@ inline int net_forward(const NetCtx& c, const float* obs, long long zsObs, const
       SGRL_TRY(run_gemm(c, g1));
       g = lin(c, c.SL(l, S_A2), 256, zS, lp[L_FG2_W], lp[L_FG2_B], ub, 256, zS, T, 128, 256);
       SGRL_TRY(run_gemm(c, g));
+      if (!ln_epi) SGRL_TRY(side_join(c, 0));
       g = lin(c, ub, 256, zS, lp[L_L3_W], lp[L_L3_B], c.SL(l, S_T31), 512, zS, T, 512, 256); g.relu = 1;   // [linear3 | linear1]
       SGRL_TRY(run_gemm(c, g));
-      pr[0] = lin(c, c.SL(l, S_T31) + 256, 512, zS, lp[L_L2_W], lp[L_L2_B], h_next, ld_hn, zS, T, 128, 256);
-      pr[0].rowdiv = c.SL(l, S_F2); pr[0].zsRow = zS;
-      pr[0].res1 = ub + 128; pr[0].zsR1 = zS; pr[0].ldr1 = 256;
-      pr[0].ln_gamma = c.P(lp[L_N2_W]); pr[0].ln_beta = c.P(lp[L_N2_B]); pr[0].ln_x = c.SL(l, S_X2); pr[0].ln_stats = c.SL(l, S_ST2);
-      pr[0].ln_x0 = c.SL(l, S_FF);
-      if (last) {        // the encoder's final LayerNorm rides on the last layer's norm2: h_final -> right part of SH = [s0 | h]
-        pr[0].ln2_gamma = c.P(Y.gp[G_NORM_W]); pr[0].ln2_beta = c.P(Y.gp[G_NORM_B]);
-        pr[0].ln2_y = c.S(T_SH) + ng; pr[0].ln2_ldy = KS; pr[0].ln2_stats = c.S(T_STF);
+      if (ln_epi) {
+        pr[0] = lin(c, c.SL(l, S_T31) + 256, 512, zS, lp[L_L2_W], lp[L_L2_B], h_next, ld_hn, zS, T, 128, 256);
+        pr[0].res1 = ub + 128; pr[0].zsR1 = zS; pr[0].ldr1 = 256;
+        pr[0].ln_gamma = c.P(lp[L_N2_W]); pr[0].ln_beta = c.P(lp[L_N2_B]); pr[0].ln_x = c.SL(l, S_X2); pr[0].ln_stats = c.SL(l, S_ST2);
+        pr[0].ln_x0 = c.SL(l, S_FF);
+        if (last) {        // the encoder's final LayerNorm rides on the last layer's norm2: h_final -> right part of SH = [s0 | h]
+          pr[0].ln2_gamma = c.P(Y.gp[G_NORM_W]); pr[0].ln2_beta = c.P(Y.gp[G_NORM_B]);
+          pr[0].ln2_y = c.S(T_SH) + ng; pr[0].ln2_ldy = KS; pr[0].ln2_stats = c.S(T_STF);
+        }
+      } else {
+        pr[0] = lin(c, c.SL(l, S_T31) + 256, 512, zS, lp[L_L2_W], lp[L_L2_B], c.SL(l, S_FF), 128, zS, T, 128, 256);
       }
+      pr[0].rowdiv = c.SL(l, S_F2); pr[0].zsRow = zS;
       pr[1] = lin(c, c.SL(l, S_T31), 512, zS, lp[L_L4_W], lp[L_L4_B], c.SL(l, S_MM), 1024, zS, T, 1024, 256);
       pr[1].rowdiv = c.SL(l, S_F2); pr[1].zsRow = zS;
       SGRL_TRY(run_group(c, pr, 2));
+      if (!ln_epi) {     // h' = LN2(h1 + linear2(..)/F2) (+ the encoder's final norm) on the branch lane, next to the matrix apply
+        SGRL_TRY(side_fork(c, &sb, 0));
+        SGRL_TRY(layernorm_fwd(c, ub + 128, 256, c.SL(l, S_FF), 128, lp[L_N2_W], lp[L_N2_B], c.SL(l, S_X2), h_next, ld_hn, c.SL(l, S_ST2), sb));
+        if (last) SGRL_TRY(layernorm_fwd(c, c.S(T_HL), 128, nullptr, 0, Y.gp[G_NORM_W], Y.gp[G_NORM_B], nullptr, c.S(T_SH) + ng, KS, c.S(T_STF), sb));
+      }
       launch_k(matapply_l5_fwd_kernel, dim3(grid_for_warps(T), c.nb), 256, 0, st, c.SL(l, S_Z3), c.SL(l, S_MM), c.P(lp[L_L5_W]), c.zsP, Vg, c.SL(l, S_DV),
                c.keep ? c.SL(l, S_R) : nullptr, Vg_next, zS, T);
       SGRL_LAUNCH_OK();
+      if (!ln_epi) SGRL_TRY(side_join(c, 0));
       continue;
     }
     // -- attention block: invariant features of Vg -> u = [g-mlp | h]
