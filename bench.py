@@ -100,45 +100,82 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------
-def cpu_reference_rate(morph, batch, budget_s=20.0, steps=None, warmup=1, threads=None):
-    """The reference algorithm (oracle port of Agent.update: torch CPU ops + torch Adam +
-    clip_grad_norm_) timed on this host's cores.  Returns samples/s and a description."""
+def _cpu_steppers(morph, batch):
+    """(kind, step(it)) callables for one TD3 update on this host's cores: the LIVE reference (src/agent.py Agent.update,
+    unmodified, imported by oracle/ref_loader from /root/reference/src, baseline/_ref/src or $SGRL_REF) when it is on this
+    machine, and always the oracle port (oracle/set_oracle.TD3Oracle)."""
     import torch
-    from oracle import set_oracle as O
+    from oracle import ref_loader, set_oracle as O
     from sgrl_b200 import graph as G, morphologies as M, synth
-    threads = threads or os.cpu_count()
-    torch.set_num_threads(threads)
     par = M.ALL[morph]
-    g = G.build_graph(par)
     pa = {"actor." + k: v for k, v in O.synth_params("actor", 11).items()}
     pc = {"critic1." + k: v for k, v in O.synth_params("critic", 12).items()}
     pc.update({"critic2." + k: v for k, v in O.synth_params("critic", 13).items()})
-    td3 = O.TD3Oracle(pa, pc)
     b = synth.make_batch(batch, len(par), seed=1)
+    out = {}
+    if ref_loader.find_reference():
+        try:
+            import contextlib
+            with contextlib.redirect_stdout(sys.stderr):      # the reference prints its argument sizes: keep stdout to the JSON line
+                ref = ref_loader.load_reference()
+                g = ref.utils.getGraphDict(par, ["pre", "inlcrs", "postlcrs"], device=torch.device("cpu"))
+                ag = ref.agent.Agent(ref_loader.default_args())
+            sd = {}
+            for pre in ("actor.", "actor_target."):
+                sd.update({pre + k: v.clone() for k, v in pa.items()})
+            for pre in ("critic.", "critic_target."):
+                sd.update({pre + k: v.clone() for k, v in pc.items()})
+            ag.load_state_dict(sd)
+            ag.change_morphology(g)
+            out["reference"] = lambda it: ag.update(b, it)
+        except Exception as ex:      # missing host-only dependency of the reference tree: say so, fall back to the port
+            sys.stderr.write(f"bench: live reference not usable ({type(ex).__name__}: {ex}); timing the oracle port\n")
+    g2 = G.build_graph(par)
+    td3 = O.TD3Oracle(pa, pc)
     noise = torch.randn(batch, 3 * len(par)) * 0.2
+    out["port"] = lambda it: td3.update(b, it, noise, g2)
+    return out
+
+
+def cpu_reference_rate(morph, batch, budget_s=20.0, steps=None, warmup=1, threads=None):
+    """The reference's CPU implementation of Agent.update timed on this host's cores: the live reference when present
+    (kind "reference"), else the oracle port (kind "port": torch CPU ops + torch Adam + clip_grad_norm_, the same math).
+    When both exist the port is timed on two updates as well and the port/reference time ratio is reported."""
+    import torch
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    steppers = _cpu_steppers(morph, batch)
+    kind = "reference" if "reference" in steppers else "port"
+    step = steppers[kind]
     it = 0
     for _ in range(max(warmup, 1)):
-        t0 = time.perf_counter(); td3.update(b, it, noise, g); it += 1
+        t0 = time.perf_counter(); step(it); it += 1
         one = time.perf_counter() - t0
     if steps is None:
         steps = max(2, int(budget_s / max(one, 1e-3)) // 2 * 2)
         steps = min(steps, 20)
-    steps += steps % 2
-    it = 0
     t0 = time.perf_counter()
     for _ in range(steps):
-        td3.update(b, it, noise, g); it += 1
+        step(it); it += 1
     dt = time.perf_counter() - t0
-    return {"value": batch * steps / dt, "unit": "samples/s", "cores": threads, "kind": "port",
-            "sample": f"{steps} TD3 updates (policy_freq=2) of {morph} B={batch} with the oracle port of src/agent.py:117-183 on {threads} host threads, {dt:.1f}s",
-            "ms_per_update": 1e3 * dt / steps}
+    r = {"value": batch * steps / dt, "unit": "samples/s", "cores": threads, "kind": kind,
+         "sample": f"{steps} TD3 updates (policy_freq=2) of {morph} B={batch} with " +
+                   ("the unmodified reference Agent.update (src/agent.py:117-183)" if kind == "reference" else
+                    "the oracle port of src/agent.py:117-183") + f" on {threads} host threads, {dt:.1f}s",
+         "ms_per_update": 1e3 * dt / steps}
+    if kind == "reference":
+        port = steppers["port"]
+        port(0); port(1)
+        t0 = time.perf_counter(); port(2); port(3)
+        r["port_over_reference_time"] = (time.perf_counter() - t0) / 2 / (dt / steps)
+    return r
 
 
 def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = a.steps + a.steps % 2
+    steps = a.steps
     # bound the sample so the whole run ends within a few minutes: shrink the per-step batch if needed
     probe = cpu_reference_rate(a.morph, a.batch, steps=2, warmup=1)
     batch = a.batch
@@ -151,7 +188,7 @@ def run_reference(a):
             "steps": steps, "warmup": a.warmup, "ms_per_step": r["ms_per_update"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{a.morph} TD3 Agent.update, B={a.batch}, N={len(M.ALL[a.morph])} limbs, policy_freq=2", "cpu_sample_batch": batch},
-            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "port_over_reference_time") if k in r},
             "e2e": {"value": r["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -171,9 +208,7 @@ def run_ours(a):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    K = a.steps + a.steps % 2
-    W = max(a.warmup, 3)
-    W += W % 2
+    K, W = a.steps, a.warmup              # exactly as asked (the contract wants W >= 3: the default is 6)
     par = M.ALL[a.morph]
     N, B = len(par), a.batch
     torch.manual_seed(0)
@@ -203,8 +238,13 @@ def run_ours(a):
             torch.cuda.synchronize()
 
     agent.lazy_stats = True
-    for i in range(W):
-        agent.update(devb[i % nbat], i, noise=noise[i % nbat])
+    # set-up (not warm-up): the first two updates of a plan run eagerly (one per kind of step), the next two are captured as
+    # CUDA graphs; from here on every update is a replay.  `it` keeps counting so actor steps alternate through all phases.
+    it = 0
+    for _ in range(4):
+        agent.update(devb[it % nbat], it, noise=noise[it % nbat]); it += 1
+    for _ in range(W):
+        agent.update(devb[it % nbat], it, noise=noise[it % nbat]); it += 1
     barrier()
     # ---- timed: K updates, inputs resident in HBM, L2 flushed between steps (outside the event pairs)
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
@@ -216,7 +256,7 @@ def run_ours(a):
     for i in range(K):
         flush.zero_()
         ev[i][0].record()
-        agent.update(devb[i % nbat], i, noise=noise[i % nbat])
+        agent.update(devb[it % nbat], it, noise=noise[it % nbat]); it += 1
         ev[i][1].record()
     barrier()
     launches = (_lib.lib.sgrl_launch_count() + agent.graph_replayed_launches - l0) / K
@@ -230,12 +270,12 @@ def run_ours(a):
 
     # ---- e2e: the public call with HOST (pinned) buffers, result read back every step
     agent.lazy_stats = False
-    for i in range(2):
-        agent.update(host[i % nbat], i)["loss/critic_loss"].item()
+    for _ in range(4 + min(W, 4)):      # host batches draw the target-policy noise in the kernel: their own pair of graphs (2 eager runs + 2 captures)
+        agent.update(host[it % nbat], it)["loss/critic_loss"].item(); it += 1
     barrier()
     t0 = time.perf_counter()
     for i in range(K):
-        ld = agent.update(host[i % nbat], i)
+        ld = agent.update(host[it % nbat], it); it += 1
         ld["loss/critic_loss"].item()
     barrier()
     e2e_s = time.perf_counter() - t0
@@ -400,7 +440,7 @@ def run_ours(a):
     # ---- reference algorithm on this box's host cores (rank 0, N=1 only; bounded sample)
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         cb = cpu_reference_rate(a.morph, B, budget_s=15.0)
-        line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "port_over_reference_time") if k in cb}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -161,6 +161,13 @@ int sgrl_split_tf32(const float* w, float* hi, float* lo, int64_t n, sgrl_stream
 /* ---- K5: TD3 glue (agent.py:127-148,167) -------------------------------------------------- */
 int sgrl_td3_smooth_action(const float* pi_target, const float* noise, float* next_action, float noise_clip,
                            float max_action, int64_t n, sgrl_stream_t stream);
+/* The same with the target-policy noise drawn inside the kernel: eps ~ N(0, policy_noise^2) (agent.py:128,
+ * torch.randn_like(action) * policy_noise) from Philox4x32-10 keyed by `seed`, counter = {element / 4, 0, *draw, 0}
+ * (Box-Muller, 4 normals per call).  `draw` is a device counter bumped once per update (sgrl_bump_step), so a replayed
+ * CUDA graph draws fresh noise.  noise_out (nullable) receives eps before clipping. */
+int sgrl_td3_smooth_action_rng(const float* pi_target, float* next_action, float* noise_out, float policy_noise,
+                               float noise_clip, float max_action, int64_t n, uint64_t seed, const int32_t* draw,
+                               sgrl_stream_t stream);
 /* target = r*scale + (1-done)*discount*min(tq1,tq2) broadcast over limbs; loss (1 float, accumulates)
  * = mse(q1,target)+mse(q2,target); dq1,dq2 = dloss/dq. tok_graph (T) maps token -> sample.
  * tok_weight (T, nullable): weight of each token in the loss for packed mixed-morphology batches
@@ -168,16 +175,19 @@ int sgrl_td3_smooth_action(const float* pi_target, const float* noise, float* ne
  * per-morphology loss, src/trainer.py:245-250); NULL = 1/T (one morphology, exactly agent.py:146-148). */
 int sgrl_td3_critic_loss(const float* q1, const float* q2, const float* tq1, const float* tq2, const float* reward,
                          const float* done, const int32_t* tok_graph, const float* tok_weight, float* target, float* dq1,
-                         float* dq2, float* loss, float discount, float reward_scale, int T, sgrl_stream_t stream);
+                         float* dq2, float* loss, float discount, float reward_scale, int T,
+                         double* reward_stats /*nullable: {sum, sum of squares} of reward*reward_scale over the G graphs, agent.py:158-161*/,
+                         int G, sgrl_stream_t stream);
 int sgrl_td3_actor_loss(const float* q1, const float* tok_weight, float* dq1, float* loss, int T, sgrl_stream_t stream);
 
 /* ---- K6: optimizer (agent.py:150-156,170-178; common/functional.py:7-10) -------------------- */
 int sgrl_sumsq(const float* g, int64_t n, float* out /*accumulates*/, sgrl_stream_t stream);
 /* clip_grad_norm_(max_norm) + Adam(lr,b1,b2,eps) in one pass over the flat live arena.  sumsq: device
  * scalar with sum(g^2) (after the all-reduce); step: device int, the 1-based step count to apply;
- * grad_scale multiplies g first (1/world_size). */
+ * grad_scale multiplies g first (1/world_size).  lr / betas / eps are doubles, like the Python floats torch.optim.Adam
+ * derives 1 - beta and the bias corrections from. */
 int sgrl_adam_clip(float* p, const float* g, float* m, float* v, int64_t n, const float* sumsq, const int32_t* step,
-                   float lr, float beta1, float beta2, float eps, float max_norm, float grad_scale,
+                   double lr, double beta1, double beta2, double eps, float max_norm, float grad_scale,
                    float* p_hi /*nullable: refreshed tf32 split of p*/, float* p_lo, sgrl_stream_t stream);
 int sgrl_bump_step(int32_t* step, sgrl_stream_t stream);
 int sgrl_polyak(float* target, const float* source, int64_t n, float tau,

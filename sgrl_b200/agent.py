@@ -52,8 +52,10 @@ class FusedAdam:
         self._sync_device()
         self.module.grad_arena().zero_()
 
-    def step(self, max_norm: float = 0.0, world_size: int = 1):
-        """Clip (if max_norm > 0) and apply one Adam step from module.grad_arena()."""
+    def step(self, max_norm: float = 0.0, world_size: int = 1, keep_split: Optional[bool] = None):
+        """Clip (if max_norm > 0) and apply one Adam step from module.grad_arena().  keep_split: also rewrite the tf32
+        hi/lo split of the parameters (None: if it is fresh now).  A caller that captures this call into a CUDA graph
+        passes the decision explicitly and invalidates the split itself when it is False (Agent._run_update)."""
         self._sync_device()
         m = self.module
         g, p = m.grad_arena(), m.live_arena
@@ -62,7 +64,9 @@ class FusedAdam:
         if max_norm > 0:
             check(lib.sgrl_sumsq(ptr(g), n, ptr(self.sumsq), st), "sgrl_sumsq")
         check(lib.sgrl_bump_step(ptr(self.step_count), st), "sgrl_bump_step")
-        fresh = m._split is not None and m._split_fresh and m._split_version == m._arena._version
+        fresh = m.split_is_fresh() if keep_split is None else (keep_split and m._split is not None)
+        if not fresh:
+            m.invalidate_split()
         hi, lo = (m._split[0], m._split[1]) if fresh else (None, None)     # keep a valid tf32 split valid (else it is rebuilt lazily)
         check(lib.sgrl_adam_clip(ptr(p), ptr(g), ptr(self.exp_avg), ptr(self.exp_avg_sq), n, ptr(self.sumsq), ptr(self.step_count),
                                  self.lr, self.betas[0], self.betas[1], self.eps, float(max_norm), 1.0 / world_size, ptr(hi), ptr(lo), st),
@@ -78,15 +82,15 @@ class FusedAdam:
         self.lr, self.betas, self.eps = sd["lr"], tuple(sd["betas"]), sd["eps"]
 
 
-def soft_update_network(source: SetNetModule, target: SetNetModule, tau: float):
+def soft_update_network(source: SetNetModule, target: SetNetModule, tau: float, keep_split: Optional[bool] = None):
     """theta_t <- tau*theta + (1-tau)*theta_t over ALL parameters incl. the dead ones
-    (src/common/functional.py:7-10) as one pass over the flat arenas."""
+    (src/common/functional.py:7-10) as one pass over the flat arenas.  keep_split: see FusedAdam.step."""
     s, t = source.full_arena, target.full_arena
     if s.device.type != "cuda":
-        with torch.no_grad():
-            t.mul_(1 - tau).add_(s, alpha=tau)
-        return
-    fresh = target._split is not None and target._split_fresh and target._split_version == target._arena._version
+        raise RuntimeError("sgrl_b200.soft_update_network needs the modules on a CUDA device (no CPU fallback)")
+    fresh = target.split_is_fresh() if keep_split is None else (keep_split and target._split is not None)
+    if not fresh:
+        target.invalidate_split()
     hi, lo = (target._split[0], target._split[1]) if fresh else (None, None)
     check(lib.sgrl_polyak(ptr(t), ptr(s), s.numel(), float(tau), ptr(hi), ptr(lo), target.live_arena.numel(), stream()), "sgrl_polyak")
 
@@ -100,9 +104,22 @@ class _UpdatePlan:
         T, G = tb.T, tb.G
         f = lambda *shape: torch.empty(*shape, dtype=torch.float32, device=dev)
         self.tb, self.agent = tb, agent
-        # inputs as packed tokens: (T,41) observations / (T,3) actions are exactly the reference's (B, N*41) / (B, N*3) rows
-        self.obs, self.nobs, self.act = f(T, 41), f(T, 41), f(T, 3)
-        self.rew, self.done, self.noise = f(G), f(G), f(T, 3)
+        # inputs as packed tokens: (T,41) observations / (T,3) actions are exactly the reference's (B, N*41) / (B, N*3) rows.
+        # One contiguous block [obs | next_obs | action | reward | done] so that a host batch arrives as ONE H2D copy out of a
+        # pinned, double-buffered staging block (the reference issues five pageable copies, src/agent.py:119-125)
+        sizes = (T * 41, T * 41, T * 3, G, G)
+        self.inbuf = f(sum(sizes))
+        self.obs, self.nobs, self.act, self.rew, self.done = (v.view(-1, w) if w else v for v, w in
+                                                              zip(torch.split(self.inbuf, sizes), (41, 41, 3, 0, 0)))
+        self.h_in = [torch.empty(sum(sizes), dtype=torch.float32, pin_memory=True) for _ in range(2)]
+        self.h_np = [tuple(x.numpy() for x in torch.split(h, sizes)) for h in self.h_in]
+        self.h_ev = [torch.cuda.Event(), torch.cuda.Event()]
+        self.h_turn = 0
+        self.noise = f(T, 3)
+        # target-policy noise drawn inside the smoothing kernel (Philox keyed by seed, counter = draw): graph-replay safe
+        self.draw = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.seed = (torch.initial_seed() + 0x9E3779B97F4A7C15 * (len(agent._plans) + 1)) & 0xFFFFFFFFFFFFFFFF
+        self.rstats = torch.zeros(2, dtype=torch.float64, device=dev)     # {sum, sum of squares} of the scaled rewards
         self.a_t, self.next_action, self.pi = f(1, T, 3), f(T, 3), f(1, T, 3)
         self.tq, self.q, self.q1 = f(2, T, 1), f(2, T, 1), f(1, T, 1)
         self.dq, self.dq1, self.dact = f(2, T, 1), f(1, T, 1), f(1, T, 3)
@@ -115,64 +132,84 @@ class _UpdatePlan:
         self.ws = f(max(cr.ws_floats(T, 2), ac.ws_floats(T, 1)))
         self.s1, self.s2 = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
         self.ev_start, self.ev_a, self.ev_c = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
+        # the fused Adam / Polyak passes of this plan also rewrite the tf32 split (decided once per plan: the captured graphs
+        # bake the pointers in).  Plans too small for the tcgen05 path leave the split stale; _run_update then marks it so.
+        self.keep_split = all(m.use_tc and T >= m.SPLIT_MIN_TOKENS for m in (agent.actor, agent.critic, agent.actor_target, agent.critic_target))
         self.graphs = {}
-        self.graph_launches = {True: 0, False: 0}      # kernels of this library inside each captured graph
-        self.eager_runs = {True: 0, False: 0}
+        self.graph_launches = {}      # (actor_step, rng) -> kernels of this library inside the captured graph
+        self.eager_runs = {}
 
-    def load(self, batches, noises, policy_noise: float):
-        """Stage the replay batch of every morphology of the plan (host numpy / pinned or device tensors) into the static
-        input buffers.  batches[i]: dict obs (B_i, 41 N_i), action (B_i, 3 N_i), next_obs, reward (B_i,1), done (B_i,1)."""
+    def load(self, batches, noises):
+        """Stage the replay batch of every morphology of the plan (host numpy / CPU or device tensors) into the static
+        input buffers.  batches[i]: dict obs (B_i, 41 N_i), action (B_i, 3 N_i), next_obs, reward (B_i,1), done (B_i,1).
+        Host batches are packed into a pinned staging block and sent as one copy; device batches are copied in place.
+        Returns True when noise was injected (False: the smoothing kernel draws it)."""
         parts = self.tb.parts
         if len(batches) != len(parts):
             raise ValueError(f"plan holds {len(parts)} morphologies, got {len(batches)} batches")
-        for i, ((t0, t1, g0, g1, n), batch) in enumerate(zip(parts, batches)):
+        keys = (("obs", 41), ("next_obs", 41), ("action", 3))
+        on_host = all(not (torch.is_tensor(b[k]) and b[k].is_cuda) for b in batches for k in ("obs", "next_obs", "action", "reward", "done"))
+        if on_host:
+            k = self.h_turn
+            self.h_turn ^= 1
+            self.h_ev[k].synchronize()                    # the copy that last read this staging block has finished
+            h_obs, h_nobs, h_act, h_rew, h_done = self.h_np[k]
+            dst_of = {"obs": h_obs, "next_obs": h_nobs, "action": h_act}
+        for (t0, t1, g0, g1, n), batch in zip(parts, batches):
             B = g1 - g0
-            for dst, key, w in ((self.obs, "obs", 41), (self.act, "action", 3), (self.nobs, "next_obs", 41)):
+            for key, w in keys:
                 src = batch[key]
-                if not torch.is_tensor(src):
-                    src = torch.as_tensor(np.asarray(src), dtype=torch.float32)
                 if tuple(src.shape) != (B, n * w):
                     raise ValueError(f"{key}: expected {(B, n * w)} for this morphology, got {tuple(src.shape)}")
-                dst[t0:t1].view(B, n * w).copy_(src, non_blocking=True)
-            for dst, key in ((self.rew, "reward"), (self.done, "done")):
+                if on_host:
+                    dst_of[key][t0 * w:t1 * w] = (src.numpy() if torch.is_tensor(src) else np.asarray(src)).reshape(-1)
+                else:
+                    dst = {"obs": self.obs, "next_obs": self.nobs, "action": self.act}[key]
+                    dst[t0:t1].view(B, n * w).copy_(_as_tensor(src), non_blocking=True)
+            for key in ("reward", "done"):
                 src = batch[key]
-                if not torch.is_tensor(src):
-                    src = torch.as_tensor(np.asarray(src), dtype=torch.float32)
-                dst[g0:g1].copy_(src.reshape(B), non_blocking=True)
-            nz = None if noises is None else noises[i]
-            if nz is not None:
-                if not torch.is_tensor(nz):
-                    nz = torch.as_tensor(np.asarray(nz), dtype=torch.float32)
-                self.noise[t0:t1].view(B, n * 3).copy_(nz.reshape(B, n * 3), non_blocking=True)
-        if noises is None:
-            self.noise.normal_(0.0, policy_noise)                                     # agent.py:128
+                if on_host:
+                    (h_rew if key == "reward" else h_done)[g0:g1] = (src.numpy() if torch.is_tensor(src) else np.asarray(src)).reshape(-1)
+                else:
+                    (self.rew if key == "reward" else self.done)[g0:g1].copy_(_as_tensor(src).reshape(B), non_blocking=True)
+        if on_host:
+            self.inbuf.copy_(self.h_in[k], non_blocking=True)
+            self.h_ev[k].record()
+        if noises is None or all(nz is None for nz in noises):
+            return False
+        for (t0, t1, g0, g1, n), nz in zip(parts, noises):
+            if nz is None:
+                raise ValueError("target-policy noise must be given for every morphology of the plan or for none")
+            self.noise[t0:t1].view(g1 - g0, n * 3).copy_(_as_tensor(nz).reshape(g1 - g0, n * 3), non_blocking=True)
+        return True
 
-    def replay(self, actor_step: bool):
-        g = self.graphs.get(actor_step)
+    def replay(self, actor_step: bool, rng: bool):
+        key = (actor_step, rng)
+        g = self.graphs.get(key)
         if g is None:
             # one eager run first (lazy one-time initialisation inside the library: function attributes, side streams,
             # tensor-map cache), then capture the second
-            if self.eager_runs[actor_step] < 1:
-                self.eager_runs[actor_step] += 1
-                self.agent._update_impl(self, actor_step)
+            if self.eager_runs.get(key, 0) < 1:
+                self.eager_runs[key] = 1
+                self.agent._update_impl(self, actor_step, rng)
                 return
             try:
                 torch.cuda.synchronize()
                 g = torch.cuda.CUDAGraph()
                 l0 = lib.sgrl_launch_count()
                 with torch.cuda.graph(g):
-                    self.agent._update_impl(self, actor_step)
-                self.graph_launches[actor_step] = lib.sgrl_launch_count() - l0
+                    self.agent._update_impl(self, actor_step, rng)
+                self.graph_launches[key] = lib.sgrl_launch_count() - l0
             except Exception as ex:   # keep running eagerly (still the CUDA path); say so once
                 warnings.warn(f"sgrl_b200: CUDA-graph capture of Agent.update failed ({ex}); running eagerly")
                 self.agent.use_graphs = False
                 torch.cuda.synchronize()
-                self.agent._update_impl(self, actor_step)
+                self.agent._update_impl(self, actor_step, rng)
                 return
-            self.graphs[actor_step] = g
-            self.agent.graph_replayed_launches -= self.graph_launches[actor_step]   # the capture itself was counted by the library
+            self.graphs[key] = g
+            self.agent.graph_replayed_launches -= self.graph_launches[key]   # the capture itself was counted by the library
         g.replay()
-        self.agent.graph_replayed_launches += self.graph_launches[actor_step]
+        self.agent.graph_replayed_launches += self.graph_launches[key]
 
 
 class _RolloutPlan:
@@ -266,6 +303,9 @@ class Agent(nn.Module):
         self.reward_scale = args.agent.reward_scale
         self.lazy_stats = False      # True: reward statistics returned as 0-dim tensors (no host sync)
         self.use_graphs = os.environ.get("SGRL_GRAPHS", "1") != "0"   # replay Agent.update as a captured CUDA graph
+        # one plan (static buffers + two or three captured graphs) per (morphology tables, batch size).  The reference's
+        # training sets hold up to ~30 morphologies (CWHH++): size the cache from SGRL_MAX_PLANS, evict least recently used
+        self.max_plans = max(1, int(os.environ.get("SGRL_MAX_PLANS", "32")))
         self._plans: Dict = {}
         self._packed_tables: Dict = {}
         self._plan_sig = None
@@ -283,16 +323,22 @@ class Agent(nn.Module):
     def _allreduce(self, g: torch.Tensor, world: int):
         if world > 1:
             import torch.distributed as dist
+            # eager runs only (no-op under capture): the collective's stream waits on an event recorded right after
+            # programmatic-launch kernels, the case csrc/net.cuh stream_fence exists for
+            if g.is_cuda:
+                check(lib.sgrl_stream_fence(stream()))
             dist.all_reduce(g, op=dist.ReduceOp.SUM)
 
     def _plan(self, tb) -> "_UpdatePlan":
         key = id(tb)
         plan = self._plans.get(key)
         if plan is None or plan.tb is not tb:
-            if len(self._plans) >= 8:
-                self._plans.clear()
+            while len(self._plans) >= self.max_plans:      # least recently used plan goes (one entry, not the whole cache)
+                self._plans.pop(next(iter(self._plans)))
             plan = _UpdatePlan(self, tb)
-            self._plans[key] = plan
+        else:
+            self._plans.pop(key)
+        self._plans[key] = plan                            # dicts keep insertion order: most recently used last
         return plan
 
     def update(self, data_batch: Dict, it: int, noise: Optional[torch.Tensor] = None):
@@ -317,8 +363,8 @@ class Agent(nn.Module):
         key = tuple((id(g.get("relation")), tuple(g["parents"]), int(b["obs"].shape[0])) for g, b in batches)
         tb = self._packed_tables.get(key)
         if tb is None:
-            if len(self._packed_tables) > 16:
-                self._packed_tables.clear()
+            while len(self._packed_tables) >= self.max_plans:
+                self._packed_tables.pop(next(iter(self._packed_tables)))
             tb = make_packed_tables([(g, int(b["obs"].shape[0])) for g, b in batches], self.actor.full_arena.device)
             self._packed_tables[key] = tb
         return self._run_update(tb, [b for _, b in batches], it, noises)
@@ -338,10 +384,10 @@ class Agent(nn.Module):
 
         def load(plan):
             buffer.gather_into(idx, plan.obs, plan.act, plan.nobs, plan.rew, plan.done)
-            if noise is not None:
-                plan.noise.view(B, n * 3).copy_(torch.as_tensor(noise, dtype=torch.float32).reshape(B, n * 3), non_blocking=True)
-            else:
-                plan.noise.normal_(0.0, float(self.args.policy_noise))                # agent.py:128
+            if noise is None:
+                return False                                                          # drawn in the smoothing kernel (agent.py:128)
+            plan.noise.view(B, n * 3).copy_(torch.as_tensor(noise, dtype=torch.float32).reshape(B, n * 3), non_blocking=True)
+            return True
 
         return self._run_update(tb, None, it, None, loader=load)
 
@@ -352,33 +398,39 @@ class Agent(nn.Module):
             raise RuntimeError("sgrl_b200.Agent.update needs the modules on a CUDA device (no CPU fallback)")
         mods = (self.actor, self.actor_target, self.critic, self.critic_target)
         # the plans (and their captured graphs) hold raw pointers: drop them when a module was moved / re-flattened or
-        # its GEMM path changed; parameters edited from Python (load_state_dict, p.data.copy_) only stale the tf32 split
-        sig = tuple((m._arena.data_ptr(), int(m.use_tc)) for m in mods)
+        # its GEMM path changed.  Parameters edited from Python only stale the tf32 split: in-place torch writes and
+        # load_state_dict are detected (SetNetModule._write_stamp), writes through p.data need module.invalidate_split()
+        for m in mods:
+            m._split_for(tb.T, True)
+        sig = tuple((m._arena.data_ptr(), int(m.use_tc), 0 if m._split is None else m._split.data_ptr()) for m in mods)
         if sig != self._plan_sig:
             self._plans.clear()
             self._plan_sig = sig
-        for m in mods:
-            m._split_for(tb.T, True)
         plan = self._plan(tb)
-        if loader is not None:
-            loader(plan)
-        else:
-            plan.load(batches, noises, float(a.policy_noise))
+        injected = loader(plan) if loader is not None else plan.load(batches, noises)
         actor_step = it % a.policy_freq == 0
         if self.use_graphs:
-            plan.replay(actor_step)
+            plan.replay(actor_step, not injected)
         else:
-            self._update_impl(plan, actor_step)
+            self._update_impl(plan, actor_step, not injected)
+        if plan.keep_split:       # the step's fused Adam / Polyak kernels rewrote hi/lo from the new parameters
+            self.critic.mark_split_fresh()
+            if actor_step:
+                for m in (self.actor, self.critic_target, self.actor_target):
+                    m.mark_split_fresh()
+        else:
+            for m in (self.critic,) + ((self.actor, self.critic_target, self.actor_target) if actor_step else ()):
+                m.invalidate_split()
         scal = plan.scal.clone()
         loss_dict = {"loss/critic_loss": scal[0]}
-        loss_dict.update(self._reward_stats([b["reward"] for b in batches] if batches is not None else [plan.rew], plan.rew))
+        loss_dict.update(self._reward_stats([b["reward"] for b in batches] if batches is not None else [plan.rew], plan))
         if actor_step:
             loss_dict["loss/actor_loss"] = scal[1]
         self.tot_update_count += 1
         self._last_target = plan.target
         return loss_dict
 
-    def _update_impl(self, p: "_UpdatePlan", actor_step: bool):
+    def _update_impl(self, p: "_UpdatePlan", actor_step: bool, rng: bool = False):
         """Enqueue one update on the current stream (+ p.s1, p.s2 and the library's side streams).  Capture-safe:
         no allocation, no host synchronisation."""
         a = self.args
@@ -391,8 +443,13 @@ class Agent(nn.Module):
         with torch.cuda.stream(p.s1):
             p.s1.wait_event(p.ev_start)
             self.actor_target.forward_raw(tb, p.nobs, None, keep=False, trusted_split=True, out=p.a_t, stash=p.stash_at)
-            check(lib.sgrl_td3_smooth_action(ptr(p.a_t), ptr(p.noise), ptr(p.next_action), float(a.noise_clip), float(a.max_action), T * 3,
-                                             stream()))
+            if rng:       # eps ~ N(0, policy_noise^2) drawn in the kernel; p.noise receives it (tests, logging)
+                check(lib.sgrl_bump_step(ptr(p.draw), stream()))
+                check(lib.sgrl_td3_smooth_action_rng(ptr(p.a_t), ptr(p.next_action), ptr(p.noise), float(a.policy_noise), float(a.noise_clip),
+                                                     float(a.max_action), T * 3, p.seed, ptr(p.draw), stream()))
+            else:
+                check(lib.sgrl_td3_smooth_action(ptr(p.a_t), ptr(p.noise), ptr(p.next_action), float(a.noise_clip), float(a.max_action), T * 3,
+                                                 stream()))
             self.critic_target.forward_raw(tb, p.nobs, p.next_action, keep=False, nb=2, trusted_split=True, out=p.tq, stash=p.stash_ct)
             check(lib.sgrl_stream_fence(stream()))       # eager runs only (no-op under capture): see csrc/net.cuh stream_fence
             p.ev_a.record(p.s1)
@@ -407,11 +464,12 @@ class Agent(nn.Module):
         self.critic.forward_raw(tb, p.obs, p.act, keep=True, nb=2, trusted_split=True, out=p.q, stash=p.stash_c)
         main.wait_event(p.ev_a)
         check(lib.sgrl_td3_critic_loss(ptr(p.q[0]), ptr(p.q[1]), ptr(p.tq[0]), ptr(p.tq[1]), ptr(p.rew), ptr(p.done), ptr(tb.tok_graph),
-                                       ptr(tb.tok_weight), ptr(p.target), ptr(p.dq[0]), ptr(p.dq[1]), ptr(p.scal), float(a.discount), float(self.reward_scale), T, st))
+                                       ptr(tb.tok_weight), ptr(p.target), ptr(p.dq[0]), ptr(p.dq[1]), ptr(p.scal), float(a.discount), float(self.reward_scale), T,
+                                       ptr(p.rstats), tb.G, st))
         self.critic_optimizer.zero_grad()
         self.critic.backward_raw(tb, p.stash_c, p.dq, 2, self.critic.grad_arena(), False, trusted_split=True, ws=p.ws)
         self._allreduce(self.critic.grad_arena(), world)
-        self.critic_optimizer.step(max_norm=float(a.grad_clipping_value), world_size=world)
+        self.critic_optimizer.step(max_norm=float(a.grad_clipping_value), world_size=world, keep_split=p.keep_split)
         # ---- delayed actor step + Polyak                                                                    agent.py:165-180
         if actor_step:
             main.wait_event(p.ev_c)
@@ -421,26 +479,30 @@ class Agent(nn.Module):
             self.actor_optimizer.zero_grad()
             self.actor.backward_raw(tb, p.stash_a, p.dact, 1, self.actor.grad_arena(), False, trusted_split=True, ws=p.ws)
             self._allreduce(self.actor.grad_arena(), world)
-            self.actor_optimizer.step(max_norm=float(a.grad_clipping_value), world_size=world)
-            self.try_update_target_network()
+            self.actor_optimizer.step(max_norm=float(a.grad_clipping_value), world_size=world, keep_split=p.keep_split)
+            self.try_update_target_network(keep_split=p.keep_split)
 
     train_step = update   # BASELINE.json calls the TD3 step "train()"; the reference name is update (agent.py:117)
 
-    def _reward_stats(self, rewards_in, rew_dev):
-        """agent.py:158-162 returns Python floats (two device syncs in the reference).  When the batch
-        arrived from host memory the statistics are computed there and nothing synchronises."""
+    def _reward_stats(self, rewards_in, plan):
+        """agent.py:158-162 returns Python floats (two device syncs in the reference).  When the batch arrived from host
+        memory the statistics are computed there and nothing synchronises; otherwise they come from the sum / sum of
+        squares the critic-loss kernel accumulated in fp64 (one 16-byte read; `lazy_stats`: left on the device)."""
         s = self.reward_scale
         if all(isinstance(r, np.ndarray) or (torch.is_tensor(r) and not r.is_cuda) for r in rewards_in):
             r = torch.cat([torch.as_tensor(x, dtype=torch.float32).reshape(-1) for x in rewards_in]) * s
             return {"misc/train_reward_mean": r.mean().item(), "misc/train_reward_var": r.var().item() if r.numel() > 1 else float("nan")}
-        r = rew_dev * s
+        n = plan.tb.G
+        st = plan.rstats.clone() if self.lazy_stats else plan.rstats.cpu()
+        mean = st[0] / n
+        var = (st[1] - st[0] * st[0] / n) / (n - 1) if n > 1 else st[0] * float("nan")
         if self.lazy_stats:
-            return {"misc/train_reward_mean": r.mean(), "misc/train_reward_var": r.var()}
-        return {"misc/train_reward_mean": r.mean().item(), "misc/train_reward_var": r.var().item()}
+            return {"misc/train_reward_mean": mean, "misc/train_reward_var": var}
+        return {"misc/train_reward_mean": float(mean), "misc/train_reward_var": float(var)}
 
-    def try_update_target_network(self):
-        soft_update_network(self.critic, self.critic_target, self.target_smoothing_tau)
-        soft_update_network(self.actor, self.actor_target, self.target_smoothing_tau)
+    def try_update_target_network(self, keep_split: Optional[bool] = None):
+        soft_update_network(self.critic, self.critic_target, self.target_smoothing_tau, keep_split)
+        soft_update_network(self.actor, self.actor_target, self.target_smoothing_tau, keep_split)
 
     # ------------------------------------------------------------------ acting
     def _rollout_plan(self, tb) -> "_RolloutPlan":
@@ -450,8 +512,8 @@ class Agent(nn.Module):
             self._rollout_sig = sig
         plan = self._rollout_plans.get(id(tb))
         if plan is None or plan.tb is not tb:
-            if len(self._rollout_plans) >= 64:
-                self._rollout_plans.clear()
+            while len(self._rollout_plans) >= 64:
+                self._rollout_plans.pop(next(iter(self._rollout_plans)))
             plan = _RolloutPlan(self, tb)
             self._rollout_plans[id(tb)] = plan
         return plan
@@ -487,8 +549,8 @@ class Agent(nn.Module):
         key = tuple((id(g.get("relation")), tuple(g["parents"])) for g in graphs)
         tb = self._rollout_tables.get(key)
         if tb is None:
-            if len(self._rollout_tables) > 16:
-                self._rollout_tables.clear()
+            while len(self._rollout_tables) >= 64:
+                self._rollout_tables.pop(next(iter(self._rollout_tables)))
             tb = make_packed_tables([(g, 1) for g in graphs], self.actor.full_arena.device)
             self._rollout_tables[key] = tb
         out = self._rollout_plan(tb).run(obs_list)
@@ -511,6 +573,10 @@ class Agent(nn.Module):
         self.actor_target = self.actor_target.train()
         self.critic = self.critic.train()
         self.critic_target = self.critic_target.train()
+
+
+def _as_tensor(x):
+    return x if torch.is_tensor(x) else torch.as_tensor(np.asarray(x), dtype=torch.float32)
 
 
 def _to_dev(x, dev):

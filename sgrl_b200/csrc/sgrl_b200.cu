@@ -243,12 +243,21 @@ int sgrl_td3_smooth_action(const float* pi_target, const float* noise, float* ne
   return 0;
 }
 
+int sgrl_td3_smooth_action_rng(const float* pi_target, float* next_action, float* noise_out, float policy_noise, float noise_clip,
+                               float max_action, int64_t n, uint64_t seed, const int32_t* draw, sgrl_stream_t stream) {
+  SGRL_CHECK(pi_target && next_action && draw, "null pointer");
+  launch_k(td3_smooth_action_rng_kernel, grid_for_flat(n), 256, 0, ST(stream), pi_target, next_action, noise_out, policy_noise, noise_clip,
+           max_action, (long long)n, (unsigned long long)seed, draw);
+  SGRL_LAUNCH_OK();
+  return 0;
+}
+
 int sgrl_td3_critic_loss(const float* q1, const float* q2, const float* tq1, const float* tq2, const float* reward, const float* done,
                          const int32_t* tok_graph, const float* tok_weight, float* target, float* dq1, float* dq2, float* loss, float discount,
-                         float reward_scale, int T, sgrl_stream_t stream) {
+                         float reward_scale, int T, double* reward_stats, int G, sgrl_stream_t stream) {
   SGRL_CHECK(q1 && q2 && tq1 && tq2 && reward && done && tok_graph && target && dq1 && dq2 && loss, "null pointer");
   int gx = ceil_div(T, 256); if (gx > NUM_SMS) gx = NUM_SMS;
-  launch_k(td3_critic_loss_kernel, gx, 256, 0, ST(stream), q1, q2, tq1, tq2, reward, done, tok_graph, tok_weight, target, dq1, dq2, loss, discount, reward_scale, T);
+  launch_k(td3_critic_loss_kernel, gx, 256, 0, ST(stream), q1, q2, tq1, tq2, reward, done, tok_graph, tok_weight, target, dq1, dq2, loss, discount, reward_scale, T, reward_stats, G);
   SGRL_LAUNCH_OK();
   return 0;
 }
@@ -277,13 +286,13 @@ int sgrl_split_tf32(const float* w, float* hi, float* lo, int64_t n, sgrl_stream
   return 0;
 }
 
-int sgrl_adam_clip(float* p, const float* g, float* m, float* v, int64_t n, const float* sumsq, const int32_t* step, float lr,
-                   float beta1, float beta2, float eps, float max_norm, float grad_scale, float* p_hi, float* p_lo,
+int sgrl_adam_clip(float* p, const float* g, float* m, float* v, int64_t n, const float* sumsq, const int32_t* step, double lr,
+                   double beta1, double beta2, double eps, float max_norm, float grad_scale, float* p_hi, float* p_lo,
                    sgrl_stream_t stream) {
   SGRL_CHECK(p && g && m && v && sumsq && step, "null pointer");
   SGRL_CHECK((p_hi == nullptr) == (p_lo == nullptr) && (!p_hi || (aligned16(p_hi) && aligned16(p_lo))), "p_hi/p_lo go together, 16-byte aligned");
   SGRL_CHECK((n & 3) == 0 && aligned16(p) && aligned16(g) && aligned16(m) && aligned16(v), "arenas must be 16-byte aligned, n % 4 == 0");
-  AdamCfg c{lr, beta1, beta2, eps, max_norm, grad_scale};
+  AdamCfg c{lr, beta1, beta2, (float)beta1, (float)beta2, (float)(1.0 - beta1), (float)(1.0 - beta2), (float)eps, max_norm, grad_scale};
   launch_k(adam_clip_kernel, grid_for_flat(n), 256, 0, ST(stream), p, g, m, v, n, sumsq, step, c, p_hi, p_lo);
   SGRL_LAUNCH_OK();
   return 0;

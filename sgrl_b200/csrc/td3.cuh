@@ -14,6 +14,48 @@ __global__ void td3_smooth_action_kernel(const float* __restrict__ a, const floa
   }
 }
 
+// Philox4x32-10 (Salmon et al., SC'11; the counter-based generator behind torch.cuda's and cuRAND's default streams),
+// checked against the Random123 known-answer vectors in tests/test_td3_glue.py through the numpy restatement.
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const unsigned hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const unsigned hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += 0x9E3779B9u; k.y += 0xBB67AE85u;
+  }
+  return c;
+}
+// Same smoothing with the noise drawn in the kernel: eps ~ N(0, policy_noise^2) (agent.py:128 torch.randn_like * policy_noise),
+// four normals per Philox call (counter = {element / 4, 0, draw, 0}, key = seed; Box-Muller).  `draw` is a device counter the
+// caller bumps once per update (sgrl_bump_step), so a replayed CUDA graph draws fresh noise every replay.
+__global__ void td3_smooth_action_rng_kernel(const float* __restrict__ a, float* __restrict__ out, float* __restrict__ noise_out,
+                                             float policy_noise, float noise_clip, float max_action, long long n,
+                                             unsigned long long seed, const int* __restrict__ draw) {
+  SGRL_PDL_ENTER();
+  const unsigned d = (unsigned)*draw;
+  const uint2 key = make_uint2((unsigned)seed, (unsigned)(seed >> 32));
+  const long long n4 = (n + 3) >> 2;
+  for (long long q = blockIdx.x * 256LL + threadIdx.x; q < n4; q += gridDim.x * 256LL) {
+    const uint4 r = philox4x32_10(make_uint4((unsigned)q, (unsigned)(q >> 32), d, 0u), key);
+    const float u0 = ((float)r.x + 0.5f) * 2.3283064365386963e-10f, u1 = ((float)r.y + 0.5f) * 2.3283064365386963e-10f;
+    const float u2 = ((float)r.z + 0.5f) * 2.3283064365386963e-10f, u3 = ((float)r.w + 0.5f) * 2.3283064365386963e-10f;
+    const float r0 = sqrtf(-2.f * logf(fminf(u0, 0.99999994f))), r1 = sqrtf(-2.f * logf(fminf(u2, 0.99999994f)));
+    float s0, c0, s1, c1;
+    sincospif(2.f * u1, &s0, &c0);
+    sincospif(2.f * u3, &s1, &c1);
+    const float z[4] = {r0 * c0, r0 * s0, r1 * c1, r1 * s1};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const long long i = q * 4 + k;
+      if (i >= n) break;
+      const float e = z[k] * policy_noise;
+      if (noise_out) noise_out[i] = e;
+      out[i] = fminf(fmaxf(a[i] + fminf(fmaxf(e, -noise_clip), noise_clip), -max_action), max_action);
+    }
+  }
+}
+
 // target[t] = r[g(t)] * reward_scale + (1 - done[g(t)]) * discount * min(q1t[t], q2t[t])   agent.py:136-139
 // dq1 = 2 (q1 - target)/T, dq2 likewise; loss += sum((q1-y)^2 + (q2-y)^2)/T               agent.py:146-148
 __global__ void __launch_bounds__(256) td3_critic_loss_kernel(
@@ -21,9 +63,17 @@ __global__ void __launch_bounds__(256) td3_critic_loss_kernel(
     const float* __restrict__ reward, const float* __restrict__ done, const int* __restrict__ tok_graph,
     const float* __restrict__ tok_w,
     float* __restrict__ target, float* __restrict__ dq1, float* __restrict__ dq2, float* __restrict__ loss,
-    float discount, float reward_scale, int T) {
+    float discount, float reward_scale, int T, double* __restrict__ rstats, int G) {
   SGRL_PDL_ENTER();
   __shared__ float red[8];
+  if (rstats && blockIdx.x == 0 && threadIdx.x < 32) {
+    // sum and sum of squares of the scaled rewards (agent.py:158-161 logs their mean / variance): fp64, one warp
+    double s1 = 0.0, s2 = 0.0;
+    for (int g = threadIdx.x; g < G; g += 32) { const double x = (double)(reward[g] * reward_scale); s1 += x; s2 += x * x; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
+    if (threadIdx.x == 0) { rstats[0] = s1; rstats[1] = s2; }
+  }
   float acc = 0.f;
   const float invT = 1.f / (float)T;
   for (int t = blockIdx.x * 256 + threadIdx.x; t < T; t += gridDim.x * 256) {
@@ -92,7 +142,9 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g,
   }
 }
 
-struct AdamCfg { float lr, beta1, beta2, eps, max_norm; float grad_scale; };
+// lr / betas arrive as doubles, like the Python floats torch.optim.Adam computes its scalars from: 1 - beta2 is 0.001
+// rounded once to fp32 (torch), not 1.f - 0.999f = 0.00099998713 (1.3e-5 off: visible in exp_avg_sq, tests/test_k6_gpu.py)
+struct AdamCfg { double lr, beta1d, beta2d; float beta1, beta2, omb1, omb2, eps, max_norm; float grad_scale; };
 
 // One pass over the live arena: clip coefficient from the global norm, Adam moment update,
 // parameter step.  `step` lives on the device so the pass can be replayed from a CUDA graph.
@@ -129,8 +181,8 @@ __global__ void __launch_bounds__(256) adam_clip_kernel(float* __restrict__ p, c
     if (c.max_norm > 0.f) { coef = c.max_norm / (nrm + 1e-6f); coef = coef > 1.f ? 1.f : coef; }
     const double t = (double)(*step);
     sh[0] = coef * c.grad_scale;
-    sh[1] = (float)((double)c.lr / (1.0 - pow((double)c.beta1, t)));
-    sh[2] = (float)sqrt(1.0 - pow((double)c.beta2, t));
+    sh[1] = (float)(c.lr / (1.0 - pow(c.beta1d, t)));
+    sh[2] = (float)sqrt(1.0 - pow(c.beta2d, t));
   }
   __syncthreads();
   const float gs = sh[0], step_size = sh[1], bc2s = sh[2];
@@ -143,8 +195,8 @@ __global__ void __launch_bounds__(256) adam_clip_kernel(float* __restrict__ p, c
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const float gk = gg[k] * gs;
-      mm[k] = mm[k] + (gk - mm[k]) * (1.f - c.beta1);
-      vq[k] = vq[k] * c.beta2 + (1.f - c.beta2) * gk * gk;
+      mm[k] = mm[k] + (gk - mm[k]) * c.omb1;
+      vq[k] = vq[k] * c.beta2 + c.omb2 * gk * gk;
       pp[k] -= step_size * (mm[k] / (sqrtf(vq[k]) / bc2s + c.eps));
     }
     stg4(p + i * 4, pv); stg4(m + i * 4, mv); stg4(v + i * 4, vv);

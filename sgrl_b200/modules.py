@@ -13,6 +13,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import operator
 from typing import Dict, List, Optional, Tuple
 
 import torch
@@ -107,6 +108,9 @@ def make_packed_tables(parts, device) -> GraphTables:
                        tok_weight=torch.cat(w).to(device).contiguous() if m > 1 else None, parts=spans)
 
 
+_VERSION_OF = operator.attrgetter("_version")
+
+
 class SetNetModule(nn.Module):
     """nb reference ``TransformerModel``s (SEActor.py:170-287) in one flat arena."""
 
@@ -123,6 +127,8 @@ class SetNetModule(nn.Module):
         self.use_tc = USE_TC_DEFAULT
         self._tables_cache: Dict = {}
         self._build(device or _device_default())
+        # whatever a load wrote (also through a parent module's load_state_dict), the split is re-derived afterwards
+        self.register_load_state_dict_post_hook(lambda module, incompatible: module.invalidate_split())
 
     # ------------------------------------------------------------------ arena
     def _abs_offset(self, z: int, off: int, live: bool) -> int:
@@ -150,6 +156,8 @@ class SetNetModule(nn.Module):
                 node.register_parameter(parts[-1], p)
                 self._slots.append((p, a, n))
         self._arena = arena
+        self._plist = [p for p, _, _ in self._slots]
+        self._shared_counter = True                    # the parameters are views created from the arena: one version counter
         self._garena: Optional[torch.Tensor] = None
         self._split: Optional[torch.Tensor] = None     # (2, nb*live): tf32 hi / lo parts of the live arena
         self._split_fresh = False                      # True only while the agent's fused kernels keep it in sync
@@ -210,6 +218,7 @@ class SetNetModule(nn.Module):
                 p.data = arena[a:a + n].view(p.shape)
                 p.grad = None
         self._arena = arena
+        self._shared_counter = False                   # p.data = ... keeps each parameter's own counter
         self._garena = None
         self._split, self._split_fresh = None, False
         self._anchor = torch.zeros((), device=dev, requires_grad=True)
@@ -244,10 +253,26 @@ class SetNetModule(nn.Module):
         check(lib.sgrl_split_tf32(ptr(self.live_arena), ptr(sp[0]), ptr(sp[1]), sp.shape[1], stream()), "sgrl_split_tf32")
         self.mark_split_fresh()
 
+    def _write_stamp(self) -> int:
+        """Sum of the version counters of the arena and of every parameter.  In-place torch writes (p.copy_, optimizers,
+        load_state_dict) bump the counter of the tensor they go through: right after construction the parameters share
+        the arena's counter, after a re-flatten (.to() / .cuda()) each parameter has its own, so all of them are summed.
+        Writes through ``p.data`` / raw pointers bump nothing: callers that do that must call invalidate_split()."""
+        if self._shared_counter:
+            return self._arena._version
+        return self._arena._version + sum(map(_VERSION_OF, self._plist))
+
     def mark_split_fresh(self):
-        """Called after a kernel (split / fused Adam / Polyak) rewrote the split from the current arena contents.
-        torch-side in-place writes to the parameters bump the arena's version counter and invalidate the mark."""
-        self._split_fresh, self._split_version = True, self._arena._version
+        """Called after a kernel (split / fused Adam / Polyak) rewrote the split from the current arena contents."""
+        self._split_fresh, self._split_version = True, self._write_stamp()
+
+    def invalidate_split(self):
+        """Force the next tcgen05 pass to re-derive the tf32 hi/lo split from the parameters.  Needed only after writes
+        the version counters cannot see (``p.data.copy_(...)``, custom kernels writing the arena)."""
+        self._split_fresh = False
+
+    def split_is_fresh(self) -> bool:
+        return self._split is not None and self._split_fresh and self._split_version == self._write_stamp()
 
     def _split_for(self, T: int, trusted: bool):
         """(hi, lo) to hand to the kernels, or (None, None).  Only a caller that owns every write to the arena
@@ -255,7 +280,7 @@ class SetNetModule(nn.Module):
         split recomputed from the current parameter values, because nn.Parameters can be modified behind our back."""
         if not self.use_tc or T < self.SPLIT_MIN_TOKENS or self._arena.device.type != "cuda":
             return None, None
-        if not (trusted and self._split is not None and self._split_fresh and self._split_version == self._arena._version):
+        if not (trusted and self.split_is_fresh()):
             self.refresh_split()
         return self._split[0], self._split[1]
 

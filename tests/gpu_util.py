@@ -59,3 +59,35 @@ def compare_stash(mod, stash, tb, nb, z, trace, n_layers=3, tol=2e-5, skip=()):
         assert ref.shape == got.shape, (key, ref.shape, got.shape)
         out.append((key, parity.rel_err(got, ref)))
     return out
+
+
+def relu_masks(mod, stash, tb, nb, z, n_layers=3):
+    """Activation pattern of net instance z in a keep=True stash, keyed like the oracle's relu sites (set_oracle._relu)."""
+    from sgrl_b200._lib import ACTOR
+    mk = {}
+    for l in range(n_layers):
+        mk[f"{l}.A1"] = stash_view(mod, stash, tb, nb, z, "A1", l) > 0
+        mk[f"{l}.A2"] = stash_view(mod, stash, tb, nb, z, "A2", l) > 0
+        t31 = stash_view(mod, stash, tb, nb, z, "T31", l)
+        mk[f"{l}.T3"], mk[f"{l}.T1"] = t31[:, :256] > 0, t31[:, 256:] > 0
+    mk["AH"] = stash_view(mod, stash, tb, nb, z, "AH") > 0
+    mk["BH"] = stash_view(mod, stash, tb, nb, z, "BH") > 0
+    if mod._kind == ACTOR:
+        mk["M1"] = stash_view(mod, stash, tb, nb, z, "M1") > 0
+    return mk
+
+
+def relu_flips(mod, stash, tb, nb, z, trace, prefix=""):
+    """relu units that the CUDA forward and the oracle trace put on different sides of zero:
+    [(site, |activation| / largest activation of the unit's row)] — ~1e-8 for a unit sitting on its kink."""
+    out = []
+    for key, ref in trace.items():
+        l, nm = (int(key.split(".")[0]), key.split(".")[1]) if "." in key else (-1, key)
+        if nm not in ("A1", "A2", "T31", "AH", "BH", "M1"):
+            continue
+        got = stash_view(mod, stash, tb, nb, z, nm, l)
+        ref = ref.detach().reshape(tb.T, -1).to(got.device)
+        for t, c in torch.nonzero((got > 0) != (ref > 0)).tolist():
+            mag = max(abs(got[t, c].item()), abs(ref[t, c].item()))
+            out.append((prefix + key, mag / max(ref[t].abs().max().item(), 1e-300)))
+    return out

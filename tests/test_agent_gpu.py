@@ -180,4 +180,50 @@ def test_replayed_graph_gradients_equal_eager_gradients():
         for ma, me in ((ag.critic, eg.critic), (ag.actor, eg.actor), (ag.critic_target, eg.critic_target)):
             assert parity.rel_err(ma.full_arena, me.full_arena) < 1e-5, it     # one Adam sign flip of a ~0 gradient entry moves this by ~2e-6
     plan = next(iter(ag._plans.values()))
-    assert set(plan.graphs) == {True, False} and not eg._plans[next(iter(eg._plans))].graphs
+    assert set(plan.graphs) == {(True, False), (False, False)} and not eg._plans[next(iter(eg._plans))].graphs
+
+
+def test_weights_written_from_python_reach_the_tensor_core_path():
+    """ADVICE r01 (modules.py tf32 split): the tcgen05 GEMMs stream a pre-split copy (hi/lo) of the weights that the fused
+    Adam / Polyak kernels keep in sync.  Every torch-side write must stale it: after a move (.cpu().cuda() re-flattens the
+    arena, so the parameters stop sharing the arena's version counter), load_state_dict, an in-place p.copy_ and — with the
+    documented invalidate_split() — a write through p.data.  Agent A goes through those edits between updates; agent B is
+    built fresh with the same weights and optimizer state each time; their next update must agree."""
+    par = M.ALL["3d_humanoid_9_full"]
+    g = G.build_graph(par, device="cuda")
+    B = 100
+    a, _, _ = make_agent()
+    a = a.cpu().cuda()                                   # forces _reflatten: per-parameter version counters from here on
+    a.change_morphology(g)
+    other = {k: v + 0.01 * torch.randn(v.shape, generator=torch.Generator().manual_seed(len(k))).to(v.device)
+             for k, v in agent_state(a).items()}
+
+    def edits():
+        yield "load_state_dict", lambda: a.load_state_dict(other)
+        def inplace():
+            with torch.no_grad():
+                for p in a.critic.parameters():
+                    p.mul_(1.001)
+        yield "in-place p.mul_", inplace
+        def through_data():
+            for p in a.actor.parameters():
+                p.data.copy_(p.data * 0.999)
+            a.actor.invalidate_split()
+        yield "p.data + invalidate_split", through_data
+
+    it = 0
+    for what, edit in edits():
+        b = {k: v.cuda() for k, v in synth.make_batch(B, len(par), seed=70 + it).items()}
+        noise = torch.randn(B, 27, generator=torch.Generator().manual_seed(7 + it)).cuda() * 0.2
+        a.update(b, it, noise=noise); a.update(b, it + 1, noise=noise)        # split fresh and trusted, graphs captured or replayed
+        edit()
+        fresh, _, _ = make_agent()
+        fresh.change_morphology(g)
+        fresh.load_state_dict(a.state_dict())
+        fresh.critic_optimizer.load_state_dict(a.critic_optimizer.state_dict())
+        fresh.actor_optimizer.load_state_dict(a.actor_optimizer.state_dict())
+        la, lf = a.update(b, it + 2, noise=noise), fresh.update(b, it + 2, noise=noise)
+        assert abs(la["loss/critic_loss"].item() - lf["loss/critic_loss"].item()) <= 1e-6 * abs(lf["loss/critic_loss"].item()), what
+        assert parity.rel_err(a.critic.grad_arena(), fresh.critic.grad_arena()) < 1e-5, what
+        assert parity.rel_err(a.actor.grad_arena(), fresh.actor.grad_arena()) < 1e-4, what
+        it += 2
