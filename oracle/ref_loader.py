@@ -24,7 +24,9 @@ _SEARCH = (
 
 
 def find_reference():
-    """Path of the reference ``src`` directory, or None when it is not on this machine."""
+    """Path of the reference ``src`` directory, or None when it is not on this machine (SGRL_REF_DISABLE=1: pretend so)."""
+    if os.environ.get("SGRL_REF_DISABLE"):
+        return None
     for p in _SEARCH:
         if p and os.path.isfile(os.path.join(p, "SEActor.py")):
             return p
