@@ -45,6 +45,7 @@ def parse():
                     "update of EVERY morphology of the set at --batch samples each (sharded round-robin over the ranks)")
     ap.add_argument("--packed", action="store_true", help="with --set: all morphologies of the rank in ONE packed update (Agent.update_packed) "
                     "instead of the reference's one-after-the-other schedule (src/trainer.py:245-250)")
+    ap.add_argument("--check-replicas", action="store_true", help="after the run, compare the parameter arenas of all ranks bit for bit")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-rollout", action="store_true")
     return ap.parse_args()
@@ -441,6 +442,8 @@ def run_ours(a):
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         cb = cpu_reference_rate(a.morph, B, budget_s=15.0)
         line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "port_over_reference_time") if k in cb}
+    if a.check_replicas:
+        line["replicas"] = check_replicas(agent, world, dev)
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -461,8 +464,14 @@ def run_set(a, agent, dev, world, rank, local):
     names = sorted(M.SETS[a.set])
     mine = names[rank::world]
     B = a.batch
-    K = a.steps + a.steps % 2
-    W = max(a.warmup, 4); W += W % 2
+    K, W = a.steps, a.warmup
+    # N > 1: the morphologies are dealt over the ranks and every rank runs its share as ONE packed update, so that all ranks
+    # issue the same number of gradient all-reduces whatever the split (23 cwhh morphologies over 8 ranks = 3,3,3,3,3,3,3,2);
+    # the per-token loss weight uses morph_count = n / world, which makes the all-reduced sum / world the mean over all n
+    packed = a.packed or world > 1
+    mcount = len(names) / world if world > 1 else None
+    if not mine:
+        raise SystemExit(f"--set {a.set}: {len(names)} morphologies cannot be dealt over {world} ranks")
     graphs = {n: G.build_graph(M.SETS[a.set][n], device=dev) for n in mine}
     host = {n: {k: v.pin_memory() for k, v in synth.make_batch(B, len(M.SETS[a.set][n]), seed=300 + i).items()} for i, n in enumerate(mine)}
     devb = {n: {k: v.to(dev) for k, v in host[n].items()} for n in mine}
@@ -474,8 +483,8 @@ def run_set(a, agent, dev, world, rank, local):
             dist.barrier(); torch.cuda.synchronize()
 
     def step(i, batches):
-        if a.packed:
-            return agent.update_packed([(graphs[n], batches[n]) for n in mine], i)
+        if packed:
+            return agent.update_packed([(graphs[n], batches[n]) for n in mine], i, morph_count=mcount)
         ld = None
         for n in mine:
             agent.change_morphology(graphs[n])
@@ -483,23 +492,26 @@ def run_set(a, agent, dev, world, rank, local):
         return ld
 
     agent.lazy_stats = True
-    for i in range(W):
-        step(i, devb)
+    it = 0
+    for _ in range(4 + W):       # 4 set-up steps (eager + graph capture per plan and kind of step), then W warm-up steps
+        step(it, devb); it += 1
     barrier()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     for i in range(K):
         flush.zero_()
-        ev[i][0].record(); step(i, devb); ev[i][1].record()
+        ev[i][0].record(); step(it, devb); it += 1; ev[i][1].record()
     barrier()
     t = torch.tensor([sum(s.elapsed_time(e) for s, e in ev)], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms = t.item()
     agent.lazy_stats = False
+    for _ in range(4):
+        step(it, host)["loss/critic_loss"].item(); it += 1
     barrier()
     t0 = time.perf_counter()
     for i in range(K):
-        step(i, host)["loss/critic_loss"].item()
+        step(it, host)["loss/critic_loss"].item(); it += 1
     barrier()
     t = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
     if world > 1:
@@ -510,15 +522,35 @@ def run_set(a, agent, dev, world, rank, local):
             "warmup": W, "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32 (3xTF32 tensor-core projections, fp32 accumulate)", "data": "synthetic",
             "config": {"workload": f"{a.set}: {len(names)} morphologies x B={B}, one TD3 update each per step, "
-                                   + ("packed into one update per rank (Agent.update_packed)" if a.packed else "one after the other (src/trainer.py:245-250)"),
+                                   + ("packed into one update per rank (Agent.update_packed)" if packed else "one after the other (src/trainer.py:245-250)"),
                        "morphologies_per_rank": len(mine), "limb_tokens_per_step": toks, "l2": "256 MiB buffer written between timed steps"},
             "e2e": {"value": nsamp * K / t.item(), "unit": "samples/s", "h2d_bytes_per_step": sum(v.numel() * 4 for n in mine for v in host[n].values()),
                     "d2h_bytes_per_step": 4, "how": "update(_packed) with pinned host batches + critic_loss.item(), wall clock, max over ranks"},
             "whole_step_tflops": FLOP_PER_TOKEN_UPDATE * toks / (total_ms / K * 1e-3) / 1e12}
+    if a.check_replicas:
+        line["replicas"] = check_replicas(agent, world, dev)
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
         barrier(); sys.stdout.flush(); os._exit(0)
+
+
+def check_replicas(agent, world, dev):
+    """Bitwise comparison of every rank's parameter arenas (live and target nets) after the run: data-parallel replicas
+    apply the identical all-reduced gradient, so they must stay identical bit for bit (SURVEY.md §4 tier 5)."""
+    import torch
+    import torch.distributed as dist
+    sums = []
+    for m in (agent.actor, agent.critic, agent.actor_target, agent.critic_target):
+        bits = m.full_arena.view(torch.int32).to(torch.int64)
+        sums += [bits.sum(), (bits * torch.arange(1, bits.numel() + 1, device=dev) % 1000003).sum()]
+    mine = torch.stack(sums)
+    if world == 1:
+        return {"identical": True, "ranks": 1}
+    allv = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(allv, mine)
+    same = all(bool((v == allv[0]).all()) for v in allv)
+    return {"identical": same, "ranks": world, "checksums_rank0": [int(x) for x in allv[0].tolist()]}
 
 
 if __name__ == "__main__":

@@ -301,6 +301,7 @@ class Agent(nn.Module):
         self.tot_update_count = 0
         self.target_smoothing_tau = args.agent.target_smoothing_tau
         self.reward_scale = args.agent.reward_scale
+        self.data_parallel = True    # False: no gradient all-reduce even inside an initialised process group (tests, replicas-only runs)
         self.lazy_stats = False      # True: reward statistics returned as 0-dim tensors (no host sync)
         self.use_graphs = os.environ.get("SGRL_GRAPHS", "1") != "0"   # replay Agent.update as a captured CUDA graph
         # one plan (static buffers + two or three captured graphs) per (morphology tables, batch size).  The reference's
@@ -318,6 +319,8 @@ class Agent(nn.Module):
     # ------------------------------------------------------------------ TD3 step
     def _world(self):
         import torch.distributed as dist
+        if not self.data_parallel:
+            return 1
         return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
 
     def _allreduce(self, g: torch.Tensor, world: int):
@@ -354,18 +357,20 @@ class Agent(nn.Module):
         tb = self.actor._tables(B)
         return self._run_update(tb, [data_batch], it, None if noise is None else [noise])
 
-    def update_packed(self, batches, it: int, noises=None):
+    def update_packed(self, batches, it: int, noises=None, morph_count: Optional[float] = None):
         """One TD3 update on a PACKED batch of several morphologies: batches = [(graph_dict, data_batch), ...].  The loss is
         the mean over morphologies of the reference's per-morphology loss, so the gradient equals the average of the
         gradients of the separate updates the reference performs one after the other (src/trainer.py:245-250) at the same
-        parameters; the limb-tokens of all morphologies go through every kernel together."""
+        parameters; the limb-tokens of all morphologies go through every kernel together.
+        morph_count: data-parallel ranks holding different numbers of morphologies pass (total morphologies / world) so the
+        all-reduced gradient is the mean over all morphologies (modules.make_packed_tables)."""
         from .modules import make_packed_tables
-        key = tuple((id(g.get("relation")), tuple(g["parents"]), int(b["obs"].shape[0])) for g, b in batches)
+        key = tuple((id(g.get("relation")), tuple(g["parents"]), int(b["obs"].shape[0])) for g, b in batches) + (morph_count,)
         tb = self._packed_tables.get(key)
         if tb is None:
             while len(self._packed_tables) >= self.max_plans:
                 self._packed_tables.pop(next(iter(self._packed_tables)))
-            tb = make_packed_tables([(g, int(b["obs"].shape[0])) for g, b in batches], self.actor.full_arena.device)
+            tb = make_packed_tables([(g, int(b["obs"].shape[0])) for g, b in batches], self.actor.full_arena.device, morph_count)
             self._packed_tables[key] = tb
         return self._run_update(tb, [b for _, b in batches], it, noises)
 

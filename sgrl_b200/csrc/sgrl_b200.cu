@@ -273,7 +273,24 @@ int sgrl_td3_actor_loss(const float* q1, const float* tok_weight, float* dq1, fl
 int sgrl_sumsq(const float* g, int64_t n, float* out, sgrl_stream_t stream) {
   SGRL_CHECK(g && out, "null pointer");
   SGRL_CHECK(aligned16(g), "gradient arena must be 16-byte aligned");
-  launch_k(sumsq_kernel, grid_for_flat(n), 256, 0, ST(stream), g, n, out);
+  // scratch for the per-block partial sums: one slot per destination scalar (hashed), so the optimizers of different modules
+  // never share one; allocated on first use (an eager call: Agent.update runs each plan eagerly before capturing it)
+  constexpr int SLOTS = 16;
+  static float* scratch[64] = {nullptr};      // per device
+  int dev = 0;
+  SGRL_CUDA(cudaGetDevice(&dev));
+  SGRL_CHECK(dev >= 0 && dev < 64, "device index");
+  if (!scratch[dev]) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    SGRL_CUDA(cudaStreamIsCapturing(ST(stream), &cs));
+    SGRL_CHECK(cs == cudaStreamCaptureStatusNone, "sgrl_sumsq: first call on a device must not be inside a stream capture");
+    SGRL_CUDA(cudaMalloc(&scratch[dev], sizeof(float) * SLOTS * SUMSQ_MAX_BLOCKS));
+  }
+  float* part = scratch[dev] + ((reinterpret_cast<uintptr_t>(out) >> 2) * 2654435761u % SLOTS) * SUMSQ_MAX_BLOCKS;
+  int nb = grid_for_flat(n); if (nb > SUMSQ_MAX_BLOCKS) nb = SUMSQ_MAX_BLOCKS;
+  launch_k(sumsq_partial_kernel, nb, 256, 0, ST(stream), g, (long long)n, part);
+  SGRL_LAUNCH_OK();
+  launch_k(sumsq_final_kernel, 1, 256, 0, ST(stream), (const float*)part, nb, out);
   SGRL_LAUNCH_OK();
   return 0;
 }

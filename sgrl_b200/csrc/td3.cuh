@@ -120,8 +120,12 @@ __global__ void __launch_bounds__(256) td3_actor_loss_kernel(const float* __rest
   }
 }
 
-// sum of squares of a flat gradient buffer -> *out (pre-zeroed)                            clip_grad_norm_, agent.py:152-155
-__global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, long long n, float* __restrict__ out) {
+// sum of squares of a flat gradient buffer                                                  clip_grad_norm_, agent.py:152-155
+// Deterministic (no atomics): every block leaves its partial sum in a scratch slot, a second one-block launch adds the
+// partials in index order.  The norm feeds the clip coefficient of every data-parallel replica: with an atomic reduction the
+// ranks disagreed in its last bit and the replicas drifted apart after ~40 steps (tools/dp_debug.py, bench.py --check-replicas).
+constexpr int SUMSQ_MAX_BLOCKS = 2048;
+__global__ void __launch_bounds__(256) sumsq_partial_kernel(const float* __restrict__ g, long long n, float* __restrict__ partial) {
   SGRL_PDL_ENTER();
   __shared__ float red[8];
   float acc = 0.f;
@@ -138,7 +142,23 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g,
     float s = red[threadIdx.x];
 #pragma unroll
     for (int o = 4; o > 0; o >>= 1) s += __shfl_xor_sync(0xffu, s, o);
-    if (threadIdx.x == 0) atomicAdd(out, s);
+    if (threadIdx.x == 0) partial[blockIdx.x] = s;
+  }
+}
+__global__ void __launch_bounds__(256) sumsq_final_kernel(const float* __restrict__ partial, int nb, float* __restrict__ out) {
+  SGRL_PDL_ENTER();
+  __shared__ double red[8];
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < nb; i += 256) acc += (double)partial[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += red[w];
+    *out += (float)s;
   }
 }
 

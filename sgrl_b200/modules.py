@@ -82,15 +82,18 @@ def make_tables(graph: Dict, batch: int, device) -> GraphTables:
     return GraphTables(cu, rank3, tok_graph, rel, None, batch * n, batch)
 
 
-def make_packed_tables(parts, device) -> GraphTables:
+def make_packed_tables(parts, device, morph_count: Optional[float] = None) -> GraphTables:
     """Tables for a PACKED batch of several morphologies: parts = [(graph_dict, batch_i), ...].  Tokens are ordered
     morphology by morphology, sample-major, limb-minor; `cu_limbs` holds the ragged graph boundaries, `rel_off` each graph's
     offset into the concatenated relation tables, `tok_weight` = 1 / (#morphologies * B_i * N_i): the loss of the packed
     batch is the mean over morphologies of the reference's per-morphology loss (the reference steps the morphologies one
-    after the other, src/trainer.py:245-250)."""
+    after the other, src/trainer.py:245-250).  morph_count (default: len(parts)) replaces
+    #morphologies in the weight: a data-parallel rank that holds n_r of n morphologies passes n / world, so that the
+    all-reduced sum / world is the mean over ALL n morphologies whatever the split (bench.py --set, N > 1)."""
     cu, rank3, tokg, rel, reloff, w, spans = [0], [], [], [], [], [], []
     t0 = g0 = ro = 0
     m = len(parts)
+    mw = float(morph_count) if morph_count else float(m)
     for graph, batch in parts:
         one = make_tables(graph, batch, "cpu")
         n = len(graph["parents"])
@@ -99,13 +102,13 @@ def make_packed_tables(parts, device) -> GraphTables:
         tokg.append(one.tok_graph + g0)
         rel.append(one.relation.reshape(-1))
         reloff.extend([ro] * batch)
-        w.append(torch.full((batch * n,), 1.0 / (m * batch * n), dtype=torch.float32))
+        w.append(torch.full((batch * n,), 1.0 / (mw * batch * n), dtype=torch.float32))
         spans.append((t0, t0 + batch * n, g0, g0 + batch, n))
         t0 += batch * n; g0 += batch; ro += n * n * 3
     i32 = lambda x: torch.as_tensor(x, dtype=torch.int32).to(device).contiguous()
     return GraphTables(i32(cu), torch.cat(rank3).to(device).contiguous(), torch.cat(tokg).to(torch.int32).to(device).contiguous(),
                        torch.cat(rel).to(device).contiguous(), i32(reloff), t0, g0,
-                       tok_weight=torch.cat(w).to(device).contiguous() if m > 1 else None, parts=spans)
+                       tok_weight=torch.cat(w).to(device).contiguous() if (m > 1 or mw != 1.0) else None, parts=spans)
 
 
 _VERSION_OF = operator.attrgetter("_version")
