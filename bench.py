@@ -48,6 +48,7 @@ def parse():
     ap.add_argument("--check-replicas", action="store_true", help="after the run, compare the parameter arenas of all ranks bit for bit")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-rollout", action="store_true")
+    ap.add_argument("--no-bf16", action="store_true", help="skip the separately reported BF16-input leg")
     return ap.parse_args()
 
 
@@ -437,6 +438,48 @@ def run_ours(a):
                           "us_per_env_batched": us_all / len(names),
                           "how": "numpy obs in, numpy actions out (pinned H2D + replayed CUDA graph + D2H + sync); batched = one packed "
                                  "forward over %d Humanoid++ envs of 6 morphologies (src/trainer.py:174-196 does them one by one)" % len(names)}
+
+    # ---- BF16-input mode, stated separately (north_star): the same update / rollout with use_tc = 2 — both operands of every
+    # tcgen05 projection rounded to bf16, ONE MMA pass, fp32 accumulate (tests/test_bf16_mode_gpu.py records its accuracy:
+    # 1e-3..1e-2 against the oracle, i.e. outside the parity bar).  Never the headline value.
+    if not a.no_bf16 and use_tc:
+        mods = (agent.actor, agent.actor_target, agent.critic, agent.critic_target)
+        for m in mods:
+            m.use_tc = 2
+        agent.lazy_stats = True
+        for _ in range(8):
+            agent.update(devb[it % nbat], it, noise=noise[it % nbat]); it += 1
+        barrier()
+        Kb = min(K, 40)
+        evb = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(Kb)]
+        for i in range(Kb):
+            flush.zero_()
+            evb[i][0].record()
+            agent.update(devb[it % nbat], it, noise=noise[it % nbat]); it += 1
+            evb[i][1].record()
+        barrier()
+        t = torch.tensor([sum(s.elapsed_time(e) for s, e in evb)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        bfl = {"dtype": "bf16 inputs / f32 accumulate, one tcgen05 pass (use_tc=2)", "value": world * B * Kb / (t.item() * 1e-3), "unit": "samples/s",
+               "ms_per_step": t.item() / Kb, "steps": Kb, "note": "separate line, not the headline: accuracy 1e-3..1e-2 vs the oracle (tests/test_bf16_mode_gpu.py)"}
+        if not a.no_rollout:
+            with torch.no_grad():
+                for _ in range(3):
+                    agent.actor(obs)
+                barrier()
+                evr = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(5)]
+                for i in range(5):
+                    flush.zero_()
+                    evr[i][0].record(); agent.actor(obs); evr[i][1].record()
+                barrier()
+                t = torch.tensor([sum(s.elapsed_time(e) for s, e in evr)], device=dev, dtype=torch.float64)
+                if world > 1:
+                    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                bfl["rollout_limb_tokens_per_s"] = world * a.rollout_envs * N * 5 / (t.item() * 1e-3)
+        line["bf16_input_mode"] = bfl
+        for m in mods:
+            m.use_tc = use_tc
 
     # ---- reference algorithm on this box's host cores (rank 0, N=1 only; bounded sample)
     if rank == 0 and world == 1 and not a.no_cpu_baseline:

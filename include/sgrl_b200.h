@@ -64,7 +64,8 @@ typedef struct {
   int32_t T;           /* limb-tokens in the packed batch */
   int32_t G;           /* graphs (samples) in the batch */
   int32_t keep;        /* 1: keep every layer's activations for backward */
-  int32_t use_tc;      /* 1: tcgen05 tensor-core projections (3xTF32), 0: fp32 SIMT */
+  int32_t use_tc;      /* 1: tcgen05 tensor-core projections (3xTF32, fp32 parity), 0: fp32 SIMT, 2: tcgen05 with BF16-rounded
+                        * inputs and one MMA pass (fp32 accumulate) — the separately reported reduced-precision mode */
   int32_t max_limbs;   /* largest graph of the batch (2..16), 0 = unknown: sizes the attention kernel's shared-memory staging */
   const float* params; /* live arena of the module (nb * live_floats) */
   float* grads;        /* gradient arena, same layout; may be NULL for forward / data-only backward */

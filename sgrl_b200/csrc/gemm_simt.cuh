@@ -37,6 +37,9 @@ struct GemmP {
   int sm2_ok;                               // tcgen05 path: the single-accumulator two-CTAs-per-SM variant may be used (inference passes only)
   long long* dbg;                           // optional (tools/gemm_trace.py): SM-clock timestamps of CTA 0's pipeline phases
   // ---- tcgen05 path only (gemm_tc.cuh) ----
+  int prec;                                 // 0: 3xTF32 error-compensated (fp32 parity); 1: BF16-INPUT mode — both operands rounded (RN-even) to bf16 in
+                                            //    the operand path, ONE tf32 MMA pass (bf16 values are exact in tf32), fp32 accumulate: numerically what
+                                            //    kind::f16 bf16 x bf16 -> f32 computes.  Never the default; reported separately (north_star).
   int sk_x;                                 // set by the launcher: the split-K index is folded into blockIdx.x (grouped launches)
   // A operand generated on the fly: row m of A is the packed upper triangle (GP_K = 544 floats, layout.h) of G_m = Z_m^T Z_m,
   // Z_m (3 x 32) read from gramZ (T, 96).  K must be GP_K, transA = 0, splitk = 1.  Replaces the Gram phase of the

@@ -108,7 +108,7 @@ struct NetCtx {
   WsLayout wl; float* ws; long long zsW;
   AttnGraphs gr; const int* rank3;
   float max_action;
-  int use_tc;                             // route eligible GEMMs to the tcgen05 kernel
+  int use_tc;                             // 0: fp32 SIMT; 1: eligible GEMMs on the tcgen05 kernel (3xTF32, fp32 parity); 2: tcgen05 in BF16-input mode
   cudaStream_t stream;
 
   const float* P(long long off) const { return params + off; }
@@ -123,8 +123,9 @@ struct NetCtx {
 inline int run_gemm(const NetCtx& c, const GemmP& g, cudaStream_t st = nullptr) {
   if (!st) st = c.stream;
   if (c.use_tc && gemm_tc_eligible(g)) {
-    if (c.keep) return gemm_tc(g, st);
-    GemmP gi = g; gi.sm2_ok = 1;
+    GemmP gi = g;
+    gi.sm2_ok = c.keep ? 0 : 1;
+    gi.prec = c.use_tc == 2 ? 1 : 0;      // use_tc 2: BF16-input mode (reported separately, never the default)
     return gemm_tc(gi, st);
   }
   SGRL_TRY(gemm_simt(g, st));
@@ -144,7 +145,11 @@ inline int run_group(const NetCtx& c, const GemmP* gs, int n, cudaStream_t st = 
   static const long long group_maxt = getenv("SGRL_GROUP_MAXT") ? atoll(getenv("SGRL_GROUP_MAXT")) : 32768;
   bool all_tc = c.use_tc && n > 1 && (long long)c.T * c.nb <= group_maxt;
   for (int i = 0; i < n && all_tc; ++i) all_tc = gemm_tc_eligible(gs[i]);
-  if (all_tc) return gemm_tc_group(gs, n, st);
+  if (all_tc) {
+    GemmP gp[TC_MAXG];
+    for (int i = 0; i < n; ++i) { gp[i] = gs[i]; gp[i].prec = c.use_tc == 2 ? 1 : 0; }
+    return gemm_tc_group(gp, n, st);
+  }
   for (int i = 0; i < n; ++i) SGRL_TRY(run_gemm(c, gs[i], st));
   return 0;
 }

@@ -168,6 +168,7 @@ int sgrl_gemm(const float* A, int lda, int trans_a, const float* B, int ldb, int
   g.splitk = splitk < 1 ? 1 : splitk;
   if (use_tc) {
     SGRL_CHECK(gemm_tc_eligible(g), "shape/epilogue not eligible for the tcgen05 path");
+    g.prec = use_tc == 2 ? 1 : 0;
     return gemm_tc(g, ST(stream));
   }
   return gemm_simt(g, ST(stream));
