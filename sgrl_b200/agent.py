@@ -130,8 +130,8 @@ class _UpdatePlan:
         self.stash_c = f(cr.stash_floats(T, True, 2))
         self.stash_a = f(ac.stash_floats(T, True, 1))
         self.ws = f(max(cr.ws_floats(T, 2), ac.ws_floats(T, 1)))
-        self.s1, self.s2 = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
-        self.ev_start, self.ev_a, self.ev_c = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
+        self.s1, self.s2, self.s3, self.s_cap = agent._streams(dev)
+        self.ev_start, self.ev_a, self.ev_b, self.ev_c = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
         # the fused Adam / Polyak passes of this plan also rewrite the tf32 split (decided once per plan: the captured graphs
         # bake the pointers in).  Plans too small for the tcgen05 path leave the split stale; _run_update then marks it so.
         self.keep_split = all(m.use_tc and T >= m.SPLIT_MIN_TOKENS for m in (agent.actor, agent.critic, agent.actor_target, agent.critic_target))
@@ -197,7 +197,7 @@ class _UpdatePlan:
                 torch.cuda.synchronize()
                 g = torch.cuda.CUDAGraph()
                 l0 = lib.sgrl_launch_count()
-                with torch.cuda.graph(g):
+                with torch.cuda.graph(g, stream=self.s_cap):
                     self.agent._update_impl(self, actor_step, rng)
                 self.graph_launches[key] = lib.sgrl_launch_count() - l0
             except Exception as ex:   # keep running eagerly (still the CUDA path); say so once
@@ -322,6 +322,22 @@ class Agent(nn.Module):
         if not self.data_parallel:
             return 1
         return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+    def _streams(self, dev):
+        """The step's forward streams, shared by every plan of the agent: s1 carries the critical chain (actor-target ->
+        twin critic-target, src/agent.py:127-139) and the capture stream the loss / backward / optimizer chain — both at
+        raised priority; s2 (actor forward of the delayed step) and s3 (critic forward) only have to be ready by the time
+        the critical chain arrives and run at plain priority, like the library's weight-gradient lanes (csrc/net.cuh Side).
+        SGRL_PRIO=1 turns the priorities on; the default is plain priority everywhere: measured on B200 the raised
+        priorities made the B=256 update 2 % slower (5.13 vs 5.03 ms, profiles/r02z_ab_knobs.txt) — the step is bound by
+        SM-time, not by the order in which waiting CTAs are placed."""
+        st = getattr(self, "_stream_set", None)
+        if st is None or st[0] != dev:
+            hi = -1 if os.environ.get("SGRL_PRIO", "0") == "1" else 0
+            st = (dev, torch.cuda.Stream(device=dev, priority=hi), torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev),
+                  torch.cuda.Stream(device=dev, priority=hi))
+            self._stream_set = st
+        return st[1:]
 
     def _allreduce(self, g: torch.Tensor, world: int):
         if world > 1:
@@ -465,8 +481,13 @@ class Agent(nn.Module):
                 self.actor.forward_raw(tb, p.obs, None, keep=True, trusted_split=True, out=p.pi, stash=p.stash_a)
                 check(lib.sgrl_stream_fence(stream()))
                 p.ev_c.record(p.s2)
-        # ---- chain B (main): critic step                                                                    agent.py:142-156
-        self.critic.forward_raw(tb, p.obs, p.act, keep=True, nb=2, trusted_split=True, out=p.q, stash=p.stash_c)
+        # ---- chain B (stream s3, then main): critic step                                                    agent.py:142-156
+        with torch.cuda.stream(p.s3):
+            p.s3.wait_event(p.ev_start)
+            self.critic.forward_raw(tb, p.obs, p.act, keep=True, nb=2, trusted_split=True, out=p.q, stash=p.stash_c)
+            check(lib.sgrl_stream_fence(stream()))
+            p.ev_b.record(p.s3)
+        main.wait_event(p.ev_b)
         main.wait_event(p.ev_a)
         check(lib.sgrl_td3_critic_loss(ptr(p.q[0]), ptr(p.q[1]), ptr(p.tq[0]), ptr(p.tq[1]), ptr(p.rew), ptr(p.done), ptr(tb.tok_graph),
                                        ptr(tb.tok_weight), ptr(p.target), ptr(p.dq[0]), ptr(p.dq[1]), ptr(p.scal), float(a.discount), float(self.reward_scale), T,

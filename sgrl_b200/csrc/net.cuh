@@ -62,21 +62,31 @@ inline int stream_fence(cudaStream_t st) {
 struct SideSet {
   static constexpr int N = 4;              // lane 0: independent branch of the dependency chain; lanes 1..3: dW / bias-gradient work
   cudaStream_t s[N]; cudaEvent_t fork_ev; cudaEvent_t join_ev[N];
+  cudaStream_t s0_low;                     // low-priority twin of the branch lane: swapped in when the owning stream has no raised priority
   bool used[N]; int rr; cudaStream_t owner;
 };
 struct Side {
-  static constexpr int NSETS = 6;          // one set per distinct main stream seen (main, the agent's two forward streams, a capture stream, ...)
+  static constexpr int NSETS = 8;          // one set per distinct main stream seen (main, the agent's two forward streams, a capture stream, ...)
   SideSet set[NSETS];
-  bool made = false; int enabled = -1; int nowners = 0; int fork_fence = 0;
+  bool made = false; int enabled = -1; int nowners = 0; int fork_fence = 0; int pr_least = 0;
   int init() {
     if (enabled < 0) { const char* e = getenv("SGRL_SIDE"); enabled = e ? atoi(e) : 1; }
     if (!made && enabled) {              // everything is created up front: nothing but event record/wait happens later (capture-safe)
+      // Stream priorities (SGRL_PRIO=1 enables; measured 2 % SLOWER on the B=256 update, profiles/r02z_ab_knobs.txt): the branch lane carries work of the dependency chain and inherits the
+      // priority class of the stream it forks from (the agent raises the priority of the step's critical chains); the
+      // weight-gradient lanes only have to finish before the optimizer step and fill the SMs the chain leaves idle (lowest
+      // priority) instead of delaying the chain's next kernel.
+      int pr_greatest = 0;
+      SGRL_CUDA(cudaDeviceGetStreamPriorityRange(&pr_least, &pr_greatest));
+      { const char* e = getenv("SGRL_PRIO"); if (!e || atoi(e) == 0) pr_greatest = pr_least; }      // off by default, see Agent._streams
+      const int pr_hi = pr_greatest < pr_least ? (pr_least - 1 < pr_greatest ? pr_greatest : pr_least - 1) : pr_least;
       for (int k = 0; k < NSETS; ++k) {
         for (int i = 0; i < SideSet::N; ++i) {
-          SGRL_CUDA(cudaStreamCreateWithFlags(&set[k].s[i], cudaStreamNonBlocking));
+          SGRL_CUDA(cudaStreamCreateWithPriority(&set[k].s[i], cudaStreamNonBlocking, i == 0 ? pr_hi : pr_least));
           SGRL_CUDA(cudaEventCreateWithFlags(&set[k].join_ev[i], cudaEventDisableTiming));
           set[k].used[i] = false;
         }
+        SGRL_CUDA(cudaStreamCreateWithPriority(&set[k].s0_low, cudaStreamNonBlocking, pr_least));
         SGRL_CUDA(cudaEventCreateWithFlags(&set[k].fork_ev, cudaEventDisableTiming));
         set[k].rr = 0; set[k].owner = nullptr;
       }
@@ -91,7 +101,14 @@ struct Side {
   }
   SideSet& of(cudaStream_t main) {
     for (int k = 0; k < nowners; ++k) if (set[k].owner == main) return set[k];
-    if (nowners < NSETS) { set[nowners].owner = main; return set[nowners++]; }
+    if (nowners < NSETS) {
+      SideSet& ss = set[nowners++];
+      ss.owner = main;
+      int pr = pr_least;
+      if (cudaStreamGetPriority(main, &pr) != cudaSuccess) { cudaGetLastError(); pr = pr_least; }
+      if (pr >= pr_least) { cudaStream_t t = ss.s[0]; ss.s[0] = ss.s0_low; ss.s0_low = t; }   // plain-priority owner: plain-priority branch lane
+      return ss;
+    }
     return set[(reinterpret_cast<uintptr_t>(main) >> 6) % NSETS];      // more mains than sets: share (only costs overlap)
   }
 };
@@ -298,8 +315,20 @@ inline int rowdiv_bwd(const NetCtx& c, float* dy, int lddy, const float* y, int 
   SGRL_LAUNCH_OK();
   return 0;
 }
-inline int zero_ws(const NetCtx& c, int f, int id) {
-  for (int z = 0; z < c.nb; ++z) SGRL_CUDA(cudaMemsetAsync(c.W(f, id) + z * c.zsW, 0, sizeof(float) * ws_sizes()[id] * (size_t)c.T, c.stream));
+// the dF accumulators (||G||_F gradients, T floats each) of EVERY frame in one launch at the start of the backward
+// (they were 2 * nb memset nodes per layer on the data-gradient chain)
+struct ZeroDesc { long long off[2 * (MAX_LAYERS + 1)]; int n; };
+__global__ void __launch_bounds__(256) zero_frames_kernel(float* __restrict__ ws, long long zsW, ZeroDesc d, int T) {
+  SGRL_PDL_ENTER();
+  float* p = ws + blockIdx.z * zsW + d.off[blockIdx.y];
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < T; i += gridDim.x * 256) p[i] = 0.f;
+}
+inline int zero_df_frames(const NetCtx& c) {
+  ZeroDesc d; d.n = 0;
+  for (int f = 0; f <= c.L; ++f) { d.off[d.n++] = c.wl.o[f][W_DF1]; if (f < c.L) d.off[d.n++] = c.wl.o[f][W_DF2]; }
+  int gx = ceil_div(c.T, 256); if (gx > 16) gx = 16; if (gx < 1) gx = 1;
+  launch_k(zero_frames_kernel, dim3(gx, d.n, c.nb), 256, 0, c.stream, c.ws, c.zsW, d, c.T);
+  SGRL_LAUNCH_OK();
   return 0;
 }
 
@@ -560,7 +589,7 @@ inline int net_backward(const NetCtx& c, const float* dOut, long long zsDo, int 
     for (int z = 0; z < c.nb; ++z) SGRL_CUDA(cudaMemsetAsync(c.ws + c.wl.gf + z * c.zsW, 0, sizeof(float) * (size_t)fold_floats(c.L), st));
 
   // ---------------------------------------------------------------- heads + final norm (frame L)
-  SGRL_TRY(zero_ws(c, f, W_DF1));   // dF of the head block
+  SGRL_TRY(zero_df_frames(c));      // dF accumulators of the head block and of every layer
   float* dFh = W(W_DF1);
   if (c.kind == CRITIC) {
     SGRL_TRY(block_copy(c, W(W_DQ), 1, zW, dOut, 1, zsDo, T, 1, 0));
@@ -626,12 +655,15 @@ inline int net_backward(const NetCtx& c, const float* dOut, long long zsDo, int 
     float* ua = c.SL(l, S_UA);
     float* ub = c.SL(l, S_UB);
     float* T31 = c.SL(l, S_T31);
-    SGRL_TRY(zero_ws(c, f, W_DF1));
-    SGRL_TRY(zero_ws(c, f, W_DF2));
     cudaStream_t sb;      // branch lane (== st when side streams are off: the program order below is a valid serial order)
     // ---- branch (sb): LN2 and f = linear2(relu(linear1(u')))/F2
     SGRL_TRY(side_fork(c, &sb, 0));
-    SGRL_TRY(layernorm_bwd(c, Wn(W_DH), 128, nullptr, 0, c.SL(l, S_X2), 128, c.SL(l, S_ST2), lp[L_N2_W], lp[L_N2_B], W(W_DX), 128, wg, sb));
+    // incoming dh: the final norm's output for the last layer; below it, dx1 + du[:, 128:] of the layer above, summed here
+    // instead of by a copy kernel at the end of that layer
+    if (l == c.L - 1)
+      SGRL_TRY(layernorm_bwd(c, Wn(W_DH), 128, nullptr, 0, c.SL(l, S_X2), 128, c.SL(l, S_ST2), lp[L_N2_W], lp[L_N2_B], W(W_DX), 128, wg, sb));
+    else
+      SGRL_TRY(layernorm_bwd(c, Wn(W_DH1), 128, Wn(W_DUA) + 128, 256, c.SL(l, S_X2), 128, c.SL(l, S_ST2), lp[L_N2_W], lp[L_N2_B], W(W_DX), 128, wg, sb));
     SGRL_TRY(block_copy(c, W(W_DFF), 128, zW, W(W_DX), 128, zW, T, 128, 0, nullptr, 0, 0, sb));
     SGRL_TRY(rowdiv_bwd(c, W(W_DFF), 128, c.SL(l, S_FF), 128, c.SL(l, S_F2), W(W_DF2), 128, 1.f, 0, sb));
     SGRL_TRY(side_w(W(W_DFF), 128, T31 + 256, 512, zS, lp[L_L2_W], 256, T, 128, 256, lp[L_L2_B], 1.f, sb));
@@ -707,8 +739,8 @@ inline int net_backward(const NetCtx& c, const float* dOut, long long zsDo, int 
     SGRL_TRY(side_join(c, 0));
     g = dgrad(c, W(W_DZ1), 32, lp[L_GPROJ], 128, W(W_DVG), 128, T3, NPJ, 128); g.accumulate = 1;
     SGRL_TRY(run_gemm(c, g));
-    // dh(in) = dx1 + du[:, 128:]
-    SGRL_TRY(block_copy(c, W(W_DH), 128, zW, W(W_DH1), 128, zW, T, 128, 0, W(W_DUA) + 128, 256, zW));
+    // dh(in) = dx1 + du[:, 128:]: materialised only for the embedding stage (three readers); the layer below sums the two itself
+    if (l == 0) SGRL_TRY(block_copy(c, W(W_DH), 128, zW, W(W_DH1), 128, zW, T, 128, 0, W(W_DUA) + 128, 256, zW));
   }
   // ---------------------------------------------------------------- embedding (reads frame 0)
   f = 0; fin = 0;
