@@ -125,6 +125,7 @@ struct NetCtx {
   WsLayout wl; float* ws; long long zsW;
   AttnGraphs gr; const int* rank3;
   float max_action;
+  int bwd = 0;                            // set by net_backward (tile-model hint: data-gradient chain)
   int use_tc;                             // 0: fp32 SIMT; 1: eligible GEMMs on the tcgen05 kernel (3xTF32, fp32 parity); 2: tcgen05 in BF16-input mode
   cudaStream_t stream;
 
@@ -142,6 +143,7 @@ inline int run_gemm(const NetCtx& c, const GemmP& g, cudaStream_t st = nullptr) 
   if (c.use_tc && gemm_tc_eligible(g)) {
     GemmP gi = g;
     gi.sm2_ok = c.keep ? 0 : 1;
+    gi.lat = (!c.keep || c.bwd) ? 1 : 0;
     gi.prec = c.use_tc == 2 ? 1 : 0;      // use_tc 2: BF16-input mode (reported separately, never the default)
     return gemm_tc(gi, st);
   }
@@ -164,7 +166,7 @@ inline int run_group(const NetCtx& c, const GemmP* gs, int n, cudaStream_t st = 
   for (int i = 0; i < n && all_tc; ++i) all_tc = gemm_tc_eligible(gs[i]);
   if (all_tc) {
     GemmP gp[TC_MAXG];
-    for (int i = 0; i < n; ++i) { gp[i] = gs[i]; gp[i].prec = c.use_tc == 2 ? 1 : 0; }
+    for (int i = 0; i < n; ++i) { gp[i] = gs[i]; gp[i].prec = c.use_tc == 2 ? 1 : 0; gp[i].lat = (!c.keep || c.bwd) ? 1 : 0; }
     return gemm_tc_group(gp, n, st);
   }
   for (int i = 0; i < n; ++i) SGRL_TRY(run_gemm(c, gs[i], st));
@@ -550,7 +552,8 @@ inline int net_forward(const NetCtx& c, const float* obs, long long zsObs, const
 // The data-gradient chain runs on c.stream; every dW GEMM / bias column sum forks to a side
 // stream (side_fork) right after the dY it consumes has been produced.
 // ======================================================================================
-inline int net_backward(const NetCtx& c, const float* dOut, long long zsDo, int need_wgrad, float* dact, long long zsDact) {
+inline int net_backward(const NetCtx& c_in, const float* dOut, long long zsDo, int need_wgrad, float* dact, long long zsDact) {
+  NetCtx c = c_in; c.bwd = 1;
   const int T = c.T, T3 = 3 * c.T, ng = c.ng(), KS = c.ks();
   const NetLayout& Y = c.lay;
   cudaStream_t st = c.stream;

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Print the roofline-relevant metrics of every kernel in an .ncu-rep (read here on the CPU box with `ncu -i`).
-usage: python tools/ncu_summary.py gpurun_out/prof.ncu-rep [...]"""
+usage: python tools/ncu_summary.py gpurun_out/prof.ncu-rep [...]   (or the `ncu -i ... --page raw --csv` export made on the GPU box)"""
 import csv
 import io
 import subprocess
@@ -16,7 +16,7 @@ WANT = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "la
 
 def main():
     for path in sys.argv[1:]:
-        out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        out = open(path).read() if path.endswith(".csv") else subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
         rows = list(csv.reader(io.StringIO(out)))
         if len(rows) < 3:
             print(f"# {path}: no kernels"); continue

@@ -71,3 +71,32 @@ half += timed("polyak x2", lambda: ag.try_update_target_network())
 print(f"# serial sum: critic-only step {tot:.3f} ms, actor step {tot + half:.3f} ms, policy_freq=2 average {tot + half / 2:.3f} ms")
 for step in (False, True):
     ms = timed(f"whole update (actor_step={step})", lambda: ag._update_impl(p, step))
+
+
+# ---- where the critic-only step's time beyond its critical chain goes: chain A -> loss -> backward -> Adam WITHOUT the concurrent
+# critic forward (its outputs are in the plan from the runs above), and the two forward chains alone
+def chain_a():
+    at.forward_raw(tb, p.nobs, None, keep=False, trusted_split=True, out=p.a_t, stash=p.stash_at)
+    ct.forward_raw(tb, p.nobs, p.a_t[0], keep=False, nb=2, trusted_split=True, out=p.tq, stash=p.stash_ct)
+
+
+def tail():
+    cr.backward_raw(tb, p.stash_c, p.dq, 2, cr.grad_arena(), False, trusted_split=True, ws=p.ws)
+    ag.critic_optimizer.step(max_norm=0.1)
+
+
+def fwd_ab():
+    main = torch.cuda.current_stream()
+    p.ev_start.record(main)
+    with torch.cuda.stream(p.s1):
+        p.s1.wait_event(p.ev_start)
+        chain_a()
+        p.ev_a.record(p.s1)
+    cr.forward_raw(tb, p.obs, p.act, keep=True, nb=2, trusted_split=True, out=p.q, stash=p.stash_c)
+    main.wait_event(p.ev_a)
+
+
+timed("chain A alone (actor_t -> critic_t)", chain_a)
+timed("chain A || critic fwd", fwd_ab)
+timed("chain A -> critic bwd -> adam (no critic fwd)", lambda: (chain_a(), tail()))
+timed("(chain A || critic fwd) -> critic bwd -> adam", lambda: (fwd_ab(), tail()))
