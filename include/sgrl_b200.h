@@ -100,6 +100,20 @@ int sgrl_set_forward(const SgrlNetCall* call, const float* obs, int64_t obs_stri
 int sgrl_set_backward(const SgrlNetCall* call, const float* dout, int64_t dout_stride, int need_wgrad,
                       float* dact, int64_t dact_stride, sgrl_stream_t stream);
 
+/* Data-parallel variant of sgrl_set_backward (need_wgrad = 1): the parameter gradients become final stage by stage — heads
+ * and final norm (stage n_layers), then encoder layers n_layers-1 .. 1; layer 0 and the embeddings when the call's work is
+ * done — and an event is recorded per stage on an internal stream without delaying the data-gradient chain.
+ * sgrl_stream_wait_stage(waiter, owner, stage) makes `waiter` wait for stage `stage` (1..n_layers) of the staged backward
+ * last enqueued on `owner`, so the all-reduce of that stage's gradient range (sgrl_param_range) overlaps the backward of
+ * the stages below.  Replaces the single flat all-reduce after loss.backward() that a DistributedDataParallel wrapper
+ * around the reference's modules would bucket the same way (src/agent.py:151-156, 171-176). */
+int sgrl_set_backward_staged(const SgrlNetCall* call, const float* dout, int64_t dout_stride, float* dact,
+                             int64_t dact_stride, sgrl_stream_t stream);
+int sgrl_stream_wait_stage(sgrl_stream_t waiter, sgrl_stream_t owner, int stage);
+/* float range [offset, offset + floats) inside one net's live arena: which = 0..n_layers-1: encoder layer; n_layers: the
+ * embedding-side globals (pos_encoder .. encoder.bias); n_layers + 1: the heads (gg_proj .. end of the live arena) */
+int sgrl_param_range(int kind, int n_layers, int which, int64_t* offset, int64_t* floats);
+
 /* ---- single kernels (unit tests, profiling) ---------------------------------------------- */
 /* K1: Z=[X P^T | gd], G=Z^T Z, F=||G||+1 (subequivariant_attentions.py:90-96; SEActor.py:93-100,
  * 256-262).  X (T,3,128); v0 (T,3,8) or NULL (head variant, C=136); P1,P2 (30,C) (P2/Z2 NULL for

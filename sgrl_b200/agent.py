@@ -348,6 +348,33 @@ class Agent(nn.Module):
                 check(lib.sgrl_stream_fence(stream()))
             dist.all_reduce(g, op=dist.ReduceOp.SUM)
 
+    def _backward_allreduce(self, module, tb, stash, dout, nb, ws, world):
+        """loss.backward() + the data-parallel gradient sum (src/agent.py:151, 171; a DistributedDataParallel wrapper around
+        the reference would bucket it the same way).  world > 1: the backward records an event per stage
+        (sgrl_set_backward_staged) and the NCCL all-reduce of a stage's gradient range runs on a communication stream while the
+        backward of the stages below continues; only layer 0 + the embedding-side parameters are reduced after the backward.
+        SGRL_AR_BUCKETS=0: one flat all-reduce after the backward (round 1)."""
+        g = module.grad_arena()
+        if world <= 1 or os.environ.get("SGRL_AR_BUCKETS", "1") == "0" or not g.is_cuda:
+            module.backward_raw(tb, stash, dout, nb, g, False, trusted_split=True, ws=ws)
+            self._allreduce(g, world)
+            return
+        import torch.distributed as dist
+        main = torch.cuda.current_stream()
+        comm = self._streams(g.device)[2]            # s3: idle during the backward (it carried the critic forward)
+        module.backward_raw(tb, stash, dout, nb, g, False, trusted_split=True, ws=ws, staged=True)
+        for stage, ranges in module.grad_buckets(nb):
+            if stage == 0:
+                check(lib.sgrl_stream_fence(stream()))    # eager runs only (no-op under capture), see _allreduce
+                for off, n in ranges:
+                    dist.all_reduce(g[off:off + n], op=dist.ReduceOp.SUM)
+                continue
+            check(lib.sgrl_stream_wait_stage(comm.cuda_stream, main.cuda_stream, stage), "sgrl_stream_wait_stage")
+            with torch.cuda.stream(comm):
+                for off, n in ranges:
+                    dist.all_reduce(g[off:off + n], op=dist.ReduceOp.SUM)
+        main.wait_stream(comm)
+
     def _plan(self, tb) -> "_UpdatePlan":
         key = id(tb)
         plan = self._plans.get(key)
@@ -493,8 +520,7 @@ class Agent(nn.Module):
                                        ptr(tb.tok_weight), ptr(p.target), ptr(p.dq[0]), ptr(p.dq[1]), ptr(p.scal), float(a.discount), float(self.reward_scale), T,
                                        ptr(p.rstats), tb.G, st))
         self.critic_optimizer.zero_grad()
-        self.critic.backward_raw(tb, p.stash_c, p.dq, 2, self.critic.grad_arena(), False, trusted_split=True, ws=p.ws)
-        self._allreduce(self.critic.grad_arena(), world)
+        self._backward_allreduce(self.critic, tb, p.stash_c, p.dq, 2, p.ws, world)
         self.critic_optimizer.step(max_norm=float(a.grad_clipping_value), world_size=world, keep_split=p.keep_split)
         # ---- delayed actor step + Polyak                                                                    agent.py:165-180
         if actor_step:
@@ -503,8 +529,7 @@ class Agent(nn.Module):
             check(lib.sgrl_td3_actor_loss(ptr(p.q1), ptr(tb.tok_weight), ptr(p.dq1), ptr(p.scal[1:]), T, st))
             self.critic.backward_raw(tb, p.stash_c, p.dq1, 1, None, True, trusted_split=True, ws=p.ws, dact=p.dact)   # only d/d(action)
             self.actor_optimizer.zero_grad()
-            self.actor.backward_raw(tb, p.stash_a, p.dact, 1, self.actor.grad_arena(), False, trusted_split=True, ws=p.ws)
-            self._allreduce(self.actor.grad_arena(), world)
+            self._backward_allreduce(self.actor, tb, p.stash_a, p.dact, 1, p.ws, world)
             self.actor_optimizer.step(max_norm=float(a.grad_clipping_value), world_size=world, keep_split=p.keep_split)
             self.try_update_target_network(keep_split=p.keep_split)
 

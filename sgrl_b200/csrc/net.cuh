@@ -63,6 +63,9 @@ struct SideSet {
   static constexpr int N = 4;              // lane 0: independent branch of the dependency chain; lanes 1..3: dW / bias-gradient work
   cudaStream_t s[N]; cudaEvent_t fork_ev; cudaEvent_t join_ev[N];
   cudaStream_t s0_low;                     // low-priority twin of the branch lane: swapped in when the owning stream has no raised priority
+  // staged backward (data-parallel gradient buckets): s_mark collects "everything of stage k has been enqueued and finished"
+  // without making the data-gradient chain wait for it; stage_ev[k] is what a communication stream waits on
+  cudaStream_t s_mark; cudaEvent_t mark_ev[N]; cudaEvent_t mark_main; cudaEvent_t stage_ev[MAX_LAYERS + 1]; bool marked;
   bool used[N]; int rr; cudaStream_t owner;
 };
 struct Side {
@@ -87,6 +90,11 @@ struct Side {
           set[k].used[i] = false;
         }
         SGRL_CUDA(cudaStreamCreateWithPriority(&set[k].s0_low, cudaStreamNonBlocking, pr_least));
+        SGRL_CUDA(cudaStreamCreateWithFlags(&set[k].s_mark, cudaStreamNonBlocking));
+        for (int i = 0; i < SideSet::N; ++i) SGRL_CUDA(cudaEventCreateWithFlags(&set[k].mark_ev[i], cudaEventDisableTiming));
+        SGRL_CUDA(cudaEventCreateWithFlags(&set[k].mark_main, cudaEventDisableTiming));
+        for (int i = 0; i <= MAX_LAYERS; ++i) SGRL_CUDA(cudaEventCreateWithFlags(&set[k].stage_ev[i], cudaEventDisableTiming));
+        set[k].marked = false;
         SGRL_CUDA(cudaEventCreateWithFlags(&set[k].fork_ev, cudaEventDisableTiming));
         set[k].rr = 0; set[k].owner = nullptr;
       }
@@ -126,6 +134,7 @@ struct NetCtx {
   AttnGraphs gr; const int* rank3;
   float max_action;
   int bwd = 0;                            // set by net_backward (tile-model hint: data-gradient chain)
+  int staged = 0;                         // backward: record a stage event when the parameter gradients of a stage are final (sgrl_set_backward_staged)
   int use_tc;                             // 0: fp32 SIMT; 1: eligible GEMMs on the tcgen05 kernel (3xTF32, fp32 parity); 2: tcgen05 in BF16-input mode
   cudaStream_t stream;
 
@@ -331,6 +340,48 @@ inline int zero_df_frames(const NetCtx& c) {
   int gx = ceil_div(c.T, 256); if (gx > 16) gx = 16; if (gx < 1) gx = 1;
   launch_k(zero_frames_kernel, dim3(gx, d.n, c.nb), 256, 0, c.stream, c.ws, c.zsW, d, c.T);
   SGRL_LAUNCH_OK();
+  return 0;
+}
+
+// vec(G) consumers whose gradients become final with backward stage `stage` (L = heads, l = encoder layer l)
+inline FoldDesc fold_desc_stage(const NetCtx& c, int stage) {
+  FoldDesc d; d.n = 0;
+  if (stage == c.L) { d.src[0] = c.lay.gp[G_H1G_W]; d.dst[0] = fold_offset(c.L, c.L, 0); d.rows[0] = D; d.n = 1; return d; }
+  for (int w = 0; w < 2; ++w) { d.src[d.n] = c.lay.lp[stage][w ? L_FG1_W : L_G1_W]; d.dst[d.n] = fold_offset(c.L, stage, w); d.rows[d.n] = HID; ++d.n; }
+  return d;
+}
+inline int unfold_grads(const NetCtx& c, const FoldDesc& d, cudaStream_t st) {
+  launch_k(unfold_sym_kernel, dim3(64, d.n, c.nb), 256, 0, st, c.ws + c.wl.gf, c.zsW, c.grads, c.zsG, d);
+  SGRL_LAUNCH_OK();
+  return 0;
+}
+// Staged backward: every weight-gradient launch of stage `stage` has been enqueued (side lanes, branch lane, main stream).
+// The mark stream waits for all of them, unfolds the stage's vec(G) gradients and records stage_ev[stage]; neither the
+// data-gradient chain nor the lanes wait for anything.  A communication stream that waits on the event
+// (sgrl_stream_wait_stage) may all-reduce the stage's gradient range while the backward of the stages below runs.
+inline int stage_mark(const NetCtx& c, int stage) {
+  Side& sd = g_side;
+  if (!sd.enabled || g_prof.on) {          // no side streams: everything is on the main stream
+    SGRL_TRY(unfold_grads(c, fold_desc_stage(c, stage), c.stream));
+    SideSet& ss0 = sd.of(c.stream);
+    SGRL_TRY(stream_fence(c.stream));
+    SGRL_CUDA(cudaEventRecord(ss0.stage_ev[stage], c.stream));
+    return 0;
+  }
+  SideSet& ss = sd.of(c.stream);
+  if (sd.fork_fence) SGRL_TRY(stream_fence(c.stream));
+  SGRL_CUDA(cudaEventRecord(ss.mark_main, c.stream));
+  SGRL_CUDA(cudaStreamWaitEvent(ss.s_mark, ss.mark_main, 0));
+  for (int i = 0; i < SideSet::N; ++i) {
+    if (!ss.used[i]) continue;
+    if (sd.fork_fence) SGRL_TRY(stream_fence(ss.s[i]));
+    SGRL_CUDA(cudaEventRecord(ss.mark_ev[i], ss.s[i]));
+    SGRL_CUDA(cudaStreamWaitEvent(ss.s_mark, ss.mark_ev[i], 0));
+  }
+  SGRL_TRY(unfold_grads(c, fold_desc_stage(c, stage), ss.s_mark));
+  if (sd.fork_fence) SGRL_TRY(stream_fence(ss.s_mark));
+  SGRL_CUDA(cudaEventRecord(ss.stage_ev[stage], ss.s_mark));
+  ss.marked = true;
   return 0;
 }
 
@@ -650,6 +701,8 @@ inline int net_backward(const NetCtx& c_in, const float* dOut, long long zsDo, i
   // final LayerNorm
   SGRL_TRY(layernorm_bwd(c, W(W_DSH) + ng, KS, nullptr, 0, c.S(T_HL), 128, c.S(T_STF), Y.gp[G_NORM_W], Y.gp[G_NORM_B], W(W_DH), 128, wg));
 
+  const bool staged = wg && c.staged;
+  if (staged) SGRL_TRY(stage_mark(c, c.L));
   // ---------------------------------------------------------------- encoder layers (frame l reads frame l+1)
   for (int l = c.L - 1; l >= 0; --l) {
     fin = l + 1; f = l;
@@ -744,6 +797,7 @@ inline int net_backward(const NetCtx& c_in, const float* dOut, long long zsDo, i
     SGRL_TRY(run_gemm(c, g));
     // dh(in) = dx1 + du[:, 128:]: materialised only for the embedding stage (three readers); the layer below sums the two itself
     if (l == 0) SGRL_TRY(block_copy(c, W(W_DH), 128, zW, W(W_DH1), 128, zW, T, 128, 0, W(W_DUA) + 128, 256, zW));
+    if (staged && l > 0) SGRL_TRY(stage_mark(c, l));
   }
   // ---------------------------------------------------------------- embedding (reads frame 0)
   f = 0; fin = 0;
@@ -761,10 +815,17 @@ inline int net_backward(const NetCtx& c_in, const float* dOut, long long zsDo, i
     SGRL_TRY(run_gemm(c, g));
   }
   SGRL_TRY(side_join(c));
-  if (wg) {      // gradients of the folded weights -> (rows,1024) gradient tensors
-    const FoldDesc d = fold_desc(c);
-    launch_k(unfold_sym_kernel, dim3(64, d.n, c.nb), 256, 0, st, c.ws + c.wl.gf, c.zsW, c.grads, c.zsG, d);
-    SGRL_LAUNCH_OK();
+  if (wg) {      // gradients of the folded weights -> (rows,1024) gradient tensors (staged: only layer 0 is left)
+    SGRL_TRY(unfold_grads(c, staged ? fold_desc_stage(c, 0) : fold_desc(c), st));
+  }
+  if (staged && g_side.enabled && !g_prof.on) {      // the mark stream rejoins the main stream (capture: every forked stream must)
+    SideSet& ss = g_side.of(c.stream);
+    if (ss.marked) {
+      if (g_side.fork_fence) SGRL_TRY(stream_fence(ss.s_mark));
+      SGRL_CUDA(cudaEventRecord(ss.mark_main, ss.s_mark));
+      SGRL_CUDA(cudaStreamWaitEvent(c.stream, ss.mark_main, 0));
+      ss.marked = false;
+    }
   }
   return 0;
 }

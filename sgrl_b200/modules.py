@@ -350,8 +350,10 @@ class SetNetModule(nn.Module):
         return out, stash
 
     def backward_raw(self, tb: GraphTables, stash: torch.Tensor, dout: torch.Tensor, nb: int, grads: Optional[torch.Tensor],
-                     want_dact: bool, trusted_split: bool = False, ws: Optional[torch.Tensor] = None, dact: Optional[torch.Tensor] = None):
-        """dout (nb,T,od).  Accumulates parameter gradients into `grads` (None: data-only)."""
+                     want_dact: bool, trusted_split: bool = False, ws: Optional[torch.Tensor] = None, dact: Optional[torch.Tensor] = None,
+                     staged: bool = False):
+        """dout (nb,T,od).  Accumulates parameter gradients into `grads` (None: data-only).  staged: record the per-stage
+        events of sgrl_set_backward_staged (data-parallel gradient buckets, Agent._backward_allreduce)."""
         dev = self._arena.device
         if ws is None:
             ws = torch.empty(self.ws_floats(tb.T, nb), dtype=torch.float32, device=dev)
@@ -359,9 +361,30 @@ class SetNetModule(nn.Module):
             dact = torch.empty(nb, tb.T, 3, dtype=torch.float32, device=dev)
         od = 3 if self._kind == ACTOR else 1
         k = self._call(tb, nb, 1, stash, grads=grads, ws=ws, split=self._split_for(tb.T, trusted_split))
+        if staged and grads is not None:
+            check(lib.sgrl_set_backward_staged(C.byref(k), ptr(dout), tb.T * od, ptr(dact), tb.T * 3, stream()), "sgrl_set_backward_staged")
+            return dact
         check(lib.sgrl_set_backward(C.byref(k), ptr(dout), tb.T * od, 1 if grads is not None else 0, ptr(dact), tb.T * 3, stream()),
               "sgrl_set_backward")
         return dact
+
+    def grad_buckets(self, nb: int):
+        """Gradient-arena ranges in the order the staged backward completes them: [(stage, [(offset, floats), ...]), ...] with
+        stage = n_layers (heads), then 1 (encoder layers n_layers-1 .. 1, contiguous in the arena), then 0 (layer 0 and the
+        embedding-side globals: final only when the backward has finished).  One range per net instance."""
+        L, live = self._n_layers, self._live
+
+        def rng(which):
+            off, n = C.c_int64(), C.c_int64()
+            check(lib.sgrl_param_range(self._kind, L, which, C.byref(off), C.byref(n)), "sgrl_param_range")
+            return off.value, n.value
+        heads, emb, l0 = rng(L + 1), rng(L), rng(0)
+        out = [(L, [(z * live + heads[0], heads[1]) for z in range(nb)])]
+        if L > 1:
+            b, e = rng(1)[0], rng(L - 1)[0] + rng(L - 1)[1]
+            out.append((1, [(z * live + b, e - b) for z in range(nb)]))
+        out.append((0, [(z * live + l0[0], l0[1]) for z in range(nb)] + [(z * live + emb[0], emb[1]) for z in range(nb)]))
+        return out
 
     # ------------------------------------------------------------------ autograd bridge
     def _run(self, state: torch.Tensor, action: Optional[torch.Tensor], nb: int) -> torch.Tensor:
