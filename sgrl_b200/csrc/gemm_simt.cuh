@@ -36,7 +36,9 @@ struct GemmP {
   int csk;                                  // tcgen05 path, set by the launcher: K is split over a (1, splitk, 1) cluster, rank 0 reduces through DSMEM
   int lat;                                  // tcgen05 path: launch sits on the step's critical chain (target-network forwards, data gradients): tile model may use its own wave
   int sm2_ok;                               // tcgen05 path: the single-accumulator two-CTAs-per-SM variant may be used (inference passes only)
-  long long* dbg;                           // optional (tools/gemm_trace.py): SM-clock timestamps of CTA 0's pipeline phases
+  long long* dbg;                           // optional (tools/gemm_trace.py): SM-clock timestamps of one CTA's pipeline phases
+  int dbg_cta;                              // which CTA (blockIdx.x) writes them (SGRL_TRACE_CTA, default 0)
+  int tma_c;                                // tcgen05 path, set by the launcher: plain / rowdiv store epilogue leaves through a TMA tensor store (TcProblem::mapC)
   // ---- tcgen05 path only (gemm_tc.cuh) ----
   int prec;                                 // 0: 3xTF32 error-compensated (fp32 parity); 1: BF16-INPUT mode — both operands rounded (RN-even) to bf16 in
                                             //    the operand path, ONE tf32 MMA pass (bf16 values are exact in tf32), fp32 accumulate: numerically what

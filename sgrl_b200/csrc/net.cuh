@@ -72,8 +72,15 @@ struct Side {
   static constexpr int NSETS = 8;          // one set per distinct main stream seen (main, the agent's two forward streams, a capture stream, ...)
   SideSet set[NSETS];
   bool made = false; int enabled = -1; int nowners = 0; int fork_fence = 0; int pr_least = 0;
+  int dev = -1;                            // device the lanes were created on: one process drives one GPU
   int init() {
     if (enabled < 0) { const char* e = getenv("SGRL_SIDE"); enabled = e ? atoi(e) : 1; }
+    if (enabled) {
+      int cur = -1;
+      SGRL_CUDA(cudaGetDevice(&cur));
+      if (!made) dev = cur;
+      SGRL_CHECK(cur == dev, "the library's side streams belong to another CUDA device: one process per GPU (set the device before the first call)");
+    }
     if (!made && enabled) {              // everything is created up front: nothing but event record/wait happens later (capture-safe)
       // Stream priorities (SGRL_PRIO=1 enables; measured 2 % SLOWER on the B=256 update, profiles/r02z_ab_knobs.txt): the branch lane carries work of the dependency chain and inherits the
       // priority class of the stream it forks from (the agent raises the priority of the step's critical chains); the
