@@ -1,0 +1,275 @@
+// K3-P — persistent variant of the tcgen05 projection kernel for inference passes with many tiles per SM (rollout:
+// 1 152 .. 3 456 row tiles per launch).  Included by gemm_tc.cuh (shares its PTX wrappers, TcGroup and descriptors).
+//
+// Why: measured on a steady-state CTA of a 147 456 x 768 x 256 launch (tools/gemm_trace.py, profiles/r04*): a 128 x 128 x 256
+// tile holds the tensor pipe for 6.1 K cycles (8 k-blocks x 12 MMAs x 64 cycles) but costs 11.6 K cycles of SM time even with
+// two CTAs per SM, because each CTA still pays its own pipeline fill (first operands land 2.5-4 K cycles after entry), a
+// 2-stage ring that exposes the TMA latency every other k-block, and an epilogue with the tensor pipe idle.  Here ONE CTA per
+// SM walks tiles  t = blockIdx.x, blockIdx.x + gridDim.x, ...  with
+//   * a 4-stage operand ring and 4 tensor-memory A slots that run on ACROSS tile boundaries (the producer and the converter
+//     warps are already working on tile t+1 while tile t's last MMAs execute),
+//   * TWO accumulator buffers in tensor memory (2 x 128 columns): dedicated epilogue warps drain buffer b (tcgen05.ld ->
+//     bias / relu / F-division in registers -> swizzled shared box -> cp.async.bulk.tensor store) while the MMA warp fills
+//     buffer b^1,
+// so that in steady state the SM's tensor pipe only waits for operands.  Like the two-CTAs-per-SM variant it keeps all three
+// product terms of the 3xTF32 split in ONE accumulator (<= 12 k-blocks, <= 144 truncating adds: measured 2e-6 relative), so
+// only passes that keep nothing for a backward use it (GemmP::sm2_ok), and only the store-class epilogues (GemmP::tma_c).
+//
+// CTA = 14 warps: warp 0 TMA producer, warp 1 TMEM owner + MMA issuer, warps 2-9 two converter groups (alternate k-blocks),
+// warps 10-13 epilogue (warp w owns TMEM lane quarter w & 3).
+#pragma once
+
+namespace sgrl {
+
+constexpr int TCP_BN = 128;
+constexpr int TCP_STAGES = 4, TCP_TA = 4;
+constexpr int TCP_B_BYTES = TCP_BN * TC_BK * 4;                    // 16 KiB (hi or lo)
+constexpr int TCP_STAGE_BYTES = TC_A_BYTES + 2 * TCP_B_BYTES;      // 48 KiB: [A raw | B hi | B lo]
+constexpr int TCP_EPI_WARPS = 4;
+constexpr int TCP_THREADS = 64 + TC_CONV_THREADS + 32 * TCP_EPI_WARPS;   // 448
+constexpr int TCP_RING_BYTES = TCP_STAGES * TCP_STAGE_BYTES;       // 192 KiB
+constexpr int TCP_BOX_BYTES = 32 * 32 * 4;                         // one warp's 32 x 32 fp32 store box
+constexpr int TCP_SMEM = TCP_RING_BYTES + TCP_EPI_WARPS * 2 * TCP_BOX_BYTES + 256 /*barriers*/ + 1024 /*align slack*/;
+constexpr int TCP_MAX_KB = 12;                                     // k-blocks per tile on the one accumulator
+
+struct TcpTile { int gi, z, m0, n0, nkb; };
+// virtual tile id -> problem of the group, instance, tile origin (n fastest: the CTAs working side by side share A rows in L2)
+__device__ __forceinline__ TcpTile tcp_decode(const TcGroup& grp, int vt) {
+  TcpTile t;
+  t.gi = 0;
+#pragma unroll
+  for (int k = 1; k < TC_MAXG; ++k) if (k < grp.n && vt >= grp.pr[k].cta_begin) t.gi = k;
+  const GemmP& p = grp.pr[t.gi].p;
+  const int local = vt - grp.pr[t.gi].cta_begin;
+  const int tiles_n = (p.N + TCP_BN - 1) / TCP_BN, tiles_m = (p.M + TC_BM - 1) / TC_BM;
+  const int per_z = tiles_m * tiles_n;
+  t.z = local / per_z;
+  const int rem = local - t.z * per_z;
+  t.m0 = (rem / tiles_n) * TC_BM;
+  t.n0 = (rem % tiles_n) * TCP_BN;
+  t.nkb = (p.K + TC_BK - 1) / TC_BK;
+  return t;
+}
+
+__global__ void __launch_bounds__(TCP_THREADS, 1) gemm_tc_persist_kernel(const __grid_constant__ TcGroup grp, int total_tiles) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t epi_base = smem_base + TCP_RING_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TCP_RING_BYTES + TCP_EPI_WARPS * 2 * TCP_BOX_BYTES);
+  const uint32_t bar_base = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (TCP_STAGES + s); };
+  auto ta_ready = [&](int t) { return bar_base + 8u * (2 * TCP_STAGES + t); };
+  auto ta_empty = [&](int t) { return bar_base + 8u * (2 * TCP_STAGES + TCP_TA + t); };
+  auto acc_full = [&](int b) { return bar_base + 8u * (2 * TCP_STAGES + 2 * TCP_TA + b); };
+  auto acc_empty = [&](int b) { return bar_base + 8u * (2 * TCP_STAGES + 2 * TCP_TA + 2 + b); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TCP_STAGES + 2 * TCP_TA + 4);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  SGRL_PDL_TRIGGER();
+  if (tid == 0) {
+    for (int s = 0; s < TCP_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int t = 0; t < TCP_TA; ++t) { mbar_init(ta_ready(t), TC_CONV_WARPS / 2); mbar_init(ta_empty(t), 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(acc_full(b), 1); mbar_init(acc_empty(b), TCP_EPI_WARPS); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    for (int g = 0; g < grp.n; ++g) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&grp.pr[g].mapA) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&grp.pr[g].mapB) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&grp.pr[g].mapBlo) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&grp.pr[g].mapC) : "memory");
+    }
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;                       // columns [0, 256): two accumulators; [256, 512): 4 A slots [hi 32 | lo 32]
+  const uint32_t ta_base = tmem_base + 2 * TCP_BN;
+  SGRL_PDL_WAIT();
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    uint32_t kbg = 0;
+    for (int vt = blockIdx.x; vt < total_tiles; vt += gridDim.x) {
+      const TcpTile t = tcp_decode(grp, vt);
+      const TcProblem& pr = grp.pr[t.gi];
+      const int zA = pr.p.zsA ? t.z : 0, zB = pr.p.zsB ? t.z : 0;
+      for (int i = 0; i < t.nkb; ++i, ++kbg) {
+        const int s = kbg % TCP_STAGES;
+        mbar_wait(empty_bar(s), ((kbg / TCP_STAGES) & 1u) ^ 1u);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(full_bar(s), TCP_STAGE_BYTES);
+          const uint32_t a_dst = smem_base + s * TCP_STAGE_BYTES, b_dst = a_dst + TC_A_BYTES;
+          tma_load_3d(a_dst, &pr.mapA, full_bar(s), i * TC_BK, t.m0, zA);
+          tma_load_3d(b_dst, &pr.mapB, full_bar(s), i * TC_BK, t.n0, zB);
+          tma_load_3d(b_dst + TCP_B_BYTES, &pr.mapBlo, full_bar(s), i * TC_BK, t.n0, zB);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (warp-uniform control flow, one elected lane issues) =====================
+    constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TCP_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+    constexpr uint32_t B_HIW = (1024u >> 4) | (1u << 14) | (2u << 29), B_LOW = (16u >> 4) << 16;     // K-major, SWIZZLE_128B
+    const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint32_t tab = tb + 2 * TCP_BN;
+    const uint32_t bdesc0 = (((smem_base + TC_A_BYTES) >> 4) & 0x3FFFu) | B_LOW;
+    uint32_t kbg = 0, tcount = 0;
+    bool ready = false;                       // barriers of the block about to be issued were already seen complete
+    for (int vt = blockIdx.x; vt < total_tiles; vt += gridDim.x, ++tcount) {
+      const TcpTile t = tcp_decode(grp, vt);
+      const uint32_t b = tcount & 1u;
+      mbar_wait(acc_empty(b), ((tcount >> 1) & 1u) ^ 1u);      // the epilogue has drained this buffer (two tiles ago)
+      tc_fence_after();
+      const uint32_t acc = tb + b * TCP_BN;
+#pragma unroll 1
+      for (int i = 0; i < t.nkb; ++i, ++kbg) {
+        const int s = kbg % TCP_STAGES, ts = kbg % TCP_TA;
+        if (!ready) {
+          mbar_wait(full_bar(s), (kbg / TCP_STAGES) & 1u);
+          mbar_wait(ta_ready(ts), (kbg / TCP_TA) & 1u);
+          tc_fence_after();
+        }
+        const uint32_t b_hi = bdesc0 + (uint32_t)(s * (TCP_STAGE_BYTES >> 4)), b_lo = b_hi + (TCP_B_BYTES >> 4);
+        const uint32_t a_hi = tab + ts * 64, a_lo = a_hi + 32;
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) tc_mma_tf32_ts(acc, a_hi + 8 * k, b_hi + 2 * k, B_HIW, idesc, (i > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            tc_mma_tf32_ts(acc, a_lo + 8 * k, b_hi + 2 * k, B_HIW, idesc, 1u);
+            tc_mma_tf32_ts(acc, a_hi + 8 * k, b_lo + 2 * k, B_HIW, idesc, 1u);
+          }
+        }
+        __syncwarp();
+        // the next block's barriers are probed behind the 8 queued MMAs; never blocked on here (see gemm_tc_kernel)
+        ready = false;
+        if (i + 1 < t.nkb) {
+          const uint32_t kn = kbg + 1;
+          ready = mbar_test_all(full_bar(kn % TCP_STAGES), (kn / TCP_STAGES) & 1u) && mbar_test_all(ta_ready(kn % TCP_TA), (kn / TCP_TA) & 1u);
+          if (ready) tc_fence_after();
+        }
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 2; k < 4; ++k) {
+            tc_mma_tf32_ts(acc, a_lo + 8 * k, b_hi + 2 * k, B_HIW, idesc, 1u);
+            tc_mma_tf32_ts(acc, a_hi + 8 * k, b_lo + 2 * k, B_HIW, idesc, 1u);
+          }
+          tc_commit(empty_bar(s));
+          tc_commit(ta_empty(ts));
+          if (i == t.nkb - 1) tc_commit(acc_full(b));
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp < 2 + TC_CONV_WARPS) {
+    // ===================== converters: landed A k-block -> [hi | lo] rows of a tensor-memory slot =====================
+    const int g = (warp - 2) >> 2, q = warp & 3, row = q * 32 + lane;
+    const uint32_t trow = ta_base + ((uint32_t)(q * 32) << 16);
+    uint32_t kbg = 0;
+    for (int vt = blockIdx.x; vt < total_tiles; vt += gridDim.x) {
+      const TcpTile t = tcp_decode(grp, vt);
+      for (int i = 0; i < t.nkb; ++i, ++kbg) {
+        if ((int)(kbg & 1u) != g) continue;
+        const int s = kbg % TCP_STAGES, ts = kbg % TCP_TA;
+        mbar_wait(full_bar(s), (kbg / TCP_STAGES) & 1u);
+        const uint32_t st = smem_base + s * TCP_STAGE_BYTES;
+        uint32_t raw[32], lo[32];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const float4 v = lds128(st + (uint32_t)row * 128u + (uint32_t)((c ^ (row & 7)) << 4));
+          raw[4 * c] = __float_as_uint(v.x); raw[4 * c + 1] = __float_as_uint(v.y);
+          raw[4 * c + 2] = __float_as_uint(v.z); raw[4 * c + 3] = __float_as_uint(v.w);
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) lo[j] = lo_of_trunc(__uint_as_float(raw[j]));
+        mbar_wait(ta_empty(ts), ((kbg / TCP_TA) & 1u) ^ 1u);
+        tc_fence_after();
+        tmem_st32(trow + (uint32_t)(ts * 64), raw);
+        tmem_st32(trow + (uint32_t)(ts * 64 + 32), lo);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(ta_ready(ts));
+      }
+    }
+  } else {
+    // ===================== epilogue warps: accumulator buffer -> registers -> swizzled box -> TMA tensor store =====================
+    const int ew = warp - (2 + TC_CONV_WARPS), q = warp & 3;
+    const uint32_t arow = tmem_base + ((uint32_t)(q * 32) << 16);
+    const uint32_t rsw = (uint32_t)(lane & 7);
+    uint32_t tcount = 0, nbox = 0;
+    for (int vt = blockIdx.x; vt < total_tiles; vt += gridDim.x, ++tcount) {
+      const TcpTile t = tcp_decode(grp, vt);
+      const TcProblem& pr = grp.pr[t.gi];
+      const GemmP& p = pr.p;
+      const uint32_t b = tcount & 1u;
+      const int m_w = t.m0 + q * 32;
+      const bool rows_ok = m_w < p.M;                            // warp-uniform
+      const float* bias = p.bias ? p.bias + t.z * p.zsBias : nullptr;
+      float rinv = 1.f;
+      if (p.rowdiv && m_w + lane < p.M) rinv = 1.f / __ldg(p.rowdiv + t.z * p.zsRow + m_w + lane);
+      if (bias && lane < TCP_BN / 32 && t.n0 + lane * 32 < p.N) asm volatile("prefetch.global.L1 [%0];" ::"l"(bias + t.n0 + lane * 32));
+      const float alpha = p.alpha, csv = p.colscale;
+      const bool relu = p.relu != 0, rdiv = p.rowdiv != nullptr;
+      mbar_wait(acc_full(b), (tcount >> 1) & 1u);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < TCP_BN / 32; ++c) {
+        const int nc = t.n0 + 32 * c;
+        uint32_t r[32];
+        tmem_ld32(arow + b * TCP_BN + (uint32_t)(32 * c), r);
+        float bj[32];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int n = nc + 4 * k;
+          float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (bias && n + 3 < p.N) bv = ldg4(bias + n);
+          bj[4 * k] = bv.x; bj[4 * k + 1] = bv.y; bj[4 * k + 2] = bv.z; bj[4 * k + 3] = bv.w;
+        }
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (c == TCP_BN / 32 - 1) {            // every column of the buffer is in registers: the MMA warp may overwrite it
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(acc_empty(b));
+        }
+        if (!rows_ok || nc >= p.N) continue;   // warp-uniform
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float x = fmaf(alpha, __uint_as_float(r[j]), bj[j]);
+          v[j] = (relu && x < 0.f) ? 0.f : x;
+        }
+        if (rdiv) {
+          const int ncs = p.colscale_n - nc;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] *= rinv * (j < ncs ? csv : 1.f);
+        }
+        const uint32_t box = epi_base + (uint32_t)(ew * 2 + (nbox & 1u)) * TCP_BOX_BYTES;
+        ++nbox;
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");     // the store that last used this box has read it
+        __syncwarp();
+        const uint32_t rowa = box + (uint32_t)lane * 128u;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) sts128(rowa + (((uint32_t)k ^ rsw) << 4), make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]));
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) { tma_store_3d(&pr.mapC, box, nc, m_w, t.z); tma_store_commit(); }
+      }
+    }
+    if (lane == 0) tma_store_wait_read();
+    __syncwarp();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+}  // namespace sgrl
