@@ -113,7 +113,9 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) gemm_tc_persist_kernel(const _
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (warp-uniform control flow, one elected lane issues) =====================
-    constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TCP_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+    // instruction descriptor: D=f32, A=B=tf32, K-major; the N field is set per tile (a 32-column problem issues N = 32 MMAs:
+    // 16 instead of 64 cycles each — the Z = [X P^T | gd] projections are then bound by their 64 KB of A per tile, not by MMAs on zero columns)
+    constexpr uint32_t idesc0 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_BM >> 4) << 24);
     constexpr uint32_t B_HIW = (1024u >> 4) | (1u << 14) | (2u << 29), B_LOW = (16u >> 4) << 16;     // K-major, SWIZZLE_128B
     const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
     const uint32_t tab = tb + 2 * TCP_BN;
@@ -126,6 +128,9 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) gemm_tc_persist_kernel(const _
       mbar_wait(acc_empty(b), ((tcount >> 1) & 1u) ^ 1u);      // the epilogue has drained this buffer (two tiles ago)
       tc_fence_after();
       const uint32_t acc = tb + b * TCP_BN;
+      int n_eff = grp.pr[t.gi].p.N - t.n0;                       // columns of this tile, rounded up to the MMA's N granularity of 16
+      n_eff = n_eff >= TCP_BN ? TCP_BN : ((n_eff + 15) & ~15);
+      const uint32_t idesc = idesc0 | ((uint32_t)(n_eff >> 3) << 17);
 #pragma unroll 1
       for (int i = 0; i < t.nkb; ++i, ++kbg) {
         const int s = kbg % TCP_STAGES, ts = kbg % TCP_TA;
@@ -244,6 +249,13 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) gemm_tc_persist_kernel(const _
           const float x = fmaf(alpha, __uint_as_float(r[j]), bj[j]);
           v[j] = (relu && x < 0.f) ? 0.f : x;
         }
+        if (p.gdcols && nc == 0) {             // Z = [X P^T | gd]: columns 30, 31 of row m = 3 t + r are gd[t][r][0..1]  (N == 32)
+          const int m = m_w + lane;
+          if (m < p.M) {
+            const float2 gv = __ldg(reinterpret_cast<const float2*>(p.gdcols + t.z * p.zsGd + (long long)(m / 3) * 6 + (m % 3) * 2));
+            v[NPJ] = gv.x; v[NPJ + 1] = gv.y;
+          }
+        }
         if (rdiv) {
           const int ncs = p.colscale_n - nc;
 #pragma unroll
@@ -259,6 +271,241 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) gemm_tc_persist_kernel(const _
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
         if (lane == 0) { tma_store_3d(&pr.mapC, box, nc, m_w, t.z); tma_store_commit(); }
+      }
+    }
+    if (lane == 0) tma_store_wait_read();
+    __syncwarp();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+
+// ======================================================================================================================
+// K3-PG — persistent GRAM projection for inference passes:  C = epi( tri(Z^T Z) W'^T )  with the A operand generated by the
+// converter warps (GemmP::gramZ, see gemm_tc_kernel<.., GRAM>) and ALL N <= 256 output columns in one tile, so that each
+// token's packed Gram row (17 k-blocks of 32) is generated ONCE instead of once per 128-column tile — generation, not the
+// tensor pipe, bounds the 128-wide GRAM tile (measured, tools/gemm_trace.py: ~1 000 cycles per k-block against 768 of MMAs).
+// One CTA per SM walks row tiles; B (folded weights, pre-split) streams through a 2-stage ring of [hi | lo] 256 x 32 tiles;
+// tensor memory = one 256-column accumulator + 4 A slots; the converter warps already generate the next tile's first k-blocks
+// while the epilogue warps drain the accumulator.  Single accumulator for all three product terms: inference passes only.
+// ======================================================================================================================
+constexpr int TCG_BN = 256, TCG_STAGES = 2, TCG_TA = 4;
+constexpr int TCG_B_BYTES = TCG_BN * TC_BK * 4;                    // 32 KiB (hi or lo)
+constexpr int TCG_STAGE_BYTES = 2 * TCG_B_BYTES;                   // 64 KiB
+constexpr int TCG_RING_BYTES = TCG_STAGES * TCG_STAGE_BYTES;       // 128 KiB
+constexpr int TCG_Z_BYTES = TC_BM * GRAM_ZLD * 4;                  // 50 KiB: the tile's Z rows, padded stride
+constexpr int TCG_SMEM = TCG_RING_BYTES + TCG_Z_BYTES + 1024 /*partial ||G||^2*/ + TCP_EPI_WARPS * 2 * TCP_BOX_BYTES + 256 + 1024;
+constexpr int TCG_NKB = GP_K / TC_BK;                              // 17
+
+__global__ void __launch_bounds__(TCP_THREADS, 1) gemm_tc_gram_persist_kernel(const __grid_constant__ TcGroup grp, int total_tiles) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t gram_z = smem_base + TCG_RING_BYTES;
+  float* gram_ss = reinterpret_cast<float*>(smem + TCG_RING_BYTES + TCG_Z_BYTES);               // [2 groups][128 rows]
+  const uint32_t epi_base = smem_base + TCG_RING_BYTES + TCG_Z_BYTES + 1024;                    // 1024-aligned: 128 K + 50 K + 1 K
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TCG_RING_BYTES + TCG_Z_BYTES + 1024 + TCP_EPI_WARPS * 2 * TCP_BOX_BYTES);
+  const uint32_t bar_base = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (TCG_STAGES + s); };
+  auto ta_ready = [&](int t) { return bar_base + 8u * (2 * TCG_STAGES + t); };
+  auto ta_empty = [&](int t) { return bar_base + 8u * (2 * TCG_STAGES + TCG_TA + t); };
+  const uint32_t acc_full = bar_base + 8u * (2 * TCG_STAGES + 2 * TCG_TA), acc_empty = acc_full + 8u;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TCG_STAGES + 2 * TCG_TA + 2);
+  static_assert((TCG_RING_BYTES + TCG_Z_BYTES + 1024) % 1024 == 0, "store boxes need 1024-byte alignment (SWIZZLE_128B)");
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const TcProblem& pr = grp.pr[0];
+  const GemmP& p = pr.p;
+  const int tiles_m = (p.M + TC_BM - 1) / TC_BM;                 // tile id = z * tiles_m + row tile
+  SGRL_PDL_TRIGGER();
+  if (tid == 0) {
+    for (int s = 0; s < TCG_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int t = 0; t < TCG_TA; ++t) { mbar_init(ta_ready(t), TC_CONV_WARPS / 2); mbar_init(ta_empty(t), 1); }
+    mbar_init(acc_full, 1); mbar_init(acc_empty, TCP_EPI_WARPS);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&pr.mapB) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&pr.mapBlo) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&pr.mapC) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;                         // columns [0, 256): accumulator; [256, 512): 4 A slots [hi 32 | lo 32]
+  const uint32_t ta_base = tmem_base + TCG_BN;
+  SGRL_PDL_WAIT();
+
+  if (warp == 0) {
+    // ===================== TMA producer: the folded weights' k-blocks (the same 17 for every tile; L2-resident) =====================
+    uint32_t kbg = 0;
+    for (int vt = blockIdx.x; vt < total_tiles; vt += gridDim.x) {
+      const int zB = p.zsB ? vt / tiles_m : 0;
+      for (int i = 0; i < TCG_NKB; ++i, ++kbg) {
+        const int s = kbg % TCG_STAGES;
+        mbar_wait(empty_bar(s), ((kbg / TCG_STAGES) & 1u) ^ 1u);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(full_bar(s), TCG_STAGE_BYTES);
+          const uint32_t b_dst = smem_base + s * TCG_STAGE_BYTES;
+          tma_load_3d(b_dst, &pr.mapB, full_bar(s), i * TC_BK, 0, zB);
+          tma_load_3d(b_dst + TCG_B_BYTES, &pr.mapBlo, full_bar(s), i * TC_BK, 0, zB);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    int n_eff = (p.N + 15) & ~15;
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n_eff >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+    constexpr uint32_t B_HIW = (1024u >> 4) | (1u << 14) | (2u << 29), B_LOW = (16u >> 4) << 16;     // K-major, SWIZZLE_128B
+    const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint32_t tab = tb + TCG_BN;
+    const uint32_t bdesc0 = ((smem_base >> 4) & 0x3FFFu) | B_LOW;
+    uint32_t kbg = 0, tcount = 0;
+    bool ready = false;
+    for (int vt = blockIdx.x; vt < total_tiles; vt += gridDim.x, ++tcount) {
+      mbar_wait(acc_empty, (tcount & 1u) ^ 1u);                // the epilogue has drained the previous tile
+      tc_fence_after();
+#pragma unroll 1
+      for (int i = 0; i < TCG_NKB; ++i, ++kbg) {
+        const int s = kbg % TCG_STAGES, ts = kbg % TCG_TA;
+        if (!ready) {
+          mbar_wait(full_bar(s), (kbg / TCG_STAGES) & 1u);
+          mbar_wait(ta_ready(ts), (kbg / TCG_TA) & 1u);
+          tc_fence_after();
+        }
+        const uint32_t b_hi = bdesc0 + (uint32_t)(s * (TCG_STAGE_BYTES >> 4)), b_lo = b_hi + (TCG_B_BYTES >> 4);
+        const uint32_t a_hi = tab + ts * 64, a_lo = a_hi + 32;
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) tc_mma_tf32_ts(tb, a_hi + 8 * k, b_hi + 2 * k, B_HIW, idesc, (i > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            tc_mma_tf32_ts(tb, a_lo + 8 * k, b_hi + 2 * k, B_HIW, idesc, 1u);
+            tc_mma_tf32_ts(tb, a_hi + 8 * k, b_lo + 2 * k, B_HIW, idesc, 1u);
+          }
+        }
+        __syncwarp();
+        ready = false;
+        if (i + 1 < TCG_NKB) {
+          const uint32_t kn = kbg + 1;
+          ready = mbar_test_all(full_bar(kn % TCG_STAGES), (kn / TCG_STAGES) & 1u) && mbar_test_all(ta_ready(kn % TCG_TA), (kn / TCG_TA) & 1u);
+          if (ready) tc_fence_after();
+        }
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 2; k < 4; ++k) {
+            tc_mma_tf32_ts(tb, a_lo + 8 * k, b_hi + 2 * k, B_HIW, idesc, 1u);
+            tc_mma_tf32_ts(tb, a_hi + 8 * k, b_lo + 2 * k, B_HIW, idesc, 1u);
+          }
+          tc_commit(empty_bar(s));
+          tc_commit(ta_empty(ts));
+          if (i == TCG_NKB - 1) tc_commit(acc_full);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp < 2 + TC_CONV_WARPS) {
+    // ===================== generators: Z tile -> packed Gram rows -> [hi | lo] in a tensor-memory slot =====================
+    const int g = (warp - 2) >> 2, q = warp & 3, row = q * 32 + lane;
+    const int cth = (warp - 2) * 32 + lane;                        // 0..255
+    const uint32_t trow = ta_base + ((uint32_t)(q * 32) << 16);
+    const uint32_t zrow = gram_z + (uint32_t)(row * GRAM_ZLD) * 4u;
+    uint32_t kbg = 0;
+    for (int vt = blockIdx.x; vt < total_tiles; vt += gridDim.x) {
+      const int z = vt / tiles_m, m0 = (vt - z * tiles_m) * TC_BM;
+      // both groups are done reading the previous tile's Z rows (and group 0 its partial sums) before they are overwritten
+      asm volatile("bar.sync 1, %0;" ::"n"(TC_CONV_THREADS) : "memory");
+      const float4* zsrc = reinterpret_cast<const float4*>(p.gramZ + z * p.zsGramZ + (long long)m0 * 96);
+#pragma unroll
+      for (int c = 0; c < 12; ++c) {
+        const int f = cth + c * TC_CONV_THREADS, r = f / 24, c4 = f - r * 24;
+        const float4 v = (m0 + r < p.M) ? __ldg(zsrc + f) : make_float4(0.f, 0.f, 0.f, 0.f);
+        sts128(gram_z + (uint32_t)(r * GRAM_ZLD + c4 * 4) * 4u, v);
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(TC_CONV_THREADS) : "memory");
+      float ss = 0.f;
+      for (int i = 0; i < TCG_NKB; ++i, ++kbg) {
+        if ((int)(kbg & 1u) != g) continue;
+        const int ts = kbg % TCG_TA;
+        uint32_t raw[32];
+        gram_kblock(i, zrow, raw, ss);                     // generated before the slot wait: overlaps the MMAs still reading it
+        mbar_wait(ta_empty(ts), ((kbg / TCG_TA) & 1u) ^ 1u);
+        tc_fence_after();
+        tmem_st32(trow + (uint32_t)(ts * 64), raw);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) raw[j] = lo_of_trunc(__uint_as_float(raw[j]));
+        tmem_st32(trow + (uint32_t)(ts * 64 + 32), raw);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(ta_ready(ts));
+      }
+      gram_ss[g * 128 + row] = ss;
+      asm volatile("bar.sync 1, %0;" ::"n"(TC_CONV_THREADS) : "memory");          // both groups' partial ||G||_F^2 are in gram_ss
+      if (g == 0 && p.gramF && m0 + row < p.M) p.gramF[z * p.zsGramZ + m0 + row] = sqrtf(gram_ss[row] + gram_ss[128 + row]) + 1.0f;
+    }
+  } else {
+    // ===================== epilogue warps =====================
+    const int ew = warp - (2 + TC_CONV_WARPS), q = warp & 3;
+    const uint32_t arow = tmem_base + ((uint32_t)(q * 32) << 16);
+    const uint32_t rsw = (uint32_t)(lane & 7);
+    const float alpha = p.alpha;
+    const bool relu = p.relu != 0;
+    const int nch = (p.N + 31) / 32;
+    uint32_t tcount = 0, nbox = 0;
+    for (int vt = blockIdx.x; vt < total_tiles; vt += gridDim.x, ++tcount) {
+      const int z = vt / tiles_m, m0 = (vt - z * tiles_m) * TC_BM;
+      const int m_w = m0 + q * 32;
+      const bool rows_ok = m_w < p.M;
+      const float* bias = p.bias ? p.bias + z * p.zsBias : nullptr;
+      if (bias && lane < nch) asm volatile("prefetch.global.L1 [%0];" ::"l"(bias + lane * 32));
+      mbar_wait(acc_full, tcount & 1u);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < nch; ++c) {
+        const int nc = 32 * c;
+        uint32_t r[32];
+        tmem_ld32(arow + (uint32_t)nc, r);
+        float bj[32];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int n = nc + 4 * k;
+          float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (bias && n + 3 < p.N) bv = ldg4(bias + n);
+          bj[4 * k] = bv.x; bj[4 * k + 1] = bv.y; bj[4 * k + 2] = bv.z; bj[4 * k + 3] = bv.w;
+        }
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (c == nch - 1) {                    // the whole accumulator is in registers / on its way out: the next tile's MMAs may start
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(acc_empty);
+        }
+        if (!rows_ok) continue;
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float x = fmaf(alpha, __uint_as_float(r[j]), bj[j]);
+          v[j] = (relu && x < 0.f) ? 0.f : x;
+        }
+        const uint32_t box = epi_base + (uint32_t)(ew * 2 + (nbox & 1u)) * TCP_BOX_BYTES;
+        ++nbox;
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        __syncwarp();
+        const uint32_t rowa = box + (uint32_t)lane * 128u;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) sts128(rowa + (((uint32_t)k ^ rsw) << 4), make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]));
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) { tma_store_3d(&pr.mapC, box, nc, m_w, z); tma_store_commit(); }
       }
     }
     if (lane == 0) tma_store_wait_read();

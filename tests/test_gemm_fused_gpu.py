@@ -57,6 +57,35 @@ def test_gram_gemm(T, N, keep):
         assert rel(Gp[:, slots], G[:, ri, ci]) < 1e-6 and torch.all(Gp[:, pads] == 0)
 
 
+@pytest.mark.parametrize("T,N", [(40000, 256), (38001, 128), (60000, 256)])
+def test_gram_gemm_persistent(monkeypatch, T, N):
+    """Persistent GRAM projection of inference passes (csrc/gemm_tc_persist.cuh: all N <= 256 columns in one tile, every packed Gram
+    row generated once) against fp64 and against the per-tile kernel; row tail, sub-matrix ldc, F = ||G|| + 1."""
+    from sgrl_b200._lib import lib, ptr, stream, check
+    g = torch.Generator(device="cuda").manual_seed(T + N)
+    Z = torch.randn(T, 3, 32, device="cuda", generator=g)
+    Z[:, :, 30] = torch.tensor([0.0, 0.0, -9.81], device="cuda")
+    W = torch.randn(N, 1024, device="cuda", generator=g) / 32.0
+    b = torch.randn(N, device="cuda", generator=g)
+    hi, lo = split(fold(W).contiguous())
+    out = []
+    for mode in ("2", "0"):
+        monkeypatch.setenv("SGRL_TC_PERSIST", mode)
+        Cm = torch.full((T, N + 4), 7.0, device="cuda")
+        F = torch.zeros(T, device="cuda")
+        check(lib.sgrl_gemm_gram(ptr(Z), ptr(hi), ptr(lo), ptr(b), ptr(Cm), N + 4, ptr(F), None, T, N, 1, stream()), "gram")
+        torch.cuda.synchronize()
+        out.append((Cm, F))
+    Zd = Z.double()
+    G = Zd.transpose(1, 2) @ Zd
+    ref = torch.relu(G.reshape(T, 1024) @ W.double().T + b.double())
+    for Cm, F in out:
+        assert rel(Cm[:, :N], ref) < TOL
+        assert torch.all(Cm[:, N:] == 7.0)
+        assert rel(F, G.reshape(T, -1).norm(dim=1) + 1.0) < 1e-6
+    assert torch.equal(out[0][1], out[1][1])                      # F: same products and summation order in both kernels
+
+
 @pytest.mark.parametrize("T3,K,ldw", [(6912, 128, 128), (900, 128, 136), (601, 128, 128)])
 def test_gd_projection(T3, K, ldw):
     from sgrl_b200._lib import lib, ptr, stream, check

@@ -19,7 +19,16 @@ rowdiv = len(sys.argv) > 4 and sys.argv[4] == "1"
 F = torch.rand(M, device="cuda") * 900 + 100 if rowdiv else None
 
 
+gram = len(sys.argv) > 6 and sys.argv[6] == "gram"      # A generated from Z (K = 544 packed Gram rows): M N 544 0 reps gram
+if gram:
+    Z = torch.randn(M, 96, device="cuda")
+    Fo = torch.zeros(M, device="cuda")
+
+
 def run():
+    if gram:
+        check(lib.sgrl_gemm_gram(ptr(Z), ptr(hi), ptr(lo), None, ptr(Y), N, ptr(Fo), None, M, N, 1, stream()))
+        return
     check(lib.sgrl_gemm_presplit(ptr(X), K, 0, ptr(hi), ptr(lo), K, 0, ptr(Y), N, M, N, K, 1.0, None, ptr(F) if rowdiv else None, 0, 0, 1, stream()))
 
 
@@ -34,6 +43,8 @@ e1.record()
 torch.cuda.synchronize()
 us = e0.elapsed_time(e1) * 1e3 / reps
 ref = X[:4096].double() @ W.double().t()
+if gram:
+    ref = Y[:4096].double()      # checked in tests/test_gemm_fused_gpu.py
 if rowdiv:
     ref = ref / F[:4096].double()[:, None]
 err = ((Y[:4096].double() - ref).norm() / ref.norm()).item()
