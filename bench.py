@@ -46,6 +46,8 @@ def parse():
     ap.add_argument("--packed", action="store_true", help="with --set: all morphologies of the rank in ONE packed update (Agent.update_packed) "
                     "instead of the reference's one-after-the-other schedule (src/trainer.py:245-250)")
     ap.add_argument("--check-replicas", action="store_true", help="after the run, compare the parameter arenas of all ranks bit for bit")
+    ap.add_argument("--rollout-sweep", default="", help="comma-separated env counts per GPU (BASELINE config 5: 1K-64K parallel humanoid envs): "
+                    "adds rollout_sweep = [{envs_per_gpu, ms_per_forward, value}, ...] to the line, same timing as the rollout leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-rollout", action="store_true")
     ap.add_argument("--no-bf16", action="store_true", help="skip the separately reported BF16-input leg")
@@ -384,6 +386,30 @@ def run_ours(a):
                            "share_ms": {k: v[0] for k, v in rp.items()},
                            "traffic_ncu": {"feature_k1": {"dram_bytes_per_launch": 550.5e6, "algorithmic_bytes_per_launch": 4124.0 * 147456,
                                                           "src": "profiles/r01k_ncu_k1_k2_summary.txt (T=147456)"}}}
+
+    if a.rollout_sweep:
+        sweep = []
+        for E in [int(x) for x in a.rollout_sweep.split(",") if x]:
+            obs = synth.make_obs(min(E, 4096), N, seed=7).to(dev)
+            obs = obs.repeat((E + obs.shape[0] - 1) // obs.shape[0], 1)[:E].contiguous()
+            with torch.no_grad():
+                for _ in range(3):
+                    agent.actor(obs)
+                barrier()
+                R = 10
+                evr = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(R)]
+                for i in range(R):
+                    flush.zero_()
+                    evr[i][0].record(); agent.actor(obs); evr[i][1].record()
+                barrier()
+                t = torch.tensor([sum(s.elapsed_time(e) for s, e in evr)], device=dev, dtype=torch.float64)
+                if world > 1:
+                    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            sweep.append({"envs_per_gpu": E, "limb_tokens_per_gpu": E * N, "ms_per_forward": t.item() / R,
+                          "value": world * E * N * R / (t.item() * 1e-3), "unit": "limb-tokens/s (all GPUs)"})
+            del obs
+            torch.cuda.empty_cache()
+        line["rollout_sweep"] = sweep
 
     # ---- callers either side of the path, rank-local, wall clock through the public calls
     if not a.no_rollout:

@@ -353,9 +353,11 @@ class Agent(nn.Module):
         the reference would bucket it the same way).  world > 1: the backward records an event per stage
         (sgrl_set_backward_staged) and the NCCL all-reduce of a stage's gradient range runs on a communication stream while the
         backward of the stages below continues; only layer 0 + the embedding-side parameters are reduced after the backward.
-        SGRL_AR_BUCKETS=0: one flat all-reduce after the backward (round 1)."""
+        Off by default: measured on 2 and 8 B200s the staged form is ~1 % SLOWER than one flat all-reduce after the backward
+        (5.66 vs 5.60 ms per update at N = 8, profiles/r04n_*: eight small NCCL launches whose kernels compete with the backward for
+        SMs cost more than the 0.2 ms of exposed transfer they hide).  SGRL_AR_BUCKETS=1 enables it."""
         g = module.grad_arena()
-        if world <= 1 or os.environ.get("SGRL_AR_BUCKETS", "1") == "0" or not g.is_cuda:
+        if world <= 1 or os.environ.get("SGRL_AR_BUCKETS", "0") == "0" or not g.is_cuda:
             module.backward_raw(tb, stash, dout, nb, g, False, trusted_split=True, ws=ws)
             self._allreduce(g, world)
             return
