@@ -457,7 +457,7 @@ inline int net_forward(const NetCtx& c, const float* obs, long long zsObs, const
       GemmP g = lin(c, ua, 256, zS, lp[L_Q_W], lp[L_Q_B], c.SL(l, S_QKV), 768, zS, T, 768, 256);
       g.rowdiv = c.SL(l, S_F1); g.zsRow = zS; g.colscale = QSCALE; g.colscale_n = 256;
       SGRL_TRY(run_gemm(c, g));
-      SGRL_TRY(attention_fwd(c.SL(l, S_QKV), c.SL(l, S_VGP), c.S(T_GD), c.SL(l, S_O), c.SL(l, S_OG), c.SL(l, S_P), zS,
+      SGRL_TRY(attention_fwd(c.SL(l, S_QKV), c.SL(l, S_VGP), c.S(T_GD), c.SL(l, S_O), c.SL(l, S_OG), c.keep ? c.SL(l, S_P) : nullptr, zS,
                              l == 0 ? c.P(Y.gp[G_REL_W]) : nullptr, l == 0 ? c.P(Y.gp[G_REL_B]) : nullptr, c.zsP, c.gr, c.nb, st));
       if (ln_epi) {
         pr[0] = lin(c, c.SL(l, S_O), 256, zS, lp[L_NGO_W], lp[L_NGO_B], ub + 128, 256, zS, T, 128, 256);
@@ -530,7 +530,7 @@ inline int net_forward(const NetCtx& c, const float* obs, long long zsObs, const
     g.rowdiv = c.SL(l, S_F1); g.zsRow = zS; g.colscale = QSCALE; g.colscale_n = 256;
     SGRL_TRY(run_gemm(c, g));
     SGRL_TRY(side_join(c));
-    SGRL_TRY(attention_fwd(c.SL(l, S_QKV), c.SL(l, S_VGP), c.S(T_GD), c.SL(l, S_O), c.SL(l, S_OG), c.SL(l, S_P), zS,
+    SGRL_TRY(attention_fwd(c.SL(l, S_QKV), c.SL(l, S_VGP), c.S(T_GD), c.SL(l, S_O), c.SL(l, S_OG), c.keep ? c.SL(l, S_P) : nullptr, zS,
                            l == 0 ? c.P(Y.gp[G_REL_W]) : nullptr, l == 0 ? c.P(Y.gp[G_REL_B]) : nullptr, c.zsP, c.gr, c.nb, st));
     // branch: scalar stream h = LN1(h + ng_out(o)) while the vector stream continues on the main stream
     SGRL_TRY(side_fork(c, &sb, 0));
