@@ -214,6 +214,13 @@ int sgrl_polyak(float* target, const float* source, int64_t n, float tau,
  * waiting stream in eager execution).  No-op during stream capture or with SGRL_PDL=0. */
 int sgrl_stream_fence(sgrl_stream_t stream);
 
+/* Deterministic mode: enable = 1 / 0 switches it, -1 only queries; returns the previous state (default: environment
+ * variable SGRL_DETERMINISTIC, off).  While on, two runs of sgrl_set_backward / the TD3 glue kernels on the same inputs give
+ * BIT-IDENTICAL gradients, like the reference's CPU autograd (src/agent.py:151,171): weight-gradient GEMMs are not split
+ * over K, the small cross-CTA reductions sum in a fixed order and no work is forked to side streams (csrc/common.cuh).
+ * The mode is read when work is enqueued: captured CUDA graphs keep the mode they were captured in. */
+int sgrl_deterministic(int enable);
+
 /* ---- K7: device-resident replay storage (common/buffer.py:35-126) --------
  * One transition = one packed row [obs (obs_dim) | action (act_dim) | next_obs (obs_dim) | reward | done] of
  * row_floats = 2*obs_dim + act_dim + 2 floats; `rows` holds `capacity` of them in HBM.

@@ -132,6 +132,11 @@ class _UpdatePlan:
         self.ws = f(max(cr.ws_floats(T, 2), ac.ws_floats(T, 1)))
         self.s1, self.s2, self.s3, self.s_cap = agent._streams(dev)
         self.ev_start, self.ev_a, self.ev_b, self.ev_c = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
+        # SGRL_TWIN_SPLIT (bit 0: target critics, bit 1: critic forward, bit 2: critic backward): run the twin critics as two
+        # one-net chains on two streams instead of one nb = 2 chain (decided per plan: the captured graphs bake it in)
+        self.twin = int(os.environ.get("SGRL_TWIN_SPLIT", "0"))
+        self.s4, self.s5 = agent._twin_streams(dev)
+        self.ev_a0, self.ev_a4, self.ev_b5, self.ev_l = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
         # the fused Adam / Polyak passes of this plan also rewrite the tf32 split (decided once per plan: the captured graphs
         # bake the pointers in).  Plans too small for the tcgen05 path leave the split stale; _run_update then marks it so.
         self.keep_split = all(m.use_tc and T >= m.SPLIT_MIN_TOKENS for m in (agent.actor, agent.critic, agent.actor_target, agent.critic_target))
@@ -339,6 +344,13 @@ class Agent(nn.Module):
             self._stream_set = st
         return st[1:]
 
+    def _twin_streams(self, dev):
+        st = getattr(self, "_twin_stream_set", None)
+        if st is None or st[0] != dev:
+            st = (dev, torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev))
+            self._twin_stream_set = st
+        return st[1:]
+
     def _allreduce(self, g: torch.Tensor, world: int):
         if world > 1:
             import torch.distributed as dist
@@ -487,6 +499,7 @@ class Agent(nn.Module):
         tb, T, st = p.tb, p.tb.T, stream()
         world = self._world()
         main = torch.cuda.current_stream()
+        twin = p.twin
         p.scal.zero_()
         p.ev_start.record(main)
         # ---- chain A (stream s1): y = r + (1-d) * gamma * min_i Q_i'(s', clip(pi'(s') + clip(eps)))        agent.py:127-139
@@ -500,7 +513,18 @@ class Agent(nn.Module):
             else:
                 check(lib.sgrl_td3_smooth_action(ptr(p.a_t), ptr(p.noise), ptr(p.next_action), float(a.noise_clip), float(a.max_action), T * 3,
                                                  stream()))
-            self.critic_target.forward_raw(tb, p.nobs, p.next_action, keep=False, nb=2, trusted_split=True, out=p.tq, stash=p.stash_ct)
+            if twin & 1:      # the twin target critics as two one-net chains (s1, s4) instead of one nb = 2 chain
+                check(lib.sgrl_stream_fence(stream()))
+                p.ev_a0.record(p.s1)
+                with torch.cuda.stream(p.s4):
+                    p.s4.wait_event(p.ev_a0)
+                    self.critic_target.forward_raw(tb, p.nobs, p.next_action, keep=False, nb=2, trusted_split=True, out=p.tq, stash=p.stash_ct, z=1)
+                    check(lib.sgrl_stream_fence(stream()))
+                    p.ev_a4.record(p.s4)
+                self.critic_target.forward_raw(tb, p.nobs, p.next_action, keep=False, nb=2, trusted_split=True, out=p.tq, stash=p.stash_ct, z=0)
+                p.s1.wait_event(p.ev_a4)
+            else:
+                self.critic_target.forward_raw(tb, p.nobs, p.next_action, keep=False, nb=2, trusted_split=True, out=p.tq, stash=p.stash_ct)
             check(lib.sgrl_stream_fence(stream()))       # eager runs only (no-op under capture): see csrc/net.cuh stream_fence
             p.ev_a.record(p.s1)
         # ---- chain C (stream s2, delayed actor step only): pi(s) — independent of the critic step           agent.py:167
@@ -511,18 +535,40 @@ class Agent(nn.Module):
                 check(lib.sgrl_stream_fence(stream()))
                 p.ev_c.record(p.s2)
         # ---- chain B (stream s3, then main): critic step                                                    agent.py:142-156
+        if twin & 2:
+            with torch.cuda.stream(p.s5):
+                p.s5.wait_event(p.ev_start)
+                self.critic.forward_raw(tb, p.obs, p.act, keep=True, nb=2, trusted_split=True, out=p.q, stash=p.stash_c, z=1)
+                check(lib.sgrl_stream_fence(stream()))
+                p.ev_b5.record(p.s5)
         with torch.cuda.stream(p.s3):
             p.s3.wait_event(p.ev_start)
-            self.critic.forward_raw(tb, p.obs, p.act, keep=True, nb=2, trusted_split=True, out=p.q, stash=p.stash_c)
+            self.critic.forward_raw(tb, p.obs, p.act, keep=True, nb=2, trusted_split=True, out=p.q, stash=p.stash_c, z=0 if twin & 2 else None)
             check(lib.sgrl_stream_fence(stream()))
             p.ev_b.record(p.s3)
         main.wait_event(p.ev_b)
+        if twin & 2:
+            main.wait_event(p.ev_b5)
         main.wait_event(p.ev_a)
         check(lib.sgrl_td3_critic_loss(ptr(p.q[0]), ptr(p.q[1]), ptr(p.tq[0]), ptr(p.tq[1]), ptr(p.rew), ptr(p.done), ptr(tb.tok_graph),
                                        ptr(tb.tok_weight), ptr(p.target), ptr(p.dq[0]), ptr(p.dq[1]), ptr(p.scal), float(a.discount), float(self.reward_scale), T,
                                        ptr(p.rstats), tb.G, st))
         self.critic_optimizer.zero_grad()
-        self._backward_allreduce(self.critic, tb, p.stash_c, p.dq, 2, p.ws, world)
+        if twin & 4 and not (world > 1 and os.environ.get("SGRL_AR_BUCKETS", "0") != "0"):
+            # the twin critics' backward passes as two one-net chains (main, s5); their gradient ranges, stashes and workspaces are disjoint
+            g = self.critic.grad_arena()
+            check(lib.sgrl_stream_fence(stream()))
+            p.ev_l.record(main)
+            with torch.cuda.stream(p.s5):
+                p.s5.wait_event(p.ev_l)
+                self.critic.backward_raw(tb, p.stash_c, p.dq, 2, g, False, trusted_split=True, ws=p.ws, z=1)
+                check(lib.sgrl_stream_fence(stream()))
+                p.ev_b5.record(p.s5)
+            self.critic.backward_raw(tb, p.stash_c, p.dq, 2, g, False, trusted_split=True, ws=p.ws, z=0)
+            main.wait_event(p.ev_b5)
+            self._allreduce(g, world)
+        else:
+            self._backward_allreduce(self.critic, tb, p.stash_c, p.dq, 2, p.ws, world)
         self.critic_optimizer.step(max_norm=float(a.grad_clipping_value), world_size=world, keep_split=p.keep_split)
         # ---- delayed actor step + Polyak                                                                    agent.py:165-180
         if actor_step:

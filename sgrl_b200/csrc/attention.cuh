@@ -328,7 +328,7 @@ __global__ void __launch_bounds__(A_FWD_THREADS, ATTN_MINB) attention_fwd_v2_ker
 constexpr size_t attn_fwd_v2_smem(int nr = MAXN) { return sizeof(float) * (nr * A_QS + 1024); }
 
 constexpr size_t attn_fwd_smem(int nr = MAXN) { return sizeof(float) * (2 * nr * A_RS + 1024); }
-constexpr size_t attn_bwd_smem(int nr = MAXN) { return sizeof(float) * (2 * nr * A_RS + nr * A_DS + 1536 + 16); }
+constexpr size_t attn_bwd_smem(int nr = MAXN) { return sizeof(float) * (2 * nr * A_RS + nr * A_DS + 1536 + 64); }
 
 // Backward.  Inputs dO (T,256), dOG (T,768) [workspace], saved P, QKV, VGP, GD [stash].
 // Outputs dQKV (T,768) — gradient w.r.t. the *stored* (post /F, post-scale) q|k|v — and
@@ -336,7 +336,7 @@ constexpr size_t attn_bwd_smem(int nr = MAXN) { return sizeof(float) * (2 * nr *
 __global__ void __launch_bounds__(A_BWD_THREADS) attention_bwd_kernel(
     const float* __restrict__ QKV, const float* __restrict__ VGP, const float* __restrict__ GD, const float* __restrict__ P, long long zsS,
     const float* __restrict__ dO, const float* __restrict__ dOG, float* __restrict__ dQKV, float* __restrict__ dVGP, long long zsW,
-    float* __restrict__ dWrel, long long zsG, AttnGraphs gr) {
+    float* __restrict__ dWrel, long long zsG, AttnGraphs gr, float* __restrict__ wpart) {
   SGRL_PDL_ENTER();
   extern __shared__ __align__(16) float smem[];
   const int nr = (gr.nmax >= 2 && gr.nmax <= MAXN) ? gr.nmax : MAXN;
@@ -346,7 +346,7 @@ __global__ void __launch_bounds__(A_BWD_THREADS) attention_bwd_kernel(
   float* Ps = ds + nr * A_DS;            // [2][16][16]
   float* dS = Ps + 512;                  // [2][16][16]
   float* dST = dS + 512;                 // [2][16][16]  transposed: [h][j][i]
-  float* wacc = dST + 512;               // [6]
+  float* wacc = dST + 512;               // [8 warps][6]
   const int tid = threadIdx.x, z = blockIdx.y;
   QKV += z * zsS; VGP += z * zsS; GD += z * zsS; P += z * zsS;
   dO += z * zsW; dOG += z * zsW; dQKV += z * zsW; dVGP += z * zsW;
@@ -468,15 +468,21 @@ __global__ void __launch_bounds__(A_BWD_THREADS) attention_bwd_kernel(
     }
   }
   if (has_bias) {
-    if (tid < 6) wacc[tid] = 0.f;
-    __syncthreads();
+    // per-warp sums added in warp order (a fixed order: the CTA's contribution does not depend on timing)
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
       const float s = warp_sum(wloc[k]);
-      if ((tid & 31) == 0) atomicAdd(&wacc[k], s);
+      if ((tid & 31) == 0) wacc[(tid >> 5) * 6 + k] = s;
     }
     __syncthreads();
-    if (tid < 6) atomicAdd(dWrel + tid, wacc[tid]);
+    if (tid < 6) {
+      float s = 0.f;
+#pragma unroll
+      for (int w = 0; w < A_BWD_THREADS / 32; ++w) s += wacc[w * 6 + tid];
+      // deterministic mode: the CTA's partial goes to a scratch row, rel_wgrad_reduce_kernel adds the rows in index order
+      if (wpart) wpart[(long long)z * zsW + (long long)blockIdx.x * 6 + tid] = s;
+      else atomicAdd(dWrel + tid, s);
+    }
   }
 }
 
@@ -517,9 +523,21 @@ inline int attention_fwd(const float* QKV, const float* VGP, const float* GD, fl
   return 0;
 }
 
+// d rel_encoder.weight += sum over the CTAs' partial rows, in index order (deterministic mode)
+__global__ void __launch_bounds__(32) rel_wgrad_reduce_kernel(const float* __restrict__ wpart, long long zsW, int nparts, float* __restrict__ dWrel, long long zsG) {
+  SGRL_PDL_ENTER();
+  const int z = blockIdx.y;
+  if (threadIdx.x < 6) {
+    float s = 0.f;
+    for (int b = 0; b < nparts; ++b) s += wpart[(long long)z * zsW + (long long)b * 6 + threadIdx.x];
+    dWrel[(long long)z * zsG + threadIdx.x] += s;
+  }
+}
+
+// scratch (deterministic mode, layer 0 only): >= 6 * min(G, 4 * NUM_SMS) floats per net instance, z-stride zsW; nullptr otherwise
 inline int attention_bwd(const float* QKV, const float* VGP, const float* GD, const float* P, long long zsS,
                          const float* dO, const float* dOG, float* dQKV, float* dVGP, long long zsW,
-                         float* dWrel, long long zsG, const AttnGraphs& gr, int nb, cudaStream_t st) {
+                         float* dWrel, long long zsG, const AttnGraphs& gr, int nb, cudaStream_t st, float* scratch = nullptr) {
   if (gr.G <= 0) return 0;
   static bool attr_done = false;
   if (!attr_done) {
@@ -528,9 +546,15 @@ inline int attention_bwd(const float* QKV, const float* VGP, const float* GD, co
   }
   const int nr = attn_rows(gr);
   const int per_sm = (int)((227 * 1024) / (attn_bwd_smem(nr) + 1024)) < 4 ? (int)((227 * 1024) / (attn_bwd_smem(nr) + 1024)) : 4;
-  const int gx = gr.G < per_sm * NUM_SMS ? gr.G : per_sm * NUM_SMS;
-  launch_k(attention_bwd_kernel, dim3(gx, nb), A_BWD_THREADS, attn_bwd_smem(nr), st, QKV, VGP, GD, P, zsS, dO, dOG, dQKV, dVGP, zsW, dWrel, zsG, gr);
+  int gx = gr.G < per_sm * NUM_SMS ? gr.G : per_sm * NUM_SMS;
+  float* wpart = (dWrel && det_enabled()) ? scratch : nullptr;
+  if (dWrel && det_enabled() && !scratch) gx = 1;      // no scratch (stand-alone call): one CTA walks every graph, one add per address
+  launch_k(attention_bwd_kernel, dim3(gx, nb), A_BWD_THREADS, attn_bwd_smem(nr), st, QKV, VGP, GD, P, zsS, dO, dOG, dQKV, dVGP, zsW, dWrel, zsG, gr, wpart);
   SGRL_LAUNCH_OK();
+  if (wpart) {
+    launch_k(rel_wgrad_reduce_kernel, dim3(1, nb), 32, 0, st, (const float*)wpart, zsW, gx, dWrel, zsG);
+    SGRL_LAUNCH_OK();
+  }
   return 0;
 }
 

@@ -32,6 +32,18 @@ inline bool pdl_enabled() {
   if (g_pdl < 0) { const char* e = getenv("SGRL_PDL"); g_pdl = e ? atoi(e) : 1; }
   return g_pdl != 0;
 }
+// ---- deterministic mode (SGRL_DETERMINISTIC=1 or sgrl_deterministic(1)): run-to-run bit-identical gradients.  The default
+// backward sums in an order that depends on timing in three places: split-K weight-gradient GEMMs (fp32 atomics), small
+// cross-CTA reductions (LayerNorm / positional / decoder / relative-bias weight gradients, the loss scalars) and the dF
+// accumulators that kernels of concurrent lanes add into.  Deterministic mode removes all three: no split-K (and no cluster
+// split-K), one CTA (or per-CTA partials summed in index order) for the small reductions, and no side lanes, so every
+// address is added to in program order.  Slower (the weight-gradient GEMMs lose their parallelism over K); the forward was
+// deterministic already (tools/determinism_probe.py).
+extern int g_det;
+inline bool det_enabled() {
+  if (g_det < 0) { const char* e = getenv("SGRL_DETERMINISTIC"); g_det = e ? (atoi(e) != 0) : 0; }
+  return g_det != 0;
+}
 #define SGRL_PDL_TRIGGER() asm volatile("griddepcontrol.launch_dependents;" ::: "memory")
 #define SGRL_PDL_WAIT() asm volatile("griddepcontrol.wait;" ::: "memory")
 #define SGRL_PDL_ENTER() do { SGRL_PDL_TRIGGER(); SGRL_PDL_WAIT(); } while (0)

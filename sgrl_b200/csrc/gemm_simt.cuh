@@ -296,6 +296,7 @@ inline int gemm_simt(const GemmP& p_in, cudaStream_t st) {
 
 // choose a split-K factor for token-contraction GEMMs (dW): fill ~2 waves of the SMs
 inline int pick_splitk(int M, int N, int K, int nb) {
+  if (det_enabled()) return 1;          // deterministic mode: no fp32 atomics over K
   const int tiles = ceil_div(M, GB_M) * ceil_div(N, GB_N) * nb;
   const int ktiles = ceil_div(K, GB_K);
   int s = (2 * NUM_SMS + tiles - 1) / tiles;

@@ -128,6 +128,8 @@ struct Side {
   }
 };
 extern Side g_side;
+// no forks: side streams switched off, the bench's per-class timing pass, or deterministic mode (program order on one stream)
+inline bool side_off(const Side& sd) { return !sd.enabled || g_prof.on || det_enabled(); }
 
 struct NetCtx {
   int kind, L, nb, T;
@@ -167,6 +169,7 @@ inline int run_gemm(const NetCtx& c, const GemmP& g, cudaStream_t st = nullptr) 
   if (g.rowsum) {      // the SIMT kernel has no fused row sum: rowsum[m] += alpha * sum_k A(m,k) as a column sum of dY (A = dY^T)
     SGRL_CHECK(g.transA, "rowsum: only for weight-gradient GEMMs (A = dY^T)");
     int gy = ceil_div(g.K, 64); if (gy > 32) gy = 32; if (gy < 1) gy = 1;
+    if (det_enabled()) gy = 1;
     launch_k(colsum_kernel, dim3(ceil_div(g.M, 32), gy, g.nb), 256, 0, st, g.A, g.lda, g.zsA, g.rowsum, g.zsRowsum, g.K, g.M, g.alpha);
     SGRL_LAUNCH_OK();
   }
@@ -193,7 +196,7 @@ inline int run_group(const NetCtx& c, const GemmP* gs, int n, cudaStream_t st = 
 // `from`: the stream whose work so far the forked stream must wait for (default: the main stream)
 inline int side_fork(const NetCtx& c, cudaStream_t* out, int lane = -1, cudaStream_t from = nullptr) {
   Side& sd = g_side;
-  if (!sd.enabled || g_prof.on) { *out = c.stream; return 0; }
+  if (side_off(sd)) { *out = c.stream; return 0; }
   SideSet& ss = sd.of(c.stream);
   int i = lane;
   if (i < 0) { i = 1 + ss.rr; ss.rr = (ss.rr + 1) % (SideSet::N - 1); }
@@ -209,7 +212,7 @@ inline int side_fork(const NetCtx& c, cudaStream_t* out, int lane = -1, cudaStre
 // lane < 0: every lane; else only that lane
 inline int side_join(const NetCtx& c, int lane = -1) {
   Side& sd = g_side;
-  if (!sd.enabled || g_prof.on) return 0;
+  if (side_off(sd)) return 0;
   SideSet& ss = sd.of(c.stream);
   for (int i = 0; i < SideSet::N; ++i) {
     if (!ss.used[i] || (lane >= 0 && i != lane)) continue;
@@ -295,6 +298,7 @@ inline int fold_weights(const NetCtx& c, cudaStream_t st) {
 
 inline int colsum(const NetCtx& c, const float* X, int ldx, long long g_off, int M, int N, float alpha, cudaStream_t st) {
   int gy = ceil_div(M, 64); if (gy > 32) gy = 32; if (gy < 1) gy = 1;
+  if (det_enabled()) gy = 1;
   launch_k(colsum_kernel, dim3(ceil_div(N, 32), gy, c.nb), 256, 0, st, X, ldx, c.zsW, c.Gr(g_off), c.zsG, M, N, alpha);
   SGRL_LAUNCH_OK();
   return 0;
@@ -320,6 +324,7 @@ inline int layernorm_bwd(const NetCtx& c, const float* dy1, int ld1, const float
                          const float* stats, long long g_off, long long b_off, float* dx, int lddx, bool wg, cudaStream_t st = nullptr) {
   if (!st) st = c.stream;
   int gx = grid_for_warps(c.T); if (gx > 2 * NUM_SMS) gx = 2 * NUM_SMS;
+  if (wg && det_enabled()) gx = 1;      // dgamma / dbeta: one add per address
   const int vf = host_vec_ok(dy1, ld1, c.zsW) | (host_vec_ok(dy2, ld2, c.zsW) << 1) | (host_vec_ok(x, ldx, c.zsS) << 2) | (host_vec_ok(dx, lddx, c.zsW) << 3);
   launch_k(layernorm_bwd_kernel, dim3(gx, c.nb), 256, 0, st, dy1, ld1, dy2, ld2, x, ldx, stats, c.zsS, c.P(g_off), c.zsP, dx, lddx, c.zsW,
                                                              wg ? c.Gr(g_off) : nullptr, wg ? c.Gr(b_off) : nullptr, c.zsG, c.T, vf);
@@ -368,7 +373,7 @@ inline int unfold_grads(const NetCtx& c, const FoldDesc& d, cudaStream_t st) {
 // (sgrl_stream_wait_stage) may all-reduce the stage's gradient range while the backward of the stages below runs.
 inline int stage_mark(const NetCtx& c, int stage) {
   Side& sd = g_side;
-  if (!sd.enabled || g_prof.on) {          // no side streams: everything is on the main stream
+  if (side_off(sd)) {          // no side streams: everything is on the main stream
     SGRL_TRY(unfold_grads(c, fold_desc_stage(c, stage), c.stream));
     SideSet& ss0 = sd.of(c.stream);
     SGRL_TRY(stream_fence(c.stream));
@@ -659,7 +664,7 @@ inline int net_backward(const NetCtx& c_in, const float* dOut, long long zsDo, i
     g = dgrad(c, W(W_DQ), 1, Y.gp[G_DNG_W], 256, W(W_DUH), 256, T, 1, 256);
     SGRL_TRY(run_gemm(c, g));
   } else {
-    launch_k(actor_out_bwd_kernel, dim3(grid_for_warps(T) > 2 * NUM_SMS ? 2 * NUM_SMS : grid_for_warps(T), c.nb), 256, 0, st, dOut, zsDo, c.S(T_OUT),
+    launch_k(actor_out_bwd_kernel, dim3((wg && det_enabled()) ? 1 : grid_for_warps(T) > 2 * NUM_SMS ? 2 * NUM_SMS : grid_for_warps(T), c.nb), 256, 0, st, dOut, zsDo, c.S(T_OUT),
              c.S(T_RH), c.S(T_V0), zS, c.P(Y.gp[G_DG_W]), c.zsP, W(W_DR), zW, wg ? c.Gr(Y.gp[G_DG_W]) : W(W_DQ) /*discarded*/, wg ? c.zsG : zW,
              c.max_action, T);
     SGRL_LAUNCH_OK();
@@ -777,7 +782,8 @@ inline int net_backward(const NetCtx& c_in, const float* dOut, long long zsDo, i
     SGRL_TRY(run_gemm(c, g));
     SGRL_TRY(side_join(c, 0));
     SGRL_TRY(attention_bwd(c.SL(l, S_QKV), c.SL(l, S_VGP), c.S(T_GD), c.SL(l, S_P), zS, W(W_DO), W(W_DOG), W(W_DQKV), W(W_DVGP), zW,
-                           (l == 0 && wg) ? c.Gr(Y.gp[G_REL_W]) : nullptr, c.zsG, c.gr, c.nb, st));
+                           (l == 0 && wg) ? c.Gr(Y.gp[G_REL_W]) : nullptr, c.zsG, c.gr, c.nb, st,
+                           W(W_DG) /* deterministic mode's partial-sum scratch: free between the two vec(G) halves of the stage */));
     // ---- branch (sb): vg = vg_proj(Vg): dVg(in) = dVg' + dvg vg_proj   (out of place: this frame's dVg)
     SGRL_TRY(side_w(W(W_DVGP), 252, Vg, 128, zS, lp[L_VG_W], 128, T3, 252, 128));
     SGRL_TRY(side_fork(c, &sb, 0));
@@ -812,6 +818,7 @@ inline int net_backward(const NetCtx& c_in, const float* dOut, long long zsDo, i
     SGRL_TRY(side_w(W(W_DVG), 128, c.S(T_V0), 8, zS, Y.gp[G_GENC_W], GN, T3, 128, GN, -1, SQRT_D));
     SGRL_TRY(side_w(W(W_DH), 128, c.S(T_SH), KS, zS, Y.gp[G_ENC_W], ng, T, 128, ng, Y.gp[G_ENC_B], SQRT_D));
     int gx = ceil_div(T, 64); if (gx > NUM_SMS) gx = NUM_SMS; if (gx < 1) gx = 1;
+    if (det_enabled()) gx = 1;
     launch_k(pos_embed_bwd_kernel, dim3(gx, c.nb), 128, 0, st, W(W_DH), 128, zW, c.rank3, c.Gr(Y.gp[G_POS0]), c.Gr(Y.gp[G_POS1]), c.Gr(Y.gp[G_POS2]), c.zsG, T);
     SGRL_LAUNCH_OK();
   }
@@ -825,7 +832,7 @@ inline int net_backward(const NetCtx& c_in, const float* dOut, long long zsDo, i
   if (wg) {      // gradients of the folded weights -> (rows,1024) gradient tensors (staged: only layer 0 is left)
     SGRL_TRY(unfold_grads(c, staged ? fold_desc_stage(c, 0) : fold_desc(c), st));
   }
-  if (staged && g_side.enabled && !g_prof.on) {      // the mark stream rejoins the main stream (capture: every forked stream must)
+  if (staged && !side_off(g_side)) {      // the mark stream rejoins the main stream (capture: every forked stream must)
     SideSet& ss = g_side.of(c.stream);
     if (ss.marked) {
       if (g_side.fork_fence) SGRL_TRY(stream_fence(ss.s_mark));

@@ -11,6 +11,7 @@ long long g_launches = 0;
 Prof g_prof;
 long long* g_gemm_trace = nullptr;
 int g_pdl = -1;
+int g_det = -1;
 cudaStream_t g_nopdl_streams[32];
 int g_nopdl_count = 0;
 Side g_side;
@@ -195,7 +196,7 @@ int sgrl_gemm(const float* A, int lda, int trans_a, const float* B, int ldb, int
   GemmP g = gemm_defaults();
   g.A = A; g.lda = lda; g.transA = trans_a; g.B = B; g.ldb = ldb; g.transB = trans_b; g.C = C; g.ldc = ldc;
   g.M = M; g.N = N; g.K = K; g.alpha = alpha; g.bias = bias; g.rowdiv = rowdiv; g.relu = relu; g.accumulate = accumulate;
-  g.splitk = splitk < 1 ? 1 : splitk;
+  g.splitk = (splitk < 1 || det_enabled()) ? 1 : splitk;
   if (use_tc) {
     SGRL_CHECK(gemm_tc_eligible(g), "shape/epilogue not eligible for the tcgen05 path");
     g.prec = use_tc == 2 ? 1 : 0;
@@ -211,7 +212,7 @@ int sgrl_gemm_presplit(const float* A, int lda, int trans_a, const float* B_hi, 
   GemmP g = gemm_defaults();
   g.A = A; g.lda = lda; g.transA = trans_a; g.B = B_hi; g.Bhi = B_hi; g.Blo = B_lo; g.ldb = ldb; g.transB = trans_b; g.C = C; g.ldc = ldc;
   g.M = M; g.N = N; g.K = K; g.alpha = alpha; g.bias = bias; g.rowdiv = rowdiv; g.relu = relu; g.accumulate = accumulate;
-  g.splitk = splitk < 1 ? 1 : splitk;
+  g.splitk = (splitk < 1 || det_enabled()) ? 1 : splitk;
   SGRL_CHECK(gemm_tc_eligible(g), "shape/epilogue not eligible for the tcgen05 path");
   return gemm_tc(g, ST(stream));
 }
@@ -288,6 +289,7 @@ int sgrl_td3_critic_loss(const float* q1, const float* q2, const float* tq1, con
                          float reward_scale, int T, double* reward_stats, int G, sgrl_stream_t stream) {
   SGRL_CHECK(q1 && q2 && tq1 && tq2 && reward && done && tok_graph && target && dq1 && dq2 && loss, "null pointer");
   int gx = ceil_div(T, 256); if (gx > NUM_SMS) gx = NUM_SMS;
+  if (det_enabled()) gx = 1;      // the loss scalar: one add
   launch_k(td3_critic_loss_kernel, gx, 256, 0, ST(stream), q1, q2, tq1, tq2, reward, done, tok_graph, tok_weight, target, dq1, dq2, loss, discount, reward_scale, T, reward_stats, G);
   SGRL_LAUNCH_OK();
   return 0;
@@ -296,6 +298,7 @@ int sgrl_td3_critic_loss(const float* q1, const float* q2, const float* tq1, con
 int sgrl_td3_actor_loss(const float* q1, const float* tok_weight, float* dq1, float* loss, int T, sgrl_stream_t stream) {
   SGRL_CHECK(q1 && dq1 && loss, "null pointer");
   int gx = ceil_div(T, 256); if (gx > NUM_SMS) gx = NUM_SMS;
+  if (det_enabled()) gx = 1;      // the loss scalar: one add
   launch_k(td3_actor_loss_kernel, gx, 256, 0, ST(stream), q1, tok_weight, dq1, loss, T);
   SGRL_LAUNCH_OK();
   return 0;
@@ -365,6 +368,12 @@ int sgrl_polyak(float* target, const float* source, int64_t n, float tau, float*
 }
 
 int sgrl_stream_fence(sgrl_stream_t stream) { return stream_fence(ST(stream)); }
+
+int sgrl_deterministic(int enable) {
+  const int prev = det_enabled() ? 1 : 0;
+  if (enable >= 0) g_det = enable ? 1 : 0;
+  return prev;
+}
 
 int sgrl_replay_gather(const float* rows, int64_t row_floats, int64_t capacity, const int64_t* idx, int batch, int obs_dim, int act_dim,
                        float* obs, float* action, float* next_obs, float* reward, float* done, sgrl_stream_t stream) {
