@@ -156,12 +156,19 @@ struct NetCtx {
   int ks() const { return D + ng(); }
 };
 
+// latency regime: so few token rows that every projection is at most one tile per SM; the GEMMs then use the shallow operand ring
+// (gemm_tc.cuh TcCfg SHAL) so that other streams' kernels fit next to them.  SGRL_TC_SHALLOW_MAXT: most token rows x nets.
+inline int shallow_regime(const NetCtx& c) {
+  static const long long maxt = getenv("SGRL_TC_SHALLOW_MAXT") ? atoll(getenv("SGRL_TC_SHALLOW_MAXT")) : 6144;
+  return (long long)c.T * c.nb <= maxt ? 1 : 0;
+}
 inline int run_gemm(const NetCtx& c, const GemmP& g, cudaStream_t st = nullptr) {
   if (!st) st = c.stream;
   if (c.use_tc && gemm_tc_eligible(g)) {
     GemmP gi = g;
     gi.sm2_ok = c.keep ? 0 : 1;
     gi.lat = (!c.keep || c.bwd) ? 1 : 0;
+    gi.shal = shallow_regime(c);
     gi.prec = c.use_tc == 2 ? 1 : 0;      // use_tc 2: BF16-input mode (reported separately, never the default)
     return gemm_tc(gi, st);
   }
@@ -185,7 +192,7 @@ inline int run_group(const NetCtx& c, const GemmP* gs, int n, cudaStream_t st = 
   for (int i = 0; i < n && all_tc; ++i) all_tc = gemm_tc_eligible(gs[i]);
   if (all_tc) {
     GemmP gp[TC_MAXG];
-    for (int i = 0; i < n; ++i) { gp[i] = gs[i]; gp[i].prec = c.use_tc == 2 ? 1 : 0; gp[i].lat = (!c.keep || c.bwd) ? 1 : 0; }
+    for (int i = 0; i < n; ++i) { gp[i] = gs[i]; gp[i].prec = c.use_tc == 2 ? 1 : 0; gp[i].lat = (!c.keep || c.bwd) ? 1 : 0; gp[i].shal = shallow_regime(c); }
     return gemm_tc_group(gp, n, st);
   }
   for (int i = 0; i < n; ++i) SGRL_TRY(run_gemm(c, gs[i], st));
