@@ -56,7 +56,8 @@ __constant__ int c_pdl_hold;
 // B=256 update (profiles/r05c..e_pdl_late.txt): 5.36 / 5.11 / 5.15 / 5.13 ms.
 inline int pdl_late_mode() { static const int m = getenv("SGRL_PDL_LATE") ? atoi(getenv("SGRL_PDL_LATE")) : 1; return m; }
 inline void pdl_init_once() {
-  static const bool once = [] { const int v = pdl_late_mode() >= 2 ? 1 : 0; cudaMemcpyToSymbol(c_pdl_hold, &v, sizeof(v)); return true; }();
+  // zero-initialised: nothing to copy (and nothing that could disturb a stream capture) unless the experiment mode is on
+  static const bool once = [] { if (pdl_late_mode() >= 2) { const int v = 1; cudaMemcpyToSymbol(c_pdl_hold, &v, sizeof(v)); } return true; }();
   (void)once;
 }
 // streams on which kernels are launched WITHOUT the programmatic attribute (experiment knob SGRL_PDL_SIDE=0: the side lanes)
