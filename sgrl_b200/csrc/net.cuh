@@ -419,6 +419,14 @@ inline int net_forward(const NetCtx& c, const float* obs, long long zsObs, const
   SGRL_CHECK(c.kind == ACTOR || act != nullptr, "critic forward needs actions");
   SGRL_TRY(g_side.init());
   cudaStream_t sb;                 // side stream of the independent branch of the moment (== st when side streams are off)
+  // fused schedule: needs the pre-split weights (tcgen05 path) and enough rows for the N = 32 projections to be worth a tile
+  static const int fused_env = getenv("SGRL_FUSED") ? atoi(getenv("SGRL_FUSED")) : 1;
+  const bool fused = fused_env && c.use_tc && c.phi != nullptr && (long long)T3 * 32 * 128 >= (1 << 21);
+  // triangle-folded vec(G) consumers of every layer: on the branch lane next to the embedding and the first projection, joined
+  // before the first Gram-generating GEMM reads them (SGRL_FOLD_SIDE=0: on the main chain)
+  static const int fold_side = getenv("SGRL_FOLD_SIDE") ? atoi(getenv("SGRL_FOLD_SIDE")) : 1;
+  bool fold_pending = false;
+  if (fused && fold_side) { SGRL_TRY(side_fork(c, &sb, 0)); SGRL_TRY(fold_weights(c, sb)); fold_pending = true; }
   {
     int gx = ceil_div(T, E_TOK); if (gx > 4 * NUM_SMS) gx = 4 * NUM_SMS;
     launch_k(embed_fwd_kernel, dim3(gx, c.nb), 128, 0, st, obs, zsObs, c.kind == CRITIC ? act : nullptr, zsAct, c.rank3,
@@ -426,10 +434,7 @@ inline int net_forward(const NetCtx& c, const float* obs, long long zsObs, const
         c.S(T_V0), c.S(T_GD), c.S(T_SH), KS, c.SL(0, S_VGIN), c.SL(0, S_UA) + 128, 256, zS, T, ng);
     SGRL_LAUNCH_OK();
   }
-  // fused schedule: needs the pre-split weights (tcgen05 path) and enough rows for the N = 32 projections to be worth a tile
-  static const int fused_env = getenv("SGRL_FUSED") ? atoi(getenv("SGRL_FUSED")) : 1;
-  const bool fused = fused_env && c.use_tc && c.phi != nullptr && (long long)T3 * 32 * 128 >= (1 << 21);
-  if (fused) SGRL_TRY(fold_weights(c, st));        // triangle-folded vec(G) consumers of every layer
+  if (fused && !fold_pending) SGRL_TRY(fold_weights(c, st));
   // residual + LayerNorm inside the N = 128 GEMMs' epilogue (gemm_tc.cuh) — measured slower than GEMM + layernorm kernel on
   // the branch lane at 2 304 tokens (23.2 vs 11.0 + 3.5 us, tools/fused_bench.py), so off by default
   static const int ln_epi = getenv("SGRL_LN_EPI") ? atoi(getenv("SGRL_LN_EPI")) : 0;
@@ -459,6 +464,7 @@ inline int net_forward(const NetCtx& c, const float* obs, long long zsObs, const
       GemmP gz = lin(c, Vg, 128, zS, lp[L_GPROJ], -1, c.SL(l, S_Z1), 32, zS, T3, 32, 128);
       gz.gdcols = c.S(T_GD); gz.zsGd = zS;
       SGRL_TRY(run_gemm(c, gz));
+      if (fold_pending) { SGRL_TRY(side_join(c, 0)); fold_pending = false; }
       GemmP g1 = lin_fold(c, nullptr, fold_offset(c.L, l, 0), lp[L_G1_B], c.SL(l, S_A1), 256, T, 256); g1.relu = 1;
       g1.gramZ = c.SL(l, S_Z1); g1.zsGramZ = zS; g1.gramF = c.SL(l, S_F1); g1.gramG = c.keep ? c.SL(l, S_G1) : nullptr;
       SGRL_TRY(run_gemm(c, g1));
