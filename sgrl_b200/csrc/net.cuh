@@ -590,15 +590,21 @@ inline int net_forward(const NetCtx& c, const float* obs, long long zsObs, const
   FeatFwdP fh{}; fh.head = 1; fh.Xg = c.S(T_VGF); fh.zsXg = zS; fh.V0 = c.S(T_V0); fh.zsV0 = zS; fh.gd = c.S(T_GD); fh.zsGd = zS;
   fh.P1 = c.P(Y.gp[G_GG_W]); fh.P2 = c.kind == ACTOR ? c.P(Y.gp[G_GPH_W]) : nullptr; fh.zsP = c.zsP;
   fh.Z = c.S(T_ZH); fh.Z2 = c.kind == ACTOR ? c.S(T_ZH2) : nullptr; fh.G = c.S(T_GH); fh.Fn = c.S(T_FH); fh.zsAct = zS; fh.T = T; fh.nb = c.nb;
+  // the scalar branch u[:, 128:] = linear2_ng(relu(linear1_ng([s0 | h]))) only needs the final norm: on the branch lane, next to
+  // the invariant branch K1 -> linear1_g -> linear2_g (3 instead of 5 dependent launches; SGRL_HEAD_SIDE=0: one after the other)
+  static const int head_side = getenv("SGRL_HEAD_SIDE") ? atoi(getenv("SGRL_HEAD_SIDE")) : 1;
+  sb = st;
+  if (head_side) SGRL_TRY(side_fork(c, &sb, 0));
+  GemmP g = lin(c, c.S(T_SH), KS, zS, Y.gp[G_H1NG_W], Y.gp[G_H1NG_B], c.S(T_BH), 128, zS, T, 128, KS); g.relu = 1;
+  SGRL_TRY(run_gemm(c, g, sb));
+  g = lin(c, c.S(T_BH), 128, zS, Y.gp[G_H2NG_W], Y.gp[G_H2NG_B], c.S(T_UH) + 128, 256, zS, T, 128, 128);
+  SGRL_TRY(run_gemm(c, g, sb));
   SGRL_TRY(inv_feature_fwd(fh, st));
-  GemmP g = lin_fold(c, c.S(T_GH), fold_offset(c.L, c.L, 0), Y.gp[G_H1G_B], c.S(T_AH), 128, T, 128); g.relu = 1;
+  g = lin_fold(c, c.S(T_GH), fold_offset(c.L, c.L, 0), Y.gp[G_H1G_B], c.S(T_AH), 128, T, 128); g.relu = 1;
   SGRL_TRY(run_gemm(c, g));
   g = lin(c, c.S(T_AH), 128, zS, Y.gp[G_H2G_W], Y.gp[G_H2G_B], c.S(T_UH), 256, zS, T, 128, 128);
   SGRL_TRY(run_gemm(c, g));
-  g = lin(c, c.S(T_SH), KS, zS, Y.gp[G_H1NG_W], Y.gp[G_H1NG_B], c.S(T_BH), 128, zS, T, 128, KS); g.relu = 1;
-  SGRL_TRY(run_gemm(c, g));
-  g = lin(c, c.S(T_BH), 128, zS, Y.gp[G_H2NG_W], Y.gp[G_H2NG_B], c.S(T_UH) + 128, 256, zS, T, 128, 128);
-  SGRL_TRY(run_gemm(c, g));
+  if (head_side) SGRL_TRY(side_join(c, 0));
   if (c.kind == CRITIC) {
     g = lin(c, c.S(T_UH), 256, zS, Y.gp[G_DNG_W], Y.gp[G_DNG_B], c.S(T_OUT), 1, zS, T, 1, 256);
     g.rowdiv = c.S(T_FH); g.zsRow = zS;
@@ -692,7 +698,22 @@ inline int net_backward(const NetCtx& c_in, const float* dOut, long long zsDo, i
     g = dgrad(c, W(W_DA), 256, Y.gp[G_H1M_W], 256, W(W_DUH), 256, T, 256, 256);
     SGRL_TRY(run_gemm(c, g));
   }
-  // u[:, :128] = linear2_g(relu(linear1_g(vec G)))
+  // ---- branch lane (hb): the scalar branch u[:, 128:] = linear2_ng(relu(linear1_ng([s0 | h]))) and the final LayerNorm, next to
+  // the invariant branch below (both start from dUH; SGRL_HEAD_SIDE=0: one after the other on the main stream)
+  static const int head_side = getenv("SGRL_HEAD_SIDE") ? atoi(getenv("SGRL_HEAD_SIDE")) : 1;
+  cudaStream_t hb = st;
+  if (head_side) SGRL_TRY(side_fork(c, &hb, 0));
+  SGRL_TRY(side_w(W(W_DUH) + 128, 256, c.S(T_BH), 128, zS, Y.gp[G_H2NG_W], 128, T, 128, 128, Y.gp[G_H2NG_B]));
+  g = dgrad(c, W(W_DUH) + 128, 256, Y.gp[G_H2NG_W], 128, W(W_DA3), 128, T, 128, 128);
+  g.mask = c.S(T_BH); g.zsMask = zS; g.ldmask = 128;
+  SGRL_TRY(run_gemm(c, g, hb));
+  SGRL_TRY(side_w(W(W_DA3), 128, c.S(T_SH), KS, zS, Y.gp[G_H1NG_W], KS, T, 128, KS, Y.gp[G_H1NG_B], 1.f, hb));
+  g = dgrad(c, W(W_DA3), 128, Y.gp[G_H1NG_W], KS, W(W_DSH), KS, T, 128, KS);
+  SGRL_TRY(run_gemm(c, g, hb));
+  if (dact) SGRL_TRY(block_copy(c, dact, 3, zsDact, W(W_DSH) + 17, KS, zW, T, 3, 0, nullptr, 0, 0, hb));
+  // final LayerNorm
+  SGRL_TRY(layernorm_bwd(c, W(W_DSH) + ng, KS, nullptr, 0, c.S(T_HL), 128, c.S(T_STF), Y.gp[G_NORM_W], Y.gp[G_NORM_B], W(W_DH), 128, wg, hb));
+  // ---- main: u[:, :128] = linear2_g(relu(linear1_g(vec G)))
   SGRL_TRY(side_w(W(W_DUH), 256, c.S(T_AH), 128, zS, Y.gp[G_H2G_W], 128, T, 128, 128, Y.gp[G_H2G_B]));
   g = dgrad(c, W(W_DUH), 256, Y.gp[G_H2G_W], 128, W(W_DA2), 128, T, 128, 128);
   g.mask = c.S(T_AH); g.zsMask = zS; g.ldmask = 128;
@@ -714,17 +735,7 @@ inline int net_backward(const NetCtx& c_in, const float* dOut, long long zsDo, i
     SGRL_TRY(side_w(W(W_DZ3), 32, c.S(T_V0), 8, zS, Y.gp[G_GPH_W], D + GN, T3, NPJ, GN));
     SGRL_TRY(side_w(W(W_DZ3), 32, c.S(T_VGF), 128, zS, Y.gp[G_GPH_W] + GN, D + GN, T3, NPJ, 128));
   }
-  // u[:, 128:] = linear2_ng(relu(linear1_ng([s0 | h])))
-  SGRL_TRY(side_w(W(W_DUH) + 128, 256, c.S(T_BH), 128, zS, Y.gp[G_H2NG_W], 128, T, 128, 128, Y.gp[G_H2NG_B]));
-  g = dgrad(c, W(W_DUH) + 128, 256, Y.gp[G_H2NG_W], 128, W(W_DA3), 128, T, 128, 128);
-  g.mask = c.S(T_BH); g.zsMask = zS; g.ldmask = 128;
-  SGRL_TRY(run_gemm(c, g));
-  SGRL_TRY(side_w(W(W_DA3), 128, c.S(T_SH), KS, zS, Y.gp[G_H1NG_W], KS, T, 128, KS, Y.gp[G_H1NG_B]));
-  g = dgrad(c, W(W_DA3), 128, Y.gp[G_H1NG_W], KS, W(W_DSH), KS, T, 128, KS);
-  SGRL_TRY(run_gemm(c, g));
-  if (dact) SGRL_TRY(block_copy(c, dact, 3, zsDact, W(W_DSH) + 17, KS, zW, T, 3, 0));
-  // final LayerNorm
-  SGRL_TRY(layernorm_bwd(c, W(W_DSH) + ng, KS, nullptr, 0, c.S(T_HL), 128, c.S(T_STF), Y.gp[G_NORM_W], Y.gp[G_NORM_B], W(W_DH), 128, wg));
+  if (head_side) SGRL_TRY(side_join(c, 0));
 
   const bool staged = wg && c.staged;
   if (staged) SGRL_TRY(stage_mark(c, c.L));
