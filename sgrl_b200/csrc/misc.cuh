@@ -425,18 +425,20 @@ __global__ void __launch_bounds__(256) actor_out_bwd_kernel(
 // =====================================================================================
 // Backward helpers
 // =====================================================================================
-// y = t/F (* colscale on the first cs_n columns):  dt = dy * cs / F  (in place),  dF[t] -= sum_n dy*y / F
+// y = t/F (* colscale on the first cs_n columns):  dt = dy * cs / F,  dF[t] -= sum_n dy*y / F.  dt is written to `dy`; the incoming
+// gradient is read from `src` (row stride ldsrc, z-stride zsSrc) when given — no separate copy kernel in front — else from `dy` (in place)
 __global__ void __launch_bounds__(256) rowdiv_bwd_kernel(
-    float* __restrict__ dy, int lddy, long long zsW, const float* __restrict__ y, int ldy, const float* __restrict__ Fn, long long zsS,
-    float* __restrict__ dF, int N, float colscale, int cs_n, int T) {
+    float* dy, int lddy, long long zsW, const float* __restrict__ y, int ldy, const float* __restrict__ Fn, long long zsS,
+    float* __restrict__ dF, int N, float colscale, int cs_n, int T, const float* src, int ldsrc, long long zsSrc) {
   SGRL_PDL_ENTER();
   const int lane = threadIdx.x & 31, z = blockIdx.y;
   dy += z * zsW; dF += z * zsW; y += z * zsS; Fn += z * zsS;
+  if (src) src += z * zsSrc; else { src = dy; ldsrc = lddy; }
   for (int t = blockIdx.x * 8 + (threadIdx.x >> 5); t < T; t += gridDim.x * 8) {
     const float invF = 1.f / Fn[t];
     float s = 0.f;
     for (int n = lane; n < N; n += 32) {
-      const float d = dy[(long long)t * lddy + n];
+      const float d = src[(long long)t * ldsrc + n];
       s = fmaf(d, y[(long long)t * ldy + n], s);
       dy[(long long)t * lddy + n] = d * invF * (n < cs_n ? colscale : 1.f);
     }

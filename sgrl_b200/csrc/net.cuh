@@ -339,9 +339,9 @@ inline int layernorm_bwd(const NetCtx& c, const float* dy1, int ld1, const float
   return 0;
 }
 inline int rowdiv_bwd(const NetCtx& c, float* dy, int lddy, const float* y, int ldy, const float* Fn, float* dF, int N, float cs, int cs_n,
-                      cudaStream_t st = nullptr) {
+                      cudaStream_t st = nullptr, const float* src = nullptr, int ldsrc = 0, long long zsSrc = 0) {
   if (!st) st = c.stream;
-  launch_k(rowdiv_bwd_kernel, dim3(grid_for_warps(c.T), c.nb), 256, 0, st, dy, lddy, c.zsW, y, ldy, Fn, c.zsS, dF, N, cs, cs_n, c.T);
+  launch_k(rowdiv_bwd_kernel, dim3(grid_for_warps(c.T), c.nb), 256, 0, st, dy, lddy, c.zsW, y, ldy, Fn, c.zsS, dF, N, cs, cs_n, c.T, src, ldsrc, zsSrc);
   SGRL_LAUNCH_OK();
   return 0;
 }
@@ -677,8 +677,7 @@ inline int net_backward(const NetCtx& c_in, const float* dOut, long long zsDo, i
   SGRL_TRY(zero_df_frames(c));      // dF accumulators of the head block and of every layer
   float* dFh = W(W_DF1);
   if (c.kind == CRITIC) {
-    SGRL_TRY(block_copy(c, W(W_DQ), 1, zW, dOut, 1, zsDo, T, 1, 0));
-    SGRL_TRY(rowdiv_bwd(c, W(W_DQ), 1, c.S(T_OUT), 1, c.S(T_FH), dFh, 1, 1.f, 0));
+    SGRL_TRY(rowdiv_bwd(c, W(W_DQ), 1, c.S(T_OUT), 1, c.S(T_FH), dFh, 1, 1.f, 0, nullptr, dOut, 1, zsDo));      // reads dOut, writes dQ
     SGRL_TRY(side_w(W(W_DQ), 1, c.S(T_UH), 256, zS, Y.gp[G_DNG_W], 256, T, 1, 256, Y.gp[G_DNG_B]));
     g = dgrad(c, W(W_DQ), 1, Y.gp[G_DNG_W], 256, W(W_DUH), 256, T, 1, 256);
     SGRL_TRY(run_gemm(c, g));
@@ -756,8 +755,7 @@ inline int net_backward(const NetCtx& c_in, const float* dOut, long long zsDo, i
       SGRL_TRY(layernorm_bwd(c, Wn(W_DH), 128, nullptr, 0, c.SL(l, S_X2), 128, c.SL(l, S_ST2), lp[L_N2_W], lp[L_N2_B], W(W_DX), 128, wg, sb));
     else
       SGRL_TRY(layernorm_bwd(c, Wn(W_DH1), 128, Wn(W_DUA) + 128, 256, c.SL(l, S_X2), 128, c.SL(l, S_ST2), lp[L_N2_W], lp[L_N2_B], W(W_DX), 128, wg, sb));
-    SGRL_TRY(block_copy(c, W(W_DFF), 128, zW, W(W_DX), 128, zW, T, 128, 0, nullptr, 0, 0, sb));
-    SGRL_TRY(rowdiv_bwd(c, W(W_DFF), 128, c.SL(l, S_FF), 128, c.SL(l, S_F2), W(W_DF2), 128, 1.f, 0, sb));
+    SGRL_TRY(rowdiv_bwd(c, W(W_DFF), 128, c.SL(l, S_FF), 128, c.SL(l, S_F2), W(W_DF2), 128, 1.f, 0, sb, W(W_DX), 128, zW));    // reads dx (kept: LN1's residual), writes dFF
     SGRL_TRY(side_w(W(W_DFF), 128, T31 + 256, 512, zS, lp[L_L2_W], 256, T, 128, 256, lp[L_L2_B], 1.f, sb));
     g = dgrad(c, W(W_DFF), 128, lp[L_L2_W], 256, W(W_DT31) + 256, 512, T, 128, 256);
     g.mask = T31 + 256; g.zsMask = zS; g.ldmask = 512;
@@ -783,6 +781,11 @@ inline int net_backward(const NetCtx& c_in, const float* dOut, long long zsDo, i
     SGRL_TRY(side_w(W(W_DH1), 128, c.SL(l, S_O), 256, zS, lp[L_NGO_W], 256, T, 128, 256, lp[L_NGO_B], 1.f, sb));
     g = dgrad(c, W(W_DH1), 128, lp[L_NGO_W], 256, W(W_DO), 256, T, 128, 256);
     SGRL_TRY(run_gemm(c, g, sb));
+    // d(dV) = dVg' + dZ3[:, :30] g_proj3 (+ dZ2[:, :30] g_proj2, added on the main stream once dZ2 exists): dZ3 has been there since
+    // the matrix-apply backward, so this term leaves the main chain
+    g = dgrad(c, W(W_DZ3), 32, lp[L_GP3], 128, W(W_DDV), 128, T3, NPJ, 128);
+    g.res1 = Wn(W_DVG); g.zsR1 = zW; g.ldr1 = 128;
+    SGRL_TRY(run_gemm(c, g, sb));
     // ---- main: u'[:, :128] = linear_g2(relu(linear_g1(vec G2)))
     SGRL_TRY(side_w(W(W_DUB), 256, c.SL(l, S_A2), 256, zS, lp[L_FG2_W], 256, T, 128, 256, lp[L_FG2_B]));
     g = dgrad(c, W(W_DUB), 256, lp[L_FG2_W], 256, W(W_DA), 256, T, 128, 256);
@@ -792,11 +795,9 @@ inline int net_backward(const NetCtx& c_in, const float* dOut, long long zsDo, i
     g = dgrad_fold(c, W(W_DA), 256, fold_offset(c.L, l, 1), W(W_DG), T, 256);
     SGRL_TRY(run_gemm(c, g));
     SGRL_TRY(inv_feature_bwd(W(W_DG), W(W_DF2), c.SL(l, S_Z2), c.SL(l, S_F2), W(W_DZ2), zS, zW, T, c.nb, st));
-    // d(dV) = dVg' + dZ2[:, :30] g_proj2 + dZ3[:, :30] g_proj3
-    g = dgrad(c, W(W_DZ2), 32, lp[L_GP2], 128, W(W_DDV), 128, T3, NPJ, 128);
-    g.res1 = Wn(W_DVG); g.zsR1 = zW; g.ldr1 = 128;
-    SGRL_TRY(run_gemm(c, g));
-    g = dgrad(c, W(W_DZ3), 32, lp[L_GP3], 128, W(W_DDV), 128, T3, NPJ, 128); g.accumulate = 1;
+    // d(dV) += dZ2[:, :30] g_proj2   (the branch lane wrote dVg' + dZ3 g_proj3, and dO for the attention backward below)
+    SGRL_TRY(side_join(c, 0));
+    g = dgrad(c, W(W_DZ2), 32, lp[L_GP2], 128, W(W_DDV), 128, T3, NPJ, 128); g.accumulate = 1;
     SGRL_TRY(run_gemm(c, g));
     SGRL_TRY(side_w(W(W_DZ2), 32, c.SL(l, S_DV), 128, zS, lp[L_GP2], 128, T3, NPJ, 128));
     SGRL_TRY(side_w(W(W_DZ3), 32, c.SL(l, S_DV), 128, zS, lp[L_GP3], 128, T3, NPJ, 128));
@@ -804,7 +805,6 @@ inline int net_backward(const NetCtx& c_in, const float* dOut, long long zsDo, i
     SGRL_TRY(side_w(W(W_DDV), 128, c.SL(l, S_OG), 256, zS, lp[L_GO_W], 256, T3, 128, 256));
     g = dgrad(c, W(W_DDV), 128, lp[L_GO_W], 256, W(W_DOG), 256, T3, 128, 256);
     SGRL_TRY(run_gemm(c, g));
-    SGRL_TRY(side_join(c, 0));
     SGRL_TRY(attention_bwd(c.SL(l, S_QKV), c.SL(l, S_VGP), c.S(T_GD), c.SL(l, S_P), zS, W(W_DO), W(W_DOG), W(W_DQKV), W(W_DVGP), zW,
                            (l == 0 && wg) ? c.Gr(Y.gp[G_REL_W]) : nullptr, c.zsG, c.gr, c.nb, st,
                            W(W_DG) /* deterministic mode's partial-sum scratch: free between the two vec(G) halves of the stage */));
