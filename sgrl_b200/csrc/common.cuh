@@ -46,20 +46,12 @@ inline bool det_enabled() {
 }
 #define SGRL_PDL_TRIGGER() asm volatile("griddepcontrol.launch_dependents;" ::: "memory")
 #define SGRL_PDL_WAIT() asm volatile("griddepcontrol.wait;" ::: "memory")
-// c_pdl_hold (SGRL_PDL_LATE=2): the small kernels do NOT release their dependents at entry (the dependents launch when this
-// kernel's CTAs exit): an early-launched tcgen05 GEMM CTA waits at its griddepcontrol.wait with a whole SM's shared and
-// tensor memory allocated, for as long as its predecessor runs.
-__constant__ int c_pdl_hold;
-#define SGRL_PDL_ENTER() do { if (!c_pdl_hold) SGRL_PDL_TRIGGER(); SGRL_PDL_WAIT(); } while (0)
+#define SGRL_PDL_ENTER() do { SGRL_PDL_TRIGGER(); SGRL_PDL_WAIT(); } while (0)
 // SGRL_PDL_LATE: 0 = every kernel releases its dependents at entry; 1 (default) = the tcgen05 GEMM releases them when its
-// accumulators are complete; 2 = additionally the small kernels never release early; 3 = nor does the GEMM.  Measured on the
-// B=256 update (profiles/r05c..e_pdl_late.txt): 5.36 / 5.11 / 5.15 / 5.13 ms.
+// accumulators are complete.  Measured on the B=256 update (profiles/r05c..e_pdl_late.txt): 5.36 / 5.11 ms; two further variants
+// that existed for the experiment — the small kernels never releasing early, and the GEMM never releasing explicitly either —
+// measured 5.15 / 5.13 ms and were removed again.
 inline int pdl_late_mode() { static const int m = getenv("SGRL_PDL_LATE") ? atoi(getenv("SGRL_PDL_LATE")) : 1; return m; }
-inline void pdl_init_once() {
-  // zero-initialised: nothing to copy (and nothing that could disturb a stream capture) unless the experiment mode is on
-  static const bool once = [] { if (pdl_late_mode() >= 2) { const int v = 1; cudaMemcpyToSymbol(c_pdl_hold, &v, sizeof(v)); } return true; }();
-  (void)once;
-}
 // streams on which kernels are launched WITHOUT the programmatic attribute (experiment knob SGRL_PDL_SIDE=0: the side lanes)
 extern cudaStream_t g_nopdl_streams[32];
 extern int g_nopdl_count;
@@ -69,7 +61,6 @@ inline bool pdl_stream_ok(cudaStream_t st) {
 }
 template <typename... KArgs, typename... Args>
 inline void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
-  pdl_init_once();
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;

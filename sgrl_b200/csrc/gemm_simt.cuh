@@ -72,6 +72,7 @@ inline GemmP gemm_defaults() {
   return p;
 }
 
+#ifndef SGRL_TC_TU      // the SIMT kernels belong to the main translation unit; the tcgen05 units (gemm_tc.cu) only need GemmP
 constexpr int GB_M = 64, GB_N = 64, GB_K = 16, G_THREADS = 256, G_PAD = 4;
 
 __device__ __forceinline__ void gemm_fetch(float (&r)[4], const float* __restrict__ src, int ld, int trans,
@@ -307,5 +308,7 @@ inline int pick_splitk(int M, int N, int K, int nb) {
   if (s > 64) s = 64;
   return s;
 }
+
+#endif
 
 }  // namespace sgrl

@@ -51,6 +51,7 @@ __device__ __forceinline__ TcpTile tcp_decode(const TcGroup& grp, int vt) {
   return t;
 }
 
+#if SGRL_TC_PART == 4      // kernel bodies only in the translation unit that launches them (gemm_tc.cuh: parts)
 __global__ void __launch_bounds__(TCP_THREADS, 1) gemm_tc_persist_kernel(const __grid_constant__ TcGroup grp, int total_tiles) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -285,6 +286,7 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) gemm_tc_persist_kernel(const _
 }
 
 
+#endif
 // ======================================================================================================================
 // K3-PG — persistent GRAM projection for inference passes:  C = epi( tri(Z^T Z) W'^T )  with the A operand generated by the
 // converter warps (GemmP::gramZ, see gemm_tc_kernel<.., GRAM>) and ALL N <= 256 output columns in one tile, so that each
@@ -302,6 +304,7 @@ constexpr int TCG_Z_BYTES = TC_BM * GRAM_ZLD * 4;                  // 50 KiB: th
 constexpr int TCG_SMEM = TCG_RING_BYTES + TCG_Z_BYTES + 1024 /*partial ||G||^2*/ + TCP_EPI_WARPS * 2 * TCP_BOX_BYTES + 256 + 1024;
 constexpr int TCG_NKB = GP_K / TC_BK;                              // 17
 
+#if SGRL_TC_PART == 4
 __global__ void __launch_bounds__(TCP_THREADS, 1) gemm_tc_gram_persist_kernel(const __grid_constant__ TcGroup grp, int total_tiles) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -519,4 +522,5 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) gemm_tc_gram_persist_kernel(co
   }
 }
 
+#endif
 }  // namespace sgrl

@@ -131,6 +131,8 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(
 }
 
 //   dy = dy1 + dy2;  dx = rstd * (g*dy - mean(g*dy) - xhat * mean(g*dy*xhat));  dgamma += dy*xhat; dbeta += dy
+// (Tried in round 2: the backward of the row division f = linear2(..)/F2 as a tail of this kernel for LayerNorm-2, one launch
+// fewer on the branch lane — the update got 1.7 % SLOWER, 4.40 -> 4.48 ms, profiles/r05r_multi_tu.txt; removed.)
 __global__ void __launch_bounds__(256) layernorm_bwd_kernel(
     const float* __restrict__ dy1, int ld1, const float* __restrict__ dy2, int ld2,
     const float* __restrict__ x, int ldx, const float* __restrict__ stats, long long zsS,

@@ -11,7 +11,7 @@
 #include "common.cuh"
 #include "feature.cuh"
 #include "gemm_simt.cuh"
-#include "gemm_tc.cuh"
+#include "gemm_tc_api.h"
 #include "layout.h"
 #include "misc.cuh"
 
