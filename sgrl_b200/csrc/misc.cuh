@@ -131,18 +131,21 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(
 }
 
 //   dy = dy1 + dy2;  dx = rstd * (g*dy - mean(g*dy) - xhat * mean(g*dy*xhat));  dgamma += dy*xhat; dbeta += dy
-// (Tried in round 2: the backward of the row division f = linear2(..)/F2 as a tail of this kernel for LayerNorm-2, one launch
-// fewer on the branch lane — the update got 1.7 % SLOWER, 4.40 -> 4.48 ms, profiles/r05r_multi_tu.txt; removed.)
+// Optional tail (LayerNorm-2 of an encoder layer, whose input branch is f = linear2(..)/F2): the backward of that row division on
+// the same rows, dff = dx / F (-> rd.out), dF[t] -= sum_n dx*f / F — what rowdiv_bwd_kernel did in a launch of its own.
+struct LnRowdiv { const float* y; const float* Fn; float* dF; float* out; int ldy, ldout; };    // y, Fn: stash (zsS); dF, out: workspace (zsW)
 __global__ void __launch_bounds__(256) layernorm_bwd_kernel(
     const float* __restrict__ dy1, int ld1, const float* __restrict__ dy2, int ld2,
     const float* __restrict__ x, int ldx, const float* __restrict__ stats, long long zsS,
     const float* __restrict__ gamma, long long zsP,
-    float* __restrict__ dx, int lddx, long long zsW, float* __restrict__ dgamma, float* __restrict__ dbeta, long long zsG, int T, int vflags) {
+    float* __restrict__ dx, int lddx, long long zsW, float* __restrict__ dgamma, float* __restrict__ dbeta, long long zsG, int T, int vflags,
+    LnRowdiv rd) {
   SGRL_PDL_ENTER();
   __shared__ float red[2][8][128];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, z = blockIdx.y;
   dy1 += z * zsW; if (dy2) dy2 += z * zsW; dx += z * zsW;
   x += z * zsS; stats += z * zsS; gamma += z * zsP;
+  if (rd.y) { rd.y += z * zsS; rd.Fn += z * zsS; rd.dF += z * zsW; rd.out += z * zsW; }
   if (dgamma) { dgamma += z * zsG; dbeta += z * zsG; }
   const float4 g = ldg4(gamma + lane * 4);
   float ag[4] = {0, 0, 0, 0}, ab[4] = {0, 0, 0, 0};
@@ -165,6 +168,13 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(
     o.x = rstd * (gd[0] - s1 - xh[0] * s2); o.y = rstd * (gd[1] - s1 - xh[1] * s2);
     o.z = rstd * (gd[2] - s1 - xh[2] * s2); o.w = rstd * (gd[3] - s1 - xh[3] * s2);
     store4(dx + (long long)t * lddx + lane * 4, o, vo);
+    if (rd.y) {
+      const float invF = 1.f / rd.Fn[t];
+      const float4 yv = load4(rd.y + (long long)t * rd.ldy + lane * 4, vflags & 16);
+      const float s = warp_sum(o.x * yv.x + o.y * yv.y + o.z * yv.z + o.w * yv.w);
+      store4(rd.out + (long long)t * rd.ldout + lane * 4, make_float4(o.x * invF, o.y * invF, o.z * invF, o.w * invF), vflags & 32);
+      if (lane == 0) atomicAdd(rd.dF + t, -s * invF);     // the other divisions by the same F add their term from a concurrent lane
+    }
   }
   if (!dgamma) return;   // data-only backward
 #pragma unroll

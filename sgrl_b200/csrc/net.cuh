@@ -328,13 +328,15 @@ inline int layernorm_fwd(const NetCtx& c, const float* a, int lda, const float* 
   return 0;
 }
 inline int layernorm_bwd(const NetCtx& c, const float* dy1, int ld1, const float* dy2, int ld2, const float* x, int ldx,
-                         const float* stats, long long g_off, long long b_off, float* dx, int lddx, bool wg, cudaStream_t st = nullptr) {
+                         const float* stats, long long g_off, long long b_off, float* dx, int lddx, bool wg, cudaStream_t st = nullptr,
+                         LnRowdiv rd = LnRowdiv{nullptr, nullptr, nullptr, nullptr, 0, 0}) {
   if (!st) st = c.stream;
   int gx = grid_for_warps(c.T); if (gx > 2 * NUM_SMS) gx = 2 * NUM_SMS;
   if (wg && det_enabled()) gx = 1;      // dgamma / dbeta: one add per address
-  const int vf = host_vec_ok(dy1, ld1, c.zsW) | (host_vec_ok(dy2, ld2, c.zsW) << 1) | (host_vec_ok(x, ldx, c.zsS) << 2) | (host_vec_ok(dx, lddx, c.zsW) << 3);
+  const int vf = host_vec_ok(dy1, ld1, c.zsW) | (host_vec_ok(dy2, ld2, c.zsW) << 1) | (host_vec_ok(x, ldx, c.zsS) << 2) | (host_vec_ok(dx, lddx, c.zsW) << 3) |
+                 ((rd.y && host_vec_ok(rd.y, rd.ldy, c.zsS)) << 4) | ((rd.out && host_vec_ok(rd.out, rd.ldout, c.zsW)) << 5);
   launch_k(layernorm_bwd_kernel, dim3(gx, c.nb), 256, 0, st, dy1, ld1, dy2, ld2, x, ldx, stats, c.zsS, c.P(g_off), c.zsP, dx, lddx, c.zsW,
-                                                             wg ? c.Gr(g_off) : nullptr, wg ? c.Gr(b_off) : nullptr, c.zsG, c.T, vf);
+                                                             wg ? c.Gr(g_off) : nullptr, wg ? c.Gr(b_off) : nullptr, c.zsG, c.T, vf, rd);
   SGRL_LAUNCH_OK();
   return 0;
 }
@@ -751,11 +753,14 @@ inline int net_backward(const NetCtx& c_in, const float* dOut, long long zsDo, i
     SGRL_TRY(side_fork(c, &sb, 0));
     // incoming dh: the final norm's output for the last layer; below it, dx1 + du[:, 128:] of the layer above, summed here
     // instead of by a copy kernel at the end of that layer
+    // ... with the backward of f = linear2(..)/F2 on the same rows: dFF = dx / F2, dF2 -= <dx, f> / F2 (dx itself stays: LN1's residual)
+    static const int ln_rd = getenv("SGRL_LN_ROWDIV") ? atoi(getenv("SGRL_LN_ROWDIV")) : 1;
+    const LnRowdiv rd = ln_rd ? LnRowdiv{c.SL(l, S_FF), c.SL(l, S_F2), W(W_DF2), W(W_DFF), 128, 128} : LnRowdiv{nullptr, nullptr, nullptr, nullptr, 0, 0};
     if (l == c.L - 1)
-      SGRL_TRY(layernorm_bwd(c, Wn(W_DH), 128, nullptr, 0, c.SL(l, S_X2), 128, c.SL(l, S_ST2), lp[L_N2_W], lp[L_N2_B], W(W_DX), 128, wg, sb));
+      SGRL_TRY(layernorm_bwd(c, Wn(W_DH), 128, nullptr, 0, c.SL(l, S_X2), 128, c.SL(l, S_ST2), lp[L_N2_W], lp[L_N2_B], W(W_DX), 128, wg, sb, rd));
     else
-      SGRL_TRY(layernorm_bwd(c, Wn(W_DH1), 128, Wn(W_DUA) + 128, 256, c.SL(l, S_X2), 128, c.SL(l, S_ST2), lp[L_N2_W], lp[L_N2_B], W(W_DX), 128, wg, sb));
-    SGRL_TRY(rowdiv_bwd(c, W(W_DFF), 128, c.SL(l, S_FF), 128, c.SL(l, S_F2), W(W_DF2), 128, 1.f, 0, sb, W(W_DX), 128, zW));    // reads dx (kept: LN1's residual), writes dFF
+      SGRL_TRY(layernorm_bwd(c, Wn(W_DH1), 128, Wn(W_DUA) + 128, 256, c.SL(l, S_X2), 128, c.SL(l, S_ST2), lp[L_N2_W], lp[L_N2_B], W(W_DX), 128, wg, sb, rd));
+    if (!ln_rd) SGRL_TRY(rowdiv_bwd(c, W(W_DFF), 128, c.SL(l, S_FF), 128, c.SL(l, S_F2), W(W_DF2), 128, 1.f, 0, sb, W(W_DX), 128, zW));    // reads dx (kept: LN1's residual), writes dFF
     SGRL_TRY(side_w(W(W_DFF), 128, T31 + 256, 512, zS, lp[L_L2_W], 256, T, 128, 256, lp[L_L2_B], 1.f, sb));
     g = dgrad(c, W(W_DFF), 128, lp[L_L2_W], 256, W(W_DT31) + 256, 512, T, 128, 256);
     g.mask = T31 + 256; g.zsMask = zS; g.ldmask = 512;
