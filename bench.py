@@ -332,10 +332,10 @@ def run_ours(a):
         alg = FLOP_PER_TOKEN_UPDATE * B * N
         ach = alg / (classes[dom]["ms_per_step"] * 1e-3) / 1e12
         line["roofline"] = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": pk["tflops_sustained"], "unit": "TFLOP/s",
-                            "frac": ach / pk["tflops_sustained"], "traffic": 6.73e6, "traffic_unit": "bytes of DRAM traffic per launch",
-                            "traffic_src": "mean of 14 launches of this class, ncu --set full (profiles/r03c_ncu_gemm_update_summary.txt): "
-                                           "6.73 MB read + 0 MB written (ncu flushes the caches before each launch; in the step the "
-                                           "activations and weights of a B=256 update stay in the 126 MB L2)",
+                            "frac": ach / pk["tflops_sustained"], "traffic": 5.84e6, "traffic_unit": "bytes of DRAM traffic per launch",
+                            "traffic_src": "mean of 12 launches of this class on the final tree, ncu --set full (profiles/r05u_ncu_gemm_update_summary.txt; "
+                                           "r03c_* mid-round: 6.73 MB): 5.84 MB read + 0 MB written (ncu flushes the caches before each launch; in the "
+                                           "step the activations and weights of a B=256 update stay in the 126 MB L2)",
                             "peak_src": pk["src"] + " bf16 sustained",
                             "algorithmic_flops_per_step": alg, "launches_per_step": classes[dom]["launches_per_step"],
                             "executed_tflops": classes[dom]["tflops"], "ceiling_frac_3xtf32": 1.0 / 6.0,
