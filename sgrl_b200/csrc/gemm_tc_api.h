@@ -2,7 +2,8 @@
 // The tensor-core kernels are compiled on their own: their code generation (30-odd instantiations of ~260 KB each) must not
 // move when an unrelated kernel of the library changes.  Measured: built in ONE translation unit with nvcc -split-compile, the
 // same gemm_tc.cuh came out as 260 KB or 298 KB per kernel depending on what else was in the module, and the B=256 update ran
-// 4.41 or 4.96 ms (profiles/r05p_ln_rowdiv.txt, r05q_timeline_ln.txt: every GEMM launch ~15 % slower, nothing else changed).
+// 4.41 or 4.96 ms (profiles/r05p_ln_rowdiv.txt, r05q_timeline_ln.txt: every GEMM launch ~15 % slower, nothing else changed;
+// DESIGN.md section 5 "Code generation is part of the measurement").
 #pragma once
 #include "gemm_simt.cuh"
 
