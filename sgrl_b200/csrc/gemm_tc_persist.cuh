@@ -99,15 +99,16 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) gemm_tc_persist_kernel(const _
       const TcpTile t = tcp_decode(grp, vt);
       const TcProblem& pr = grp.pr[t.gi];
       const int zA = pr.p.zsA ? t.z : 0, zB = pr.p.zsB ? t.z : 0;
+      const bool bf = pr.p.prec == 1;          // BF16-input mode: the weights' lo tile is never read
       for (int i = 0; i < t.nkb; ++i, ++kbg) {
         const int s = kbg % TCP_STAGES;
         mbar_wait(empty_bar(s), ((kbg / TCP_STAGES) & 1u) ^ 1u);
         if (elect_one()) {
-          mbar_arrive_expect_tx(full_bar(s), TCP_STAGE_BYTES);
+          mbar_arrive_expect_tx(full_bar(s), bf ? TCP_STAGE_BYTES - TCP_B_BYTES : TCP_STAGE_BYTES);
           const uint32_t a_dst = smem_base + s * TCP_STAGE_BYTES, b_dst = a_dst + TC_A_BYTES;
           tma_load_3d(a_dst, &pr.mapA, full_bar(s), i * TC_BK, t.m0, zA);
           tma_load_3d(b_dst, &pr.mapB, full_bar(s), i * TC_BK, t.n0, zB);
-          tma_load_3d(b_dst + TCP_B_BYTES, &pr.mapBlo, full_bar(s), i * TC_BK, t.n0, zB);
+          if (!bf) tma_load_3d(b_dst + TCP_B_BYTES, &pr.mapBlo, full_bar(s), i * TC_BK, t.n0, zB);
         }
         __syncwarp();
       }
@@ -132,6 +133,7 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) gemm_tc_persist_kernel(const _
       int n_eff = grp.pr[t.gi].p.N - t.n0;                       // columns of this tile, rounded up to the MMA's N granularity of 16
       n_eff = n_eff >= TCP_BN ? TCP_BN : ((n_eff + 15) & ~15);
       const uint32_t idesc = idesc0 | ((uint32_t)(n_eff >> 3) << 17);
+      const bool bf = grp.pr[t.gi].p.prec == 1;     // BF16-input mode (warp-uniform): operands rounded to bf16 by the converters, hi*hi only
 #pragma unroll 1
       for (int i = 0; i < t.nkb; ++i, ++kbg) {
         const int s = kbg % TCP_STAGES, ts = kbg % TCP_TA;
@@ -145,10 +147,12 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) gemm_tc_persist_kernel(const _
         if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < 4; ++k) tc_mma_tf32_ts(acc, a_hi + 8 * k, b_hi + 2 * k, B_HIW, idesc, (i > 0 || k > 0) ? 1u : 0u);
+          if (!bf) {
 #pragma unroll
-          for (int k = 0; k < 2; ++k) {
-            tc_mma_tf32_ts(acc, a_lo + 8 * k, b_hi + 2 * k, B_HIW, idesc, 1u);
-            tc_mma_tf32_ts(acc, a_hi + 8 * k, b_lo + 2 * k, B_HIW, idesc, 1u);
+            for (int k = 0; k < 2; ++k) {
+              tc_mma_tf32_ts(acc, a_lo + 8 * k, b_hi + 2 * k, B_HIW, idesc, 1u);
+              tc_mma_tf32_ts(acc, a_hi + 8 * k, b_lo + 2 * k, B_HIW, idesc, 1u);
+            }
           }
         }
         __syncwarp();
@@ -160,10 +164,12 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) gemm_tc_persist_kernel(const _
           if (ready) tc_fence_after();
         }
         if (elect_one()) {
+          if (!bf) {
 #pragma unroll
-          for (int k = 2; k < 4; ++k) {
-            tc_mma_tf32_ts(acc, a_lo + 8 * k, b_hi + 2 * k, B_HIW, idesc, 1u);
-            tc_mma_tf32_ts(acc, a_hi + 8 * k, b_lo + 2 * k, B_HIW, idesc, 1u);
+            for (int k = 2; k < 4; ++k) {
+              tc_mma_tf32_ts(acc, a_lo + 8 * k, b_hi + 2 * k, B_HIW, idesc, 1u);
+              tc_mma_tf32_ts(acc, a_hi + 8 * k, b_lo + 2 * k, B_HIW, idesc, 1u);
+            }
           }
           tc_commit(empty_bar(s));
           tc_commit(ta_empty(ts));
@@ -174,11 +180,12 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) gemm_tc_persist_kernel(const _
     }
   } else if (warp < 2 + TC_CONV_WARPS) {
     // ===================== converters: landed A k-block -> [hi | lo] rows of a tensor-memory slot =====================
-    const int g = (warp - 2) >> 2, q = warp & 3, row = q * 32 + lane;
+    const int g = (warp - 2) >> 2, q = warp & 3, row = q * 32 + lane, cgt = ((warp - 2) & 3) * 32 + lane;
     const uint32_t trow = ta_base + ((uint32_t)(q * 32) << 16);
     uint32_t kbg = 0;
     for (int vt = blockIdx.x; vt < total_tiles; vt += gridDim.x) {
       const TcpTile t = tcp_decode(grp, vt);
+      const bool bf = grp.pr[t.gi].p.prec == 1;
       for (int i = 0; i < t.nkb; ++i, ++kbg) {
         if ((int)(kbg & 1u) != g) continue;
         const int s = kbg % TCP_STAGES, ts = kbg % TCP_TA;
@@ -191,13 +198,20 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) gemm_tc_persist_kernel(const _
           raw[4 * c] = __float_as_uint(v.x); raw[4 * c + 1] = __float_as_uint(v.y);
           raw[4 * c + 2] = __float_as_uint(v.z); raw[4 * c + 3] = __float_as_uint(v.w);
         }
+        if (bf) {            // BF16-input mode: the weights' hi tile rounded in place by this group's 128 threads, the A rows in registers
+          round_tile_bf16<TCP_B_BYTES / 16, 128>(st + TC_A_BYTES, cgt);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) lo[j] = lo_of_trunc(__uint_as_float(raw[j]));
+          for (int j = 0; j < 32; ++j) raw[j] = bf16_rn_bits(raw[j]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) lo[j] = lo_of_trunc(__uint_as_float(raw[j]));
+        }
         mbar_wait(ta_empty(ts), ((kbg / TCP_TA) & 1u) ^ 1u);
         tc_fence_after();
         tmem_st32(trow + (uint32_t)(ts * 64), raw);
-        tmem_st32(trow + (uint32_t)(ts * 64 + 32), lo);
+        if (!bf) tmem_st32(trow + (uint32_t)(ts * 64 + 32), lo);
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        if (bf) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy smem writes -> visible to the tensor core
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(ta_ready(ts));
@@ -356,10 +370,10 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) gemm_tc_gram_persist_kernel(co
         const int s = kbg % TCG_STAGES;
         mbar_wait(empty_bar(s), ((kbg / TCG_STAGES) & 1u) ^ 1u);
         if (elect_one()) {
-          mbar_arrive_expect_tx(full_bar(s), TCG_STAGE_BYTES);
+          mbar_arrive_expect_tx(full_bar(s), p.prec == 1 ? TCG_B_BYTES : TCG_STAGE_BYTES);        // BF16-input mode: no lo tile
           const uint32_t b_dst = smem_base + s * TCG_STAGE_BYTES;
           tma_load_3d(b_dst, &pr.mapB, full_bar(s), i * TC_BK, 0, zB);
-          tma_load_3d(b_dst + TCG_B_BYTES, &pr.mapBlo, full_bar(s), i * TC_BK, 0, zB);
+          if (p.prec != 1) tma_load_3d(b_dst + TCG_B_BYTES, &pr.mapBlo, full_bar(s), i * TC_BK, 0, zB);
         }
         __syncwarp();
       }
@@ -390,10 +404,12 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) gemm_tc_gram_persist_kernel(co
         if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < 4; ++k) tc_mma_tf32_ts(tb, a_hi + 8 * k, b_hi + 2 * k, B_HIW, idesc, (i > 0 || k > 0) ? 1u : 0u);
+          if (p.prec != 1) {
 #pragma unroll
-          for (int k = 0; k < 2; ++k) {
-            tc_mma_tf32_ts(tb, a_lo + 8 * k, b_hi + 2 * k, B_HIW, idesc, 1u);
-            tc_mma_tf32_ts(tb, a_hi + 8 * k, b_lo + 2 * k, B_HIW, idesc, 1u);
+            for (int k = 0; k < 2; ++k) {
+              tc_mma_tf32_ts(tb, a_lo + 8 * k, b_hi + 2 * k, B_HIW, idesc, 1u);
+              tc_mma_tf32_ts(tb, a_hi + 8 * k, b_lo + 2 * k, B_HIW, idesc, 1u);
+            }
           }
         }
         __syncwarp();
@@ -404,10 +420,12 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) gemm_tc_gram_persist_kernel(co
           if (ready) tc_fence_after();
         }
         if (elect_one()) {
+          if (p.prec != 1) {
 #pragma unroll
-          for (int k = 2; k < 4; ++k) {
-            tc_mma_tf32_ts(tb, a_lo + 8 * k, b_hi + 2 * k, B_HIW, idesc, 1u);
-            tc_mma_tf32_ts(tb, a_hi + 8 * k, b_lo + 2 * k, B_HIW, idesc, 1u);
+            for (int k = 2; k < 4; ++k) {
+              tc_mma_tf32_ts(tb, a_lo + 8 * k, b_hi + 2 * k, B_HIW, idesc, 1u);
+              tc_mma_tf32_ts(tb, a_hi + 8 * k, b_lo + 2 * k, B_HIW, idesc, 1u);
+            }
           }
           tc_commit(empty_bar(s));
           tc_commit(ta_empty(ts));
@@ -441,13 +459,24 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) gemm_tc_gram_persist_kernel(co
         const int ts = kbg % TCG_TA;
         uint32_t raw[32];
         gram_kblock(i, zrow, raw, ss);                     // generated before the slot wait: overlaps the MMAs still reading it
+        const bool bf = p.prec == 1;
+        if (bf) {            // BF16-input mode: this group's 128 threads round the landed folded-weight tile in place, and the generated rows
+          const int s = kbg % TCG_STAGES;
+          mbar_wait(full_bar(s), (kbg / TCG_STAGES) & 1u);
+          round_tile_bf16<TCG_B_BYTES / 16, 128>(smem_base + s * TCG_STAGE_BYTES, ((warp - 2) & 3) * 32 + lane);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) raw[j] = bf16_rn_bits(raw[j]);
+        }
         mbar_wait(ta_empty(ts), ((kbg / TCG_TA) & 1u) ^ 1u);
         tc_fence_after();
         tmem_st32(trow + (uint32_t)(ts * 64), raw);
+        if (!bf) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) raw[j] = lo_of_trunc(__uint_as_float(raw[j]));
-        tmem_st32(trow + (uint32_t)(ts * 64 + 32), raw);
+          for (int j = 0; j < 32; ++j) raw[j] = lo_of_trunc(__uint_as_float(raw[j]));
+          tmem_st32(trow + (uint32_t)(ts * 64 + 32), raw);
+        }
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        if (bf) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(ta_ready(ts));

@@ -85,3 +85,26 @@ def test_network_accuracy_in_bf16_input_mode_is_recorded_and_bounded(capsys):
               f"(worst tensor {worst:.2e}); rotation about gravity: actions {e_rot_a:.2e}, Q {e_rot_q:.2e}")
     assert e_a < 5e-2 and e_q < 5e-2 and glob < 1e-1 and e_rot_a < 5e-2 and e_rot_q < 5e-2
     assert e_a > parity.RTOL or e_q > parity.RTOL        # a reduced-precision mode: it must not be mistaken for the parity path
+
+
+def test_persistent_kernels_in_bf16_input_mode(monkeypatch):
+    """At rollout sizes the BF16-input mode runs its projections in the persistent tcgen05 kernels too (one MMA pass per
+    k-block, the weights' lo tile is not even loaded).  The short-K projections accumulate in the same order as the per-tile
+    kernels (bit-identical); the K = 544 Gram projection sums 17 k-blocks on one accumulator instead of two, and a 1e-7
+    difference in an activation that sits on a bf16 rounding boundary becomes a bf16 ulp (4e-3) in the next projection's
+    operand — so the two schedules agree at the mode's own noise level, and both are equally far from the fp64 oracle."""
+    from test_agent_gpu import make_agent
+    ag, pa, _ = make_agent(2)
+    par = M.ALL["3d_walker_7_full"]
+    g = G.build_graph(par, device="cuda")
+    ag.change_morphology(g)
+    obs = synth.make_obs(8192, len(par), seed=21).cuda()              # 57 344 tokens: 448 row tiles
+    with torch.no_grad():
+        got = ag.actor(obs).clone()
+        monkeypatch.setenv("SGRL_TC_PERSIST", "0")
+        want = ag.actor(obs).clone()
+        ref = O.actor_forward({k: v.cuda() for k, v in pa.items()}, obs, g)
+    e_pt, e_p, e_t = parity.rel_err(got, want), parity.rel_err(got, ref), parity.rel_err(want, ref)
+    print(f"  BF16-input mode at 57k tokens: persistent vs per-tile {e_pt:.2e}; vs the oracle: persistent {e_p:.2e}, per-tile {e_t:.2e}")
+    assert e_pt < 5e-3
+    assert e_p < 2e-2 and e_t < 2e-2 and e_p < 1.5 * e_t + 1e-3
