@@ -64,6 +64,17 @@ def test_error_reporting_without_gpu():
     assert _lib.lib.sgrl_ws_floats(3, 900) > 0
 
 
+def test_deterministic_mode_switch_without_gpu():
+    """sgrl_deterministic(enable): 1 / 0 switch the mode, -1 only queries; each call returns the previous state (no GPU work)."""
+    from sgrl_b200 import _lib
+    lib = _lib.lib
+    prev = lib.sgrl_deterministic(-1)
+    assert prev in (0, 1)
+    assert lib.sgrl_deterministic(1) == prev and lib.sgrl_deterministic(-1) == 1
+    assert lib.sgrl_deterministic(0) == 1 and lib.sgrl_deterministic(-1) == 0
+    lib.sgrl_deterministic(prev)
+
+
 def test_modules_build_on_cpu_with_reference_state_dict_keys():
     import torch
     from oracle import ref_loader
