@@ -146,16 +146,17 @@ def _arena_grads(mod):
     return {names[id(p)]: (ga[a:a + n].view(p.shape) if a < live else None) for p, a, n in mod._slots}
 
 
-def test_replayed_graph_gradients_equal_eager_gradients():
+@pytest.mark.parametrize("B", [100, 256])
+def test_replayed_graph_gradients_equal_eager_gradients(B):
     """Race detector for the captured update: two agents with identical state take the same eight steps (humanoid-9,
-    B=100, the size where a cross-stream ordering hazard once showed), one replaying the captured CUDA graphs
+    B=100, the size where a cross-stream ordering hazard once showed, and B=256, the benched size), one replaying the captured CUDA graphs
     (iterations 2-7), the other running every launch eagerly.  The forward passes are deterministic and the only
     run-to-run freedom in the backward is the order of the split-K atomics (~1e-7), so the raw gradients of both must
     agree far below the parity bar; a forked weight-gradient GEMM reading a half-written dY would not.
 
     (Comparing LATER steps tensor by tensor against an fp64 oracle is not meaningful: of the ~6 M relu evaluations of a
     step a handful have |pre-activation| < 1e-6 of their row scale, and their sign - hence a gradient contribution of up
-    to 1e-2 of one sample - is decided by fp32 summation order; tests/debug_relu_masks.py lists them.  Fresh-weight
+    to 1e-2 of one sample - is decided by fp32 summation order; tools/debug_relu_masks.py lists them.  Fresh-weight
     gradients are checked against the oracle in tests/test_backward_gpu.py.)"""
     ag, _, _ = make_agent()
     eg, _, _ = make_agent()
@@ -163,7 +164,6 @@ def test_replayed_graph_gradients_equal_eager_gradients():
     par = M.ALL["3d_humanoid_9_full"]
     g = G.build_graph(par, device="cuda")
     ag.change_morphology(g); eg.change_morphology(g)
-    B = 100
     for it in range(8):
         # both start every step from bit-identical state (the atomics-order noise of the previous step would otherwise grow,
         # through a relu kink, into a 1e-4 difference within a few steps)
